@@ -1,0 +1,192 @@
+"""Generate the golden fixtures under tests/golden/ from the LIVE reference.
+
+TEST INFRASTRUCTURE.  Run in the build container only (``/root/reference`` does not exist on
+the GPU box):
+
+    python oracle/make_golden.py
+
+It imports the reference's own modules (``yolo_clip_detector.model.heads.*``,
+``yolo_clip_detector.inference.detector``, ``yolo_clip_detector.model.yolo_clip`` with the
+``clip`` stub from ``oracle/clip_stub.py``), runs them on seeded inputs and stores inputs and
+outputs as small ``.npz`` files.  The reference has no tests or golden vectors of its own
+(SURVEY.md section 4), so these files are what pins ``oracle/ref_port.py``.
+"""
+from __future__ import annotations
+
+import logging
+import os
+import sys
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+REF = os.environ.get("OVDET_REFERENCE", "/root/reference")
+OUT = os.path.join(ROOT, "tests", "golden")
+sys.path.insert(0, ROOT)
+sys.path.insert(0, REF)
+
+from oracle import clip_stub  # noqa: E402
+
+clip_stub.install()
+logging.disable(logging.CRITICAL)
+
+from yolo_clip_detector.model.heads.text_contrastive import TextContrastiveHead  # noqa: E402
+from yolo_clip_detector.model.heads.box_head import BoxHead  # noqa: E402
+from yolo_clip_detector.inference.detector import YOLOCLIPDetector  # noqa: E402
+from yolo_clip_detector.model.yolo_clip import YOLOCLIP  # noqa: E402
+
+from ovdet import synth  # noqa: E402
+
+
+def _bare_detector(conf=0.25, iou=0.45, image_size=(640, 640), class_names=None):
+    det = YOLOCLIPDetector.__new__(YOLOCLIPDetector)      # no model / CLIP needed for post-process
+    det.conf_threshold = conf
+    det.iou_threshold = iou
+    det.image_size = image_size
+    det.class_names = class_names
+    return det
+
+
+def save(name, **arrays):
+    path = os.path.join(OUT, name + ".npz")
+    np.savez_compressed(path, **arrays)
+    print(f"{name}: {os.path.getsize(path) / 1024:.1f} KiB")
+
+
+def similarity_cases():
+    torch.manual_seed(11)
+    for name, (b, d, h, w, c, alpha, beta, shared) in {
+        "sim_batched_d512": (2, 512, 5, 4, 7, 1.0, 0.0, False),
+        "sim_shared_affine_d64": (3, 64, 6, 6, 33, 1.3, -0.1, True),
+    }.items():
+        head = TextContrastiveHead(in_channels=8, embed_dim=d, cls_alpha=alpha, cls_beta=beta)
+        obj = torch.randn(b, d, h, w) * 3.0
+        if shared:
+            text = (torch.randn(c, d) * 0.5).unsqueeze(0).expand(b, -1, -1)
+        else:
+            # the neck hands over a [B,C,D] tensor whose batch is NOT the outer memory dim
+            text = torch.randn(c, b, d).transpose(0, 1)
+        with torch.no_grad():
+            sim = head.compute_similarity(obj, text)
+        assert not sim.is_contiguous() and sim.shape == (b, c, h, w)
+        assert sim.stride() == (c * h * w, 1, w * c, c)          # memory is [B,HW,C]
+        save(name, obj=obj.numpy(), text=text.contiguous().numpy(), sim=sim.contiguous().numpy(),
+             alpha=np.float64(alpha), beta=np.float64(beta), strides=np.array(sim.stride()))
+
+
+def decode_case():
+    torch.manual_seed(12)
+    inp = synth.make_inputs(batch=2, image_size=64, num_classes=5, embed_dim=16, seed=5)
+    head = BoxHead(in_channels=[8, 8, 8])
+    grids = [head._create_grid(2, p.shape[2], p.shape[3], s, p.device)
+             for p, s in zip(inp.box_preds, head.strides)]
+    with torch.no_grad():
+        boxes = head.decode_boxes(inp.box_preds, grids)
+    noise = [torch.randn_like(p) * 2.0 for p in inp.box_preds]     # pure-noise logits too
+    with torch.no_grad():
+        boxes_noise = head.decode_boxes(noise, grids)
+    save("decode_3level", p0=inp.box_preds[0].numpy(), p1=inp.box_preds[1].numpy(),
+         p2=inp.box_preds[2].numpy(), boxes=boxes.numpy(),
+         n0=noise[0].numpy(), n1=noise[1].numpy(), n2=noise[2].numpy(), boxes_noise=boxes_noise.numpy(),
+         grid0=grids[0].contiguous().numpy())
+
+
+def nms_cases():
+    rng = np.random.default_rng(13)
+    det = _bare_detector()
+    cases = {}
+
+    def rand_boxes(n, span, size):
+        xy = rng.uniform(0, span, (n, 2)).astype(np.float32)
+        wh = rng.uniform(1, size, (n, 2)).astype(np.float32)
+        return np.concatenate([xy, xy + wh], axis=1).astype(np.float32)
+
+    def distinct_scores(n):
+        return rng.permutation(np.linspace(0.26, 0.99, n)).astype(np.float32)
+
+    cases["uniform300"] = (rand_boxes(300, 600, 120), distinct_scores(300), 0.45)
+    cases["dense1000"] = (rand_boxes(1000, 200, 150), distinct_scores(1000), 0.45)
+    cases["loose_thr"] = (rand_boxes(257, 100, 90), distinct_scores(257), 0.7)
+    cases["tight_thr"] = (rand_boxes(129, 100, 90), distinct_scores(129), 0.05)
+    b = rand_boxes(64, 50, 40)
+    b[10:20] = b[10]                       # exact duplicates
+    b[30:34, 2:] = b[30:34, :2]            # zero-area boxes
+    b[40, [0, 2]] = b[40, [2, 0]]          # inverted box (negative width)
+    cases["degenerate64"] = (b, distinct_scores(64), 0.45)
+    cases["single"] = (rand_boxes(1, 10, 5), distinct_scores(1), 0.45)
+    cases["empty"] = (np.zeros((0, 4), np.float32), np.zeros((0,), np.float32), 0.45)
+    out = {}
+    for name, (boxes, scores, thr) in cases.items():
+        keep = det._nms(boxes.copy(), scores.copy(), thr)
+        out[name + "_boxes"] = boxes
+        out[name + "_scores"] = scores
+        out[name + "_thr"] = np.float64(thr)
+        out[name + "_keep"] = np.asarray(keep, dtype=np.int64)
+        if len(boxes) > 1:
+            out[name + "_iou0"] = det._compute_iou(boxes[0], boxes[1:])
+    # documented tie behaviour: equal scores -> higher index first
+    tie_scores = np.array([.5, .7, .5, .7, .1], np.float32)
+    out["tie_order"] = np.argsort(tie_scores)[::-1].copy()
+    save("nms_cases", **out)
+
+
+def postprocess_case():
+    # synthetic head outputs for B=3 at 128x128 with enough survivors for NMS to matter
+    from oracle import ref_port
+    inp = synth.make_inputs(batch=3, image_size=128, num_classes=40, embed_dim=64, seed=21,
+                            plant_frac=0.08)
+    tail = ref_port.head_tail(inp.obj_embeds, inp.text_batched(), inp.box_preds)
+    names = [f"thing{i}" for i in range(40)]
+    out = {"boxes": tail["boxes"].numpy(), "scores": tail["scores"].numpy(),
+           "class_ids": tail["class_ids"].numpy()}
+    geometry = [((128, 128), 1.0), ((100, 160), 0.8), ((300, 200), 128 / 300)]
+    for i, (orig, scale) in enumerate(geometry):
+        det = _bare_detector(conf=0.25, iou=0.45, image_size=(128, 128), class_names=names)
+        sliced = {k: torch.from_numpy(out[k][i:i + 1].copy()) for k in ("boxes", "scores", "class_ids")}
+        dets = det.postprocess_detections(sliced, orig, scale)
+        out[f"img{i}_orig"] = np.array(orig)
+        out[f"img{i}_scale"] = np.float64(scale)
+        out[f"img{i}_box"] = np.array([d["box"] for d in dets], dtype=np.int64).reshape(-1, 4)
+        out[f"img{i}_score"] = np.array([d["score"] for d in dets], dtype=np.float64)
+        out[f"img{i}_class"] = np.array([d["class_id"] for d in dets], dtype=np.int64)
+        out[f"img{i}_name0"] = np.array(dets[0]["class_name"] if dets else "")
+        print(f"  postprocess img{i}: {len(dets)} detections")
+    save("postprocess_b3", **out)
+
+
+def forward_tail_case():
+    """Full reference YOLOCLIP.forward on a 64x64 image; capture the tensors entering the
+    tail (per-level obj_embed, box_preds, neck text) and the dict leaving it."""
+    torch.manual_seed(14)
+    model = YOLOCLIP(backbone_variant="n", num_classes=6, offline_mode=True).eval()
+    model.offline_vocabulary = torch.randn(6, 512)
+    captured = {"obj": [], "text": None, "box": None}
+    hooks = [h.register_forward_hook(lambda m, i, o: captured["obj"].append(o[0].detach()))
+             for h in model.contrastive_heads]
+    hooks.append(model.neck.register_forward_hook(
+        lambda m, i, o: captured.__setitem__("text", o[1].detach())))
+    hooks.append(model.box_head.register_forward_hook(
+        lambda m, i, o: captured.__setitem__("box", [t.detach() for t in o[0]])))
+    with torch.no_grad():
+        out = model(torch.rand(2, 3, 64, 64))
+    for h in hooks:
+        h.remove()
+    arrays = {f"obj{i}": t.numpy() for i, t in enumerate(captured["obj"])}
+    arrays.update({f"box{i}": t.numpy() for i, t in enumerate(captured["box"])})
+    arrays["text"] = captured["text"].contiguous().numpy()
+    arrays["text_strides"] = np.array(captured["text"].stride())
+    arrays["boxes"] = out["boxes"].numpy()
+    arrays["scores"] = out["scores"].numpy()
+    arrays["class_ids"] = out["class_ids"].numpy()
+    arrays["keys"] = np.array(sorted(out.keys()))
+    save("forward_tail_64", **arrays)
+
+
+if __name__ == "__main__":
+    os.makedirs(OUT, exist_ok=True)
+    similarity_cases()
+    decode_case()
+    nms_cases()
+    postprocess_case()
+    forward_tail_case()
