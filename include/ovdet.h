@@ -1,0 +1,180 @@
+/*
+ * ovdet.h - C ABI of libovdet.so: the B200 (sm_100a) open-vocabulary detection head and
+ * post-processing.  This is the drop-in boundary for the hot path of `yolo_clip_detector`.
+ *
+ * The reference is pure Python (no plugin / operator registry, no FFI); each entry point below
+ * names the reference code it replaces (paths relative to /root/reference/yolo_clip_detector).
+ * INTEGRATION.md shows the ctypes stub a maintainer of the reference would add.
+ *
+ * Conventions
+ *   - every pointer is CALLER-OWNED DEVICE memory (e.g. torch.Tensor.data_ptr()) unless the
+ *     comment says "host"; the library never allocates, frees or keeps device pointers;
+ *   - every function enqueues on `stream` (a cudaStream_t passed as void*) and returns without
+ *     synchronising; the caller has already selected the device;
+ *   - return value: 0 on success, a negative ovdet_status otherwise; nothing throws or aborts;
+ *   - there is NO CPU fallback: on a device that is not compute capability 10.x every compute
+ *     entry returns OVDET_ERR_WRONG_ARCH;
+ *   - strides and pitches are in ELEMENTS, sizes in elements unless named *_bytes.
+ */
+#ifndef OVDET_H_
+#define OVDET_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define OVDET_VERSION 100 /* 0.1.0 */
+
+#if defined(__GNUC__)
+#define OVDET_API __attribute__((visibility("default")))
+#else
+#define OVDET_API
+#endif
+
+typedef enum ovdet_status {
+  OVDET_OK = 0,
+  OVDET_ERR_INVALID_ARG = -1,       /* null pointer, negative size, bad enum */
+  OVDET_ERR_UNSUPPORTED_SHAPE = -2, /* e.g. embed dim not a multiple of 64, > 8 levels */
+  OVDET_ERR_WRONG_ARCH = -3,        /* device is not sm_100 */
+  OVDET_ERR_CUDA = -4,              /* a CUDA call failed; see ovdet_last_cuda_error() */
+  OVDET_ERR_WORKSPACE = -5,         /* workspace too small / misaligned */
+  OVDET_ERR_DRIVER = -6             /* cuTensorMapEncodeTiled unavailable or failed */
+} ovdet_status;
+
+typedef enum ovdet_dtype { OVDET_F32 = 0, OVDET_BF16 = 1 } ovdet_dtype;
+typedef enum ovdet_activation { OVDET_ACT_NONE = 0, OVDET_ACT_SIGMOID = 1 } ovdet_activation;
+
+#define OVDET_MAX_LEVELS 8
+
+OVDET_API int ovdet_version(void);
+OVDET_API const char* ovdet_strerror(int status);
+/* cudaError_t of the most recent failing CUDA call on this thread (0 if none). */
+OVDET_API int ovdet_last_cuda_error(void);
+/* 0 when the current device can run the kernels (compute capability 10.x). */
+OVDET_API int ovdet_check_device(void);
+
+/* ------------------------------------------------------------------------------------------
+ * K1a  L2 norm of the per-anchor region embeddings + tensor-core operand.
+ * Replaces: model/heads/text_contrastive.py:134,137  (permute/reshape + F.normalize(p=2,
+ *           eps=1e-12) of obj_embed), for one feature level.
+ *
+ *   x         fp32 [batch, dim, hw]   NCHW as obj_embed_conv emits it; element (b,d,a) at
+ *             x[b*stride_b + d*stride_d + a]; the hw axis must be contiguous.
+ *   operand   bf16 [batch, rows_per_batch, kop]; this level writes rows
+ *             [row_offset, row_offset+hw) of every batch.  kop = dim (split=0) or 2*dim
+ *             (split=1: columns [0,dim) hold hi = bf16(x), [dim,2dim) hold lo = bf16(x - hi)).
+ *             Values are NOT pre-scaled: the 1/norm factor is applied by ovdet_similarity.
+ *   inv_norm  fp32 [batch, rows_per_batch], same row window: 1 / max(||x||_2, 1e-12).
+ * ---------------------------------------------------------------------------------------- */
+OVDET_API int ovdet_l2norm_regions(const float* x, int64_t batch, int64_t dim, int64_t hw,
+                         int64_t stride_b, int64_t stride_d,
+                         void* operand, int64_t rows_per_batch, int64_t row_offset,
+                         int64_t kop, int split, float* inv_norm, void* stream);
+
+/* K1b  L2 norm of the text-prompt embeddings + tensor-core operand.
+ * Replaces: model/heads/text_contrastive.py:138 (F.normalize of text_embed).
+ *
+ *   t         fp32 [batch, classes, dim]; element (b,c,d) at t[b*stride_b + c*stride_c + d].
+ *             Pass batch=1 for a shared vocabulary (stride-0 expand, model/yolo_clip.py:123).
+ *   operand   bf16 [batch, classes, kop], NORMALISED rows t/max(||t||,1e-12); hi/lo as above.
+ *   inv_norm  optional fp32 [batch, classes] (diagnostics), may be NULL.
+ */
+OVDET_API int ovdet_l2norm_text(const float* t, int64_t batch, int64_t classes, int64_t dim,
+                      int64_t stride_b, int64_t stride_c,
+                      void* operand, int64_t kop, int split, float* inv_norm, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * K2  region x text similarity on tcgen05 tensor cores (TMA-staged, TMEM accumulators).
+ * Replaces: model/heads/text_contrastive.py:144,147 (matmul + alpha*s+beta) and, through the
+ *           fused epilogue, model/yolo_clip.py:198-202 (max/argmax over classes).
+ *
+ *   regions_op   bf16 [batch, rows, kop]   from ovdet_l2norm_regions
+ *   text_op      bf16 [text_batch, classes, kop] from ovdet_l2norm_text; text_batch is 1
+ *                (shared) or batch (per-image text, as the neck produces, repvl_pan.py:173-182)
+ *   inv_norm_r   fp32 [batch, rows] row scale; NULL = 1
+ *   logits       optional [batch, rows, ldc] (fp32 or bf16 per logits_dtype), columns
+ *                [0,classes) written: alpha * <a^,t^> + beta.  Memory order [B,HW,C] is what the
+ *                reference's compute_similarity returns a transposed view of
+ *                (text_contrastive.py:150-151).
+ *   row_max      optional fp32 [batch, rows]  max over classes of the logits (before rounding
+ *                to bf16 when logits_dtype is bf16)
+ *   row_arg      optional int32 [batch, rows] argmax, lowest class index on ties
+ *   split        0: one bf16 pass (operand error ~2^-9 relative, |dlogit| <~ 4e-3);
+ *                1: three bf16 passes over hi/lo operands, fp32-class accuracy (~1e-6).
+ *   dim must be a multiple of 64; kop = dim*(1+split).
+ * ---------------------------------------------------------------------------------------- */
+OVDET_API int ovdet_similarity(const void* regions_op, const void* text_op, const float* inv_norm_r,
+                     int64_t batch, int64_t rows, int64_t classes, int64_t dim,
+                     int split, int text_batched, float alpha, float beta,
+                     void* logits, int logits_dtype, int64_t ldc,
+                     float* row_max, int32_t* row_arg, void* stream);
+
+/* K2b  max/argmax over classes of materialised logits (any producer).
+ * Replaces: model/yolo_clip.py:198-202 (similarity.max(dim=1)); ties -> lowest class index.
+ *   logits [rows, ldc] fp32 or bf16, columns [0,classes) are read. */
+OVDET_API int ovdet_rowmax(const void* logits, int logits_dtype, int64_t rows, int64_t classes, int64_t ldc,
+                 float* row_max, int32_t* row_arg, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * K3  DFL box decode for all levels + score activation + confidence threshold.
+ * Replaces: model/heads/box_head.py:150-218 (decode_boxes; grid of :115-148 is implicit),
+ *           inference/detector.py:184 (scores > conf).
+ *
+ *   box_preds    HOST array of num_levels device pointers, level l is fp32
+ *                [batch, 4*bins, heights[l], widths[l]] with batch stride batch_strides[l]
+ *                (channel stride heights[l]*widths[l], spatial contiguous)
+ *   heights/widths/strides/batch_strides  HOST arrays of num_levels entries
+ *   scores       optional fp32 [batch, anchors] (anchors = sum h*w, levels concatenated in
+ *                order, row-major inside a level - model/yolo_clip.py:205)
+ *   boxes        fp32 [batch, anchors, 4] xyxy, centre/size decode of the reference:
+ *                c = (cell + E[xy]) * stride, wh = exp(E[wh]) * stride * {width,height}_scale
+ *   scores_act   optional fp32 [batch, anchors]: activation(scores) (needed for sigmoid)
+ *   pass_mask    optional uint32 [batch, ceil(anchors/32)]: bit a%32 of word a/32 set iff
+ *                activation(score[a]) > conf   (strict, NaN never passes)
+ * ---------------------------------------------------------------------------------------- */
+OVDET_API int ovdet_decode_filter(const float* const* box_preds, const int32_t* heights,
+                        const int32_t* widths, const int32_t* strides,
+                        const int64_t* batch_strides, int num_levels, int bins,
+                        int64_t batch, float width_scale, float height_scale,
+                        const float* scores, float conf, int activation,
+                        float* boxes, float* scores_act, uint32_t* pass_mask, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * K4  per-image candidate gather, rescale/clip, sort, greedy NMS.
+ * Replaces: inference/detector.py:185-208 (mask, boxes/scale, clip, _nms :225-256,
+ *           _compute_iou :258-287) for EVERY image of the batch (the reference handles image 0).
+ *
+ *   boxes [batch, anchors, 4], scores [batch, anchors], classes (optional int32 [batch,anchors])
+ *   pass_mask  optional (NULL = every anchor is a candidate)
+ *   scale      optional fp32 [batch]: boxes are divided by it (IEEE division); NULL = 1
+ *   clip_wh    optional fp32 [batch, 2] = (orig_w, orig_h): x clipped to [0,w], y to [0,h]
+ *   iou_thr    a candidate is dropped when NOT (iou <= iou_thr) against a kept one, with
+ *              iou = inter / (area_a + area_b - inter + 1e-7f) in float32, no FMA contraction
+ *   class_aware 0 = class-agnostic (reference); 1 = only same-class boxes suppress each other
+ *   topk       0 = all candidates (reference); K = keep the K best (score desc, index desc)
+ *              candidates before NMS
+ *   max_det    capacity of the per-image output rows
+ * Outputs (per image, in kept order = score desc, ties: higher anchor index first):
+ *   out_boxes [batch,max_det,4] rescaled+clipped, out_scores, out_classes (optional),
+ *   out_anchor int32 (anchor index), out_keep int32 (index into the thresholded array - what
+ *   the reference's _nms returns), out_count int32 [batch] (kept, <= max_det),
+ *   out_candidates optional int32 [batch] (number that passed the threshold)
+ *   workspace: ovdet_nms_workspace_bytes(batch, anchors) bytes, 16-byte aligned.
+ * ---------------------------------------------------------------------------------------- */
+OVDET_API size_t ovdet_nms_workspace_bytes(int64_t batch, int64_t anchors);
+OVDET_API int ovdet_nms_batched(const float* boxes, const float* scores, const int32_t* classes,
+                      const uint32_t* pass_mask, int64_t batch, int64_t anchors,
+                      const float* scale, const float* clip_wh,
+                      float iou_thr, int class_aware, int topk, int64_t max_det,
+                      float* out_boxes, float* out_scores, int32_t* out_classes,
+                      int32_t* out_anchor, int32_t* out_keep, int32_t* out_count,
+                      int32_t* out_candidates, void* workspace, size_t workspace_bytes,
+                      void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* OVDET_H_ */

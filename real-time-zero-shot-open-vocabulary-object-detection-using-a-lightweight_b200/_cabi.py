@@ -1,0 +1,77 @@
+"""ctypes binding of ``libovdet.so`` - the C ABI declared in ``include/ovdet.h``.
+
+The library is the product: there is no CPU or PyTorch fallback.  ``lib()`` raises when the
+shared object is missing, and every compute entry returns ``OVDET_ERR_WRONG_ARCH`` on a device
+that is not compute capability 10.x; ``check()`` turns any non-zero status into ``RuntimeError``.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+from ctypes import POINTER, c_char_p, c_float, c_int, c_int32, c_int64, c_size_t, c_uint32, c_void_p
+
+PKG_DIR = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(PKG_DIR, "libovdet.so")
+
+OVDET_F32, OVDET_BF16 = 0, 1
+ACT_NONE, ACT_SIGMOID = 0, 1
+MAX_LEVELS = 8
+
+# name -> (restype, argtypes); mirrors include/ovdet.h one to one
+PROTOTYPES = {
+    "ovdet_version": (c_int, []),
+    "ovdet_strerror": (c_char_p, [c_int]),
+    "ovdet_last_cuda_error": (c_int, []),
+    "ovdet_check_device": (c_int, []),
+    "ovdet_l2norm_regions": (c_int, [c_void_p, c_int64, c_int64, c_int64, c_int64, c_int64,
+                                     c_void_p, c_int64, c_int64, c_int64, c_int, c_void_p, c_void_p]),
+    "ovdet_l2norm_text": (c_int, [c_void_p, c_int64, c_int64, c_int64, c_int64, c_int64,
+                                  c_void_p, c_int64, c_int, c_void_p, c_void_p]),
+    "ovdet_similarity": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int64, c_int64,
+                                 c_int, c_int, c_float, c_float, c_void_p, c_int, c_int64,
+                                 c_void_p, c_void_p, c_void_p]),
+    "ovdet_rowmax": (c_int, [c_void_p, c_int, c_int64, c_int64, c_int64, c_void_p, c_void_p, c_void_p]),
+    "ovdet_decode_filter": (c_int, [POINTER(c_void_p), POINTER(c_int32), POINTER(c_int32),
+                                    POINTER(c_int32), POINTER(c_int64), c_int, c_int, c_int64,
+                                    c_float, c_float, c_void_p, c_float, c_int,
+                                    c_void_p, c_void_p, c_void_p, c_void_p]),
+    "ovdet_nms_workspace_bytes": (c_size_t, [c_int64, c_int64]),
+    "ovdet_nms_batched": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int64,
+                                  c_void_p, c_void_p, c_float, c_int, c_int, c_int64,
+                                  c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+                                  c_void_p, c_void_p, c_size_t, c_void_p]),
+}
+
+_lib = None
+
+
+def lib() -> ctypes.CDLL:
+    """Load (once) and return the library; raise loudly when it has not been built."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError(
+                f"{LIB_PATH} is missing: build it with `python -m ovdet.build` (nvcc, sm_100a). "
+                "ovdet has no CPU/PyTorch fallback.")
+        handle = ctypes.CDLL(LIB_PATH)
+        for name, (restype, argtypes) in PROTOTYPES.items():
+            fn = getattr(handle, name)        # AttributeError if the ABI drifted
+            fn.restype = restype
+            fn.argtypes = argtypes
+        _lib = handle
+    return _lib
+
+
+class OvdetError(RuntimeError):
+    def __init__(self, status: int, where: str):
+        handle = lib()
+        msg = handle.ovdet_strerror(status).decode()
+        if status == -4:
+            msg += f" [cudaError {handle.ovdet_last_cuda_error()}]"
+        super().__init__(f"{where}: {msg} (status {status})")
+        self.status = status
+
+
+def check(status: int, where: str) -> None:
+    if status != 0:
+        raise OvdetError(status, where)

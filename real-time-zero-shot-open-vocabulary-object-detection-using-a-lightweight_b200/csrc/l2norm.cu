@@ -1,0 +1,182 @@
+// K1: L2 normalisation + bf16 tensor-core operand construction.
+//
+// Replaces the permute + F.normalize pair of the reference
+// (model/heads/text_contrastive.py:134,137-138).  HBM-bound streaming kernels:
+//   regions: read  fp32 [B, D, HW] (NCHW, HW contiguous)           4 B / element
+//            write bf16 [B, A, D]  (anchor-major = K-major operand) 2 B / element (4 B split)
+//            write fp32 inv_norm [B, A]
+//   text:    one warp per prompt row, normalised before rounding.
+#include "common.cuh"
+
+namespace ovdet {
+
+// ---------------------------------------------------------------------------------------------
+// Regions.  One CTA owns ANCH consecutive anchors of one image and walks the whole embedding
+// dimension.  Global reads are coalesced along HW (each warp instruction covers one or two
+// 128 B lines); the transpose to anchor-major happens in shared memory with a 16 B-chunk XOR
+// swizzle (chunk ^ (anchor & 7)) so that both the column-wise fill and the row-wise drain are
+// bank-conflict free; global writes are 16 B per lane, 512 B contiguous per warp instruction.
+// ---------------------------------------------------------------------------------------------
+template <int ANCH, bool SPLIT>
+__global__ void __launch_bounds__(256)
+l2norm_regions_kernel(const float* __restrict__ x, int dim, int hw, int64_t stride_b,
+                      int64_t stride_d, __nv_bfloat16* __restrict__ operand,
+                      int64_t rows_per_batch, int64_t row_offset, int kop,
+                      float* __restrict__ inv_norm) {
+  constexpr int APL = ANCH / 32;            // anchors per lane
+  constexpr int WARPS = 8;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int chunks = dim >> 3;              // 16-byte chunks per operand row
+  uint4* tile_hi = reinterpret_cast<uint4*>(smem_raw);
+  uint4* tile_lo = tile_hi + (SPLIT ? ANCH * chunks : 0);
+  float* partial = reinterpret_cast<float*>(tile_hi + (SPLIT ? 2 : 1) * ANCH * chunks);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int a0 = blockIdx.x * ANCH;
+  const int b = blockIdx.y;
+  const float* xb = x + b * stride_b;
+
+  float ss[APL];
+#pragma unroll
+  for (int j = 0; j < APL; ++j) ss[j] = 0.f;
+
+  for (int g = warp; g < chunks; g += WARPS) {
+    float v[APL][8];
+#pragma unroll
+    for (int r = 0; r < 8; ++r) {
+      const float* row = xb + (int64_t)(g * 8 + r) * stride_d + a0;
+#pragma unroll
+      for (int j = 0; j < APL; ++j) {
+        const int a = lane + 32 * j;
+        v[j][r] = (a0 + a < hw) ? ld_stream_f32(row + a) : 0.f;
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < APL; ++j) {
+      const int a = lane + 32 * j;
+      uint32_t hi[4], lo[4];
+#pragma unroll
+      for (int r = 0; r < 8; r += 2) {
+        const float f0 = v[j][r], f1 = v[j][r + 1];
+        ss[j] = fmaf(f0, f0, ss[j]);
+        ss[j] = fmaf(f1, f1, ss[j]);
+        const __nv_bfloat16 h0 = __float2bfloat16_rn(f0), h1 = __float2bfloat16_rn(f1);
+        hi[r >> 1] = (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
+        if (SPLIT) lo[r >> 1] = pack_bf16x2(f0 - __bfloat162float(h0), f1 - __bfloat162float(h1));
+      }
+      const int slot = a * chunks + (g ^ (a & 7));
+      tile_hi[slot] = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+      if (SPLIT) tile_lo[slot] = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < APL; ++j) partial[warp * ANCH + lane + 32 * j] = ss[j];
+  __syncthreads();
+
+  if (threadIdx.x < ANCH) {
+    float s = 0.f;
+#pragma unroll
+    for (int w = 0; w < WARPS; ++w) s += partial[w * ANCH + threadIdx.x];
+    const int a = a0 + threadIdx.x;
+    if (a < hw)
+      inv_norm[b * rows_per_batch + row_offset + a] = 1.0f / fmaxf(sqrtf(s), 1e-12f);
+  }
+
+  for (int a = warp; a < ANCH; a += WARPS) {
+    if (a0 + a >= hw) break;
+    uint4* dst = reinterpret_cast<uint4*>(operand + (b * rows_per_batch + row_offset + a0 + a) * kop);
+    for (int c = lane; c < chunks; c += 32) {
+      const int slot = a * chunks + (c ^ (a & 7));
+      dst[c] = tile_hi[slot];
+      if (SPLIT) dst[chunks + c] = tile_lo[slot];
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Text.  One warp per prompt; rows are tiny (D floats) so the second pass re-reads L1/L2.
+// ---------------------------------------------------------------------------------------------
+template <bool SPLIT>
+__global__ void __launch_bounds__(256)
+l2norm_text_kernel(const float* __restrict__ t, int64_t total_rows, int classes, int dim,
+                   int64_t stride_b, int64_t stride_c, __nv_bfloat16* __restrict__ operand,
+                   int kop, float* __restrict__ inv_norm) {
+  const int64_t row = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (row >= total_rows) return;
+  const int64_t b = row / classes, c = row % classes;
+  const float* src = t + b * stride_b + c * stride_c;
+  float ss = 0.f;
+  for (int i = lane; i < dim; i += 32) { const float f = src[i]; ss = fmaf(f, f, ss); }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
+  const float denom = fmaxf(sqrtf(ss), 1e-12f);
+  if (inv_norm != nullptr && lane == 0) inv_norm[row] = 1.0f / denom;
+  __nv_bfloat16* dst = operand + row * kop;
+  for (int i = lane; i < dim; i += 32) {
+    const float f = __fdiv_rn(src[i], denom);
+    const __nv_bfloat16 h = __float2bfloat16_rn(f);
+    dst[i] = h;
+    if (SPLIT) dst[dim + i] = __float2bfloat16_rn(f - __bfloat162float(h));
+  }
+}
+
+template <int ANCH, bool SPLIT>
+static int launch_regions(const float* x, int64_t batch, int dim, int hw, int64_t stride_b,
+                          int64_t stride_d, __nv_bfloat16* operand, int64_t rows_per_batch,
+                          int64_t row_offset, int kop, float* inv_norm, cudaStream_t stream) {
+  const size_t smem = (size_t)ANCH * dim * 2 * (SPLIT ? 2 : 1) + 8 * ANCH * sizeof(float);
+  if (smem > 227 * 1024) return OVDET_ERR_UNSUPPORTED_SHAPE;
+  auto kern = l2norm_regions_kernel<ANCH, SPLIT>;
+  OVDET_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  dim3 grid((unsigned)ceil_div<int64_t>(hw, ANCH), (unsigned)batch);
+  kern<<<grid, 256, smem, stream>>>(x, dim, hw, stride_b, stride_d, operand, rows_per_batch,
+                                    row_offset, kop, inv_norm);
+  OVDET_LAUNCH_CHECK();
+  return OVDET_OK;
+}
+
+}  // namespace ovdet
+
+extern "C" int ovdet_l2norm_regions(const float* x, int64_t batch, int64_t dim, int64_t hw,
+                                    int64_t stride_b, int64_t stride_d, void* operand,
+                                    int64_t rows_per_batch, int64_t row_offset, int64_t kop,
+                                    int split, float* inv_norm, void* stream) {
+  using namespace ovdet;
+  if (!x || !operand || !inv_norm || batch < 0 || dim <= 0 || hw < 0) return OVDET_ERR_INVALID_ARG;
+  if (row_offset < 0 || row_offset + hw > rows_per_batch) return OVDET_ERR_INVALID_ARG;
+  if (dim % 64 != 0 || batch > 65535) return OVDET_ERR_UNSUPPORTED_SHAPE;
+  if (kop != dim * (split ? 2 : 1)) return OVDET_ERR_INVALID_ARG;
+  if ((reinterpret_cast<uintptr_t>(operand) & 15) != 0) return OVDET_ERR_INVALID_ARG;
+  if (int rc = check_device()) return rc;
+  if (batch == 0 || hw == 0) return OVDET_OK;
+  auto* op = static_cast<__nv_bfloat16*>(operand);
+  cudaStream_t s = as_stream(stream);
+  if (split)
+    return launch_regions<32, true>(x, batch, (int)dim, (int)hw, stride_b, stride_d, op,
+                                    rows_per_batch, row_offset, (int)kop, inv_norm, s);
+  return launch_regions<64, false>(x, batch, (int)dim, (int)hw, stride_b, stride_d, op,
+                                   rows_per_batch, row_offset, (int)kop, inv_norm, s);
+}
+
+extern "C" int ovdet_l2norm_text(const float* t, int64_t batch, int64_t classes, int64_t dim,
+                                 int64_t stride_b, int64_t stride_c, void* operand, int64_t kop,
+                                 int split, float* inv_norm, void* stream) {
+  using namespace ovdet;
+  if (!t || !operand || batch < 0 || classes < 0 || dim <= 0) return OVDET_ERR_INVALID_ARG;
+  if (dim % 64 != 0) return OVDET_ERR_UNSUPPORTED_SHAPE;
+  if (kop != dim * (split ? 2 : 1)) return OVDET_ERR_INVALID_ARG;
+  if (int rc = check_device()) return rc;
+  const int64_t total = batch * classes;
+  if (total == 0) return OVDET_OK;
+  auto* op = static_cast<__nv_bfloat16*>(operand);
+  const unsigned grid = (unsigned)ceil_div<int64_t>(total, 8);
+  if (split)
+    l2norm_text_kernel<true><<<grid, 256, 0, as_stream(stream)>>>(t, total, (int)classes, (int)dim,
+                                                                  stride_b, stride_c, op, (int)kop, inv_norm);
+  else
+    l2norm_text_kernel<false><<<grid, 256, 0, as_stream(stream)>>>(t, total, (int)classes, (int)dim,
+                                                                   stride_b, stride_c, op, (int)kop, inv_norm);
+  OVDET_LAUNCH_CHECK();
+  return OVDET_OK;
+}

@@ -1,0 +1,423 @@
+// K4: per-image candidate gather, rescale/clip, total-order sort, optional top-k and greedy NMS.
+//
+// Replaces the host numpy tail of the reference, inference/detector.py:185-208: the boolean
+// mask gather (:185-187), boxes / scale_factor (:193-196), np.clip to the original size
+// (:199-202), `_nms` (:225-256: argsort(scores)[::-1], greedy, keep iou <= thr) and
+// `_compute_iou` (:258-287: float32, +1e-7 on the union) - for every image of the batch, where
+// the reference handles image 0 only.
+//
+// One CTA per image, four phases separated by block barriers:
+//   1. gather   pass-mask words -> 64-bit keys (ordered(score) << 32 | anchor) in the workspace
+//   2. sort     bitonic, descending; 4096-key blocks in shared memory, larger merge steps in the
+//               (L2-resident) workspace.  Keys are pairwise distinct, so the order is the total
+//               order (score desc, anchor index desc) == np.argsort(kind='stable')[::-1]
+//   3. select   optional top-k truncation; bitmask of the selected anchors + prefix popcounts so
+//               that every survivor knows its index in the thresholded array (what `_nms` returns)
+//   4. nms      chunks of 512 sorted candidates: boxes gathered / rescaled / clipped into shared
+//               memory, a 512 x 512 suppression bitmask built with one warp ballot per 32 IoUs
+//               (only tiles on or above the diagonal), one warp resolves the chunk 32 candidates
+//               at a time; later chunks are first tested against the boxes already kept.
+//
+// The float32 IoU follows numpy operation by operation (no FMA contraction, IEEE division).
+#include "common.cuh"
+
+namespace ovdet {
+namespace {
+
+constexpr int NMS_THREADS = 512;
+constexpr int NMS_WARPS = NMS_THREADS / 32;
+constexpr int SORT_CAP = 4096;                 // keys per shared-memory sort block (32 KiB)
+constexpr int CHUNK = 512;                     // candidates per NMS chunk
+constexpr int CHUNK_WORDS = CHUNK / 32;        // 16
+constexpr int NMS_SMEM_BYTES = SORT_CAP * 8 + CHUNK * 16 + 4 * CHUNK * 4 + NMS_THREADS * 4;
+static_assert(CHUNK * CHUNK_WORDS * 4 <= SORT_CAP * 8, "mask must fit in the sort block");
+static_assert(CHUNK == NMS_THREADS, "one thread per chunk candidate");
+
+struct NmsParams {
+  const float* boxes;
+  const float* scores;
+  const int* classes;
+  const uint32_t* pass_mask;
+  int anchors;
+  int words;
+  const float* scale;
+  const float* clip_wh;
+  float iou_thr;
+  int class_aware;
+  int topk;
+  int max_det;
+  float* out_boxes;
+  float* out_scores;
+  int* out_classes;
+  int* out_anchor;
+  int* out_keep;
+  int* out_count;
+  int* out_candidates;
+  unsigned char* ws;
+  size_t ws_per_image;
+  int pow2_cap;                                // next power of two >= anchors (>= 32)
+};
+
+// workspace carve-up of one image (all offsets 16-byte aligned)
+struct WsLayout {
+  size_t keys, kept_boxes, kept_cls, sel, prefix, total;
+  __host__ __device__ WsLayout(int anchors, int words, int pow2_cap) {
+    size_t o = 0;
+    keys = o;        o += (size_t)pow2_cap * 8;
+    kept_boxes = o;  o += (size_t)anchors * 16;
+    kept_cls = o;    o += (((size_t)anchors * 4) + 15) & ~(size_t)15;
+    sel = o;         o += (((size_t)words * 4) + 15) & ~(size_t)15;
+    prefix = o;      o += (((size_t)(words + 1) * 4) + 15) & ~(size_t)15;
+    total = o;
+  }
+};
+
+__device__ __forceinline__ void cmp_swap_desc(unsigned long long& a, unsigned long long& b, bool desc) {
+  // desc: larger key first
+  if ((a < b) == desc) { const unsigned long long t = a; a = b; b = t; }
+}
+
+// bitonic steps j = j_hi, j_hi/2, ..., 1 of merge size k over `len` keys held in shared memory;
+// `base` is the global index of sk[0] (direction depends on the global index).
+__device__ void smem_bitonic_steps(unsigned long long* sk, int len, int base, int k, int j_hi) {
+  for (int j = j_hi; j >= 1; j >>= 1) {
+    for (int t = threadIdx.x; t < (len >> 1); t += NMS_THREADS) {
+      const int i = ((t & ~(j - 1)) << 1) | (t & (j - 1));
+      const int l = i | j;
+      const bool desc = (((base + i) & k) == 0);
+      unsigned long long a = sk[i], b = sk[l];
+      cmp_swap_desc(a, b, desc);
+      sk[i] = a; sk[l] = b;
+    }
+    __syncthreads();
+  }
+}
+
+// descending bitonic sort of keys[0, P) (P a power of two) held in the workspace
+__device__ void sort_keys_desc(unsigned long long* keys, int P, unsigned long long* sk) {
+  const int blk = P < SORT_CAP ? P : SORT_CAP;
+  // phase A: every block fully sorted (direction alternates with the global index)
+  for (int base = 0; base < P; base += blk) {
+    for (int i = threadIdx.x; i < blk; i += NMS_THREADS) sk[i] = keys[base + i];
+    __syncthreads();
+    for (int k = 2; k <= blk; k <<= 1) smem_bitonic_steps(sk, blk, base, k, k >> 1);
+    for (int i = threadIdx.x; i < blk; i += NMS_THREADS) keys[base + i] = sk[i];
+    __syncthreads();
+  }
+  // phase B: merges wider than one block: wide steps in the workspace, the rest in smem
+  for (int k = blk << 1; k <= P; k <<= 1) {
+    for (int j = k >> 1; j >= blk; j >>= 1) {
+      for (int t = threadIdx.x; t < (P >> 1); t += NMS_THREADS) {
+        const int i = ((t & ~(j - 1)) << 1) | (t & (j - 1));
+        const int l = i | j;
+        unsigned long long a = keys[i], b = keys[l];
+        const bool desc = ((i & k) == 0);
+        if ((a < b) == desc) { keys[i] = b; keys[l] = a; }
+      }
+      __syncthreads();
+    }
+    for (int base = 0; base < P; base += blk) {
+      for (int i = threadIdx.x; i < blk; i += NMS_THREADS) sk[i] = keys[base + i];
+      __syncthreads();
+      smem_bitonic_steps(sk, blk, base, k, blk >> 1);
+      for (int i = threadIdx.x; i < blk; i += NMS_THREADS) keys[base + i] = sk[i];
+      __syncthreads();
+    }
+  }
+}
+
+__device__ __forceinline__ float box_area(const float4 b) {
+  return __fmul_rn(__fsub_rn(b.z, b.x), __fsub_rn(b.w, b.y));
+}
+
+// true when `b` must be dropped because of the already kept `a`: NOT (iou <= thr)
+__device__ __forceinline__ bool suppresses(const float4 a, const float area_a, const float4 b,
+                                           const float area_b, const float thr) {
+  const float ix1 = fmaxf(a.x, b.x), iy1 = fmaxf(a.y, b.y);
+  const float ix2 = fminf(a.z, b.z), iy2 = fminf(a.w, b.w);
+  const float iw = fmaxf(0.f, __fsub_rn(ix2, ix1));
+  const float ih = fmaxf(0.f, __fsub_rn(iy2, iy1));
+  const float inter = __fmul_rn(iw, ih);
+  const float uni = __fsub_rn(__fadd_rn(area_a, area_b), inter);
+  const float iou = __fdiv_rn(inter, __fadd_rn(uni, 1e-7f));
+  return !(iou <= thr);
+}
+
+__global__ void __launch_bounds__(NMS_THREADS)
+nms_batched_kernel(const NmsParams p) {
+  // shared memory (dynamic, > 48 KiB in total): the sort block and the suppression mask alias
+  // each other (different phases)
+  extern __shared__ __align__(16) unsigned char s_raw[];
+  unsigned long long* s_big = reinterpret_cast<unsigned long long*>(s_raw);      // 32 KiB
+  float4* s_box = reinterpret_cast<float4*>(s_raw + SORT_CAP * 8);                // 8 KiB
+  float* s_area = reinterpret_cast<float*>(s_box + CHUNK);
+  int* s_cls = reinterpret_cast<int*>(s_area + CHUNK);
+  int* s_anchor = s_cls + CHUNK;
+  int* s_kept_pos = s_anchor + CHUNK;           // positions (inside the chunk) kept by this chunk
+  int* s_scan = s_kept_pos + CHUNK;             // NMS_THREADS entries
+  __shared__ uint32_t s_removed[CHUNK_WORDS];
+  __shared__ int s_count, s_kept_total, s_kept_chunk, s_carry;
+
+  const int b = blockIdx.x;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int A = p.anchors, W = p.words;
+  const WsLayout L(A, W, p.pow2_cap);
+  unsigned char* ws = p.ws + (size_t)b * p.ws_per_image;
+  unsigned long long* keys = reinterpret_cast<unsigned long long*>(ws + L.keys);
+  float4* kept_boxes = reinterpret_cast<float4*>(ws + L.kept_boxes);
+  int* kept_cls = reinterpret_cast<int*>(ws + L.kept_cls);
+  uint32_t* sel = reinterpret_cast<uint32_t*>(ws + L.sel);
+  int* prefix = reinterpret_cast<int*>(ws + L.prefix);
+
+  const float* scores = p.scores + (size_t)b * A;
+  const float4* boxes = reinterpret_cast<const float4*>(p.boxes) + (size_t)b * A;
+  const int* classes = p.classes ? p.classes + (size_t)b * A : nullptr;
+  const uint32_t* pm = p.pass_mask ? p.pass_mask + (size_t)b * W : nullptr;
+
+  if (tid == 0) { s_count = 0; s_kept_total = 0; s_carry = 0; }
+  __syncthreads();
+
+  // ---- 1. gather ---------------------------------------------------------------------------
+  const uint32_t tail_bits = (A & 31) ? ((1u << (A & 31)) - 1u) : 0xffffffffu;
+  for (int w = tid; w < W; w += NMS_THREADS) {
+    uint32_t bits = pm ? pm[w] : 0xffffffffu;
+    if (w == W - 1) bits &= tail_bits;
+    const int c = __popc(bits);
+    if (c) {
+      int slot = atomicAdd(&s_count, c);
+      while (bits) {
+        const int l = __ffs(bits) - 1;
+        bits &= bits - 1;
+        const int a = (w << 5) + l;
+        keys[slot++] = ((unsigned long long)float_to_ordered(scores[a]) << 32) | (unsigned)a;
+      }
+    }
+  }
+  __syncthreads();
+  const int N = s_count;
+  if (p.out_candidates && tid == 0) p.out_candidates[b] = N;
+  if (N == 0) {
+    if (tid == 0) p.out_count[b] = 0;
+    return;
+  }
+  int P = 32;
+  while (P < N) P <<= 1;
+  for (int i = N + tid; i < P; i += NMS_THREADS) keys[i] = 0ull;
+  __syncthreads();
+
+  // ---- 2. sort -----------------------------------------------------------------------------
+  sort_keys_desc(keys, P, s_big);
+
+  // ---- 3. select (top-k) + rank of every selected anchor in the thresholded array ------------
+  const int M = (p.topk > 0 && p.topk < N) ? p.topk : N;
+  for (int w = tid; w < W; w += NMS_THREADS) sel[w] = 0u;
+  __syncthreads();
+  for (int i = tid; i < M; i += NMS_THREADS) {
+    const unsigned a = (unsigned)(keys[i] & 0xffffffffull);
+    atomicOr(&sel[a >> 5], 1u << (a & 31));
+  }
+  __syncthreads();
+  for (int w0 = 0; w0 < W; w0 += NMS_THREADS) {       // exclusive scan of popcounts
+    const int w = w0 + tid;
+    const int c = (w < W) ? __popc(sel[w]) : 0;
+    s_scan[tid] = c;
+    __syncthreads();
+    for (int off = 1; off < NMS_THREADS; off <<= 1) {
+      const int v = (tid >= off) ? s_scan[tid - off] : 0;
+      __syncthreads();
+      s_scan[tid] += v;
+      __syncthreads();
+    }
+    const int carry = s_carry;
+    if (w < W) prefix[w] = carry + s_scan[tid] - c;
+    __syncthreads();
+    if (tid == NMS_THREADS - 1) s_carry = carry + s_scan[tid];
+    __syncthreads();
+  }
+
+  // ---- 4. greedy NMS over the sorted candidates ----------------------------------------------
+  const float scale = p.scale ? p.scale[b] : 1.0f;
+  const bool do_scale = p.scale != nullptr;
+  const bool do_clip = p.clip_wh != nullptr;
+  const float clip_w = do_clip ? p.clip_wh[2 * b] : 0.f;
+  const float clip_h = do_clip ? p.clip_wh[2 * b + 1] : 0.f;
+  const float thr = p.iou_thr;
+  const bool aware = p.class_aware && classes != nullptr;
+  uint32_t* mask = reinterpret_cast<uint32_t*>(s_big);           // [CHUNK][CHUNK_WORDS]
+
+  for (int c0 = 0; c0 < M; c0 += CHUNK) {
+    const int n = min(CHUNK, M - c0);
+    const int kept_before = s_kept_total;
+    if (kept_before >= p.max_det) break;
+    // 4a. load the chunk: gather, rescale, clip
+    float4 mine = make_float4(0.f, 0.f, 0.f, 0.f);
+    float my_area = 0.f;
+    int my_cls = -1;
+    if (tid < n) {
+      const unsigned a = (unsigned)(keys[c0 + tid] & 0xffffffffull);
+      float4 v = boxes[a];
+      if (do_scale) {
+        v.x = __fdiv_rn(v.x, scale); v.y = __fdiv_rn(v.y, scale);
+        v.z = __fdiv_rn(v.z, scale); v.w = __fdiv_rn(v.w, scale);
+      }
+      if (do_clip) {
+        v.x = fminf(fmaxf(v.x, 0.f), clip_w); v.y = fminf(fmaxf(v.y, 0.f), clip_h);
+        v.z = fminf(fmaxf(v.z, 0.f), clip_w); v.w = fminf(fmaxf(v.w, 0.f), clip_h);
+      }
+      mine = v;
+      my_area = box_area(v);
+      my_cls = classes ? classes[a] : 0;
+      s_anchor[tid] = (int)a;
+    }
+    s_box[tid] = mine;
+    s_area[tid] = my_area;
+    s_cls[tid] = my_cls;
+    // 4b. candidates beyond n are born removed; later chunks: test against everything kept
+    bool dead = tid >= n;
+    if (!dead && kept_before > 0) {
+      for (int k = 0; k < kept_before; ++k) {
+        const float4 kb = kept_boxes[k];
+        if (aware && kept_cls[k] != my_cls) continue;
+        if (suppresses(kb, box_area(kb), mine, my_area, thr)) { dead = true; break; }
+      }
+    }
+    const uint32_t dead_bits = __ballot_sync(0xffffffffu, dead);
+    if (lane == 0) s_removed[warp] = dead_bits;
+    __syncthreads();
+    // 4c. suppression bitmask, 32 x 32 tiles on or above the diagonal, one ballot per row
+    const int nblk = (n + 31) >> 5;
+    const int ntiles = nblk * (nblk + 1) / 2;
+    for (int t = warp; t < ntiles; t += NMS_WARPS) {
+      // tile index -> (row block rb <= column block cb)
+      int cb = 0;
+      while ((cb + 1) * (cb + 2) / 2 <= t) ++cb;
+      const int rb = t - cb * (cb + 1) / 2;
+      const int j = (cb << 5) + lane;
+      const float4 bj = s_box[j];
+      const float aj = s_area[j];
+      const int cj = s_cls[j];
+      uint32_t my_word = 0;
+#pragma unroll 4
+      for (int r = 0; r < 32; ++r) {
+        const int i = (rb << 5) + r;
+        const float4 bi = s_box[i];
+        bool sup = (j > i) && suppresses(bi, s_area[i], bj, aj, thr);
+        if (aware) sup = sup && (s_cls[i] == cj);
+        const uint32_t word = __ballot_sync(0xffffffffu, sup);
+        if (lane == r) my_word = word;
+      }
+      mask[((rb << 5) + lane) * CHUNK_WORDS + cb] = my_word;
+    }
+    __syncthreads();
+    // 4d. resolve: warp 0, 32 candidates per step
+    if (warp == 0) {
+      uint32_t removed = (lane < CHUNK_WORDS) ? s_removed[lane] : 0xffffffffu;
+      int kept_chunk = 0;
+      for (int wb = 0; wb < nblk; ++wb) {
+        const uint32_t cur = __shfl_sync(0xffffffffu, removed, wb);
+        uint32_t alive = ~cur;
+        const uint32_t diag = mask[((wb << 5) + lane) * CHUNK_WORDS + wb];
+#pragma unroll
+        for (int r = 0; r < 32; ++r) {
+          const uint32_t d = __shfl_sync(0xffffffffu, diag, r);
+          if ((alive >> r) & 1u) alive &= ~d;
+        }
+        // rows of the kept candidates suppress later blocks
+        if (lane < CHUNK_WORDS && lane > wb) {
+          uint32_t bits = alive;
+          while (bits) {
+            const int r = __ffs(bits) - 1;
+            bits &= bits - 1;
+            removed |= mask[((wb << 5) + r) * CHUNK_WORDS + lane];
+          }
+        }
+        if ((alive >> lane) & 1u)
+          s_kept_pos[kept_chunk + __popc(alive & ((1u << lane) - 1u))] = (wb << 5) + lane;
+        kept_chunk += __popc(alive);
+      }
+      if (lane == 0) s_kept_chunk = kept_chunk;
+    }
+    __syncthreads();
+    // 4e. emit the survivors of this chunk (kept order == score order)
+    const int kept_chunk = s_kept_chunk;
+    for (int e = tid; e < kept_chunk; e += NMS_THREADS) {
+      const int pos = s_kept_pos[e];
+      const int k = kept_before + e;
+      const float4 v = s_box[pos];
+      kept_boxes[k] = v;
+      kept_cls[k] = s_cls[pos];
+      if (k < p.max_det) {
+        const size_t o = (size_t)b * p.max_det + k;
+        const int a = s_anchor[pos];
+        reinterpret_cast<float4*>(p.out_boxes)[o] = v;
+        if (p.out_scores) p.out_scores[o] = scores[a];
+        if (p.out_classes) p.out_classes[o] = classes ? s_cls[pos] : 0;
+        if (p.out_anchor) p.out_anchor[o] = a;
+        if (p.out_keep) p.out_keep[o] = prefix[a >> 5] + __popc(sel[a >> 5] & ((1u << (a & 31)) - 1u));
+      }
+    }
+    __syncthreads();
+    if (tid == 0) s_kept_total = kept_before + kept_chunk;
+    __syncthreads();
+  }
+  if (tid == 0) p.out_count[b] = min(s_kept_total, p.max_det);
+}
+
+int next_pow2_cap(int64_t anchors) {
+  int p = 32;
+  while (p < anchors) p <<= 1;
+  return p;
+}
+
+}  // namespace
+}  // namespace ovdet
+
+extern "C" size_t ovdet_nms_workspace_bytes(int64_t batch, int64_t anchors) {
+  using namespace ovdet;
+  if (batch <= 0 || anchors <= 0 || anchors >= (1ll << 30)) return 0;
+  const WsLayout L((int)anchors, (int)((anchors + 31) / 32), next_pow2_cap(anchors));
+  return (size_t)batch * L.total;
+}
+
+extern "C" int ovdet_nms_batched(const float* boxes, const float* scores, const int32_t* classes,
+                                 const uint32_t* pass_mask, int64_t batch, int64_t anchors,
+                                 const float* scale, const float* clip_wh, float iou_thr,
+                                 int class_aware, int topk, int64_t max_det, float* out_boxes,
+                                 float* out_scores, int32_t* out_classes, int32_t* out_anchor,
+                                 int32_t* out_keep, int32_t* out_count, int32_t* out_candidates,
+                                 void* workspace, size_t workspace_bytes, void* stream) {
+  using namespace ovdet;
+  if (!boxes || !scores || !out_boxes || !out_count || batch < 0 || anchors < 0 || max_det <= 0 || topk < 0)
+    return OVDET_ERR_INVALID_ARG;
+  if (class_aware && !classes) return OVDET_ERR_INVALID_ARG;
+  if (anchors >= (1ll << 30) || max_det >= (1ll << 30) || batch >= (1ll << 31)) return OVDET_ERR_UNSUPPORTED_SHAPE;
+  if (((uintptr_t)boxes & 15) || ((uintptr_t)out_boxes & 15)) return OVDET_ERR_INVALID_ARG;
+  if (int rc = check_device()) return rc;
+  if (batch == 0) return OVDET_OK;
+  if (anchors == 0) {
+    OVDET_CUDA_TRY(cudaMemsetAsync(out_count, 0, sizeof(int32_t) * batch, as_stream(stream)));
+    if (out_candidates) OVDET_CUDA_TRY(cudaMemsetAsync(out_candidates, 0, sizeof(int32_t) * batch, as_stream(stream)));
+    return OVDET_OK;
+  }
+  const size_t need = ovdet_nms_workspace_bytes(batch, anchors);
+  if (!workspace || workspace_bytes < need || ((uintptr_t)workspace & 15)) return OVDET_ERR_WORKSPACE;
+  NmsParams p{};
+  p.boxes = boxes; p.scores = scores; p.classes = classes; p.pass_mask = pass_mask;
+  p.anchors = (int)anchors; p.words = (int)((anchors + 31) / 32);
+  p.scale = scale; p.clip_wh = clip_wh; p.iou_thr = iou_thr;
+  p.class_aware = class_aware; p.topk = topk; p.max_det = (int)max_det;
+  p.out_boxes = out_boxes; p.out_scores = out_scores; p.out_classes = out_classes;
+  p.out_anchor = out_anchor; p.out_keep = out_keep; p.out_count = out_count;
+  p.out_candidates = out_candidates;
+  p.ws = static_cast<unsigned char*>(workspace);
+  p.pow2_cap = next_pow2_cap(anchors);
+  p.ws_per_image = WsLayout(p.anchors, p.words, p.pow2_cap).total;
+  static bool attr_set = false;
+  if (!attr_set) {
+    OVDET_CUDA_TRY(cudaFuncSetAttribute(nms_batched_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, NMS_SMEM_BYTES));
+    attr_set = true;
+  }
+  nms_batched_kernel<<<(unsigned)batch, NMS_THREADS, NMS_SMEM_BYTES, as_stream(stream)>>>(p);
+  OVDET_LAUNCH_CHECK();
+  return OVDET_OK;
+}

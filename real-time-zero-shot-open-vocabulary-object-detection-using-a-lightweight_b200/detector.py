@@ -1,0 +1,210 @@
+"""Post-processing and the predict entry point behind the reference's detector API.
+
+Mirrors ``YOLOCLIPDetector`` (inference/detector.py:14-393) for the part of it that is on the
+hot path: ``postprocess_detections`` (:163-223), ``_nms`` (:225-256) and ``detect``'s
+model-output -> detections step (:310-319).  Image loading, the backbone/neck forward and
+drawing stay with the caller (out of scope).
+
+Every method accepts the host buffers the reference's methods receive (numpy arrays / CPU
+tensors are copied to the device, the kernels run there, results come back) as well as CUDA
+tensors; nothing is computed on the CPU.
+"""
+from __future__ import annotations
+
+from typing import Dict, List, Optional, Sequence, Tuple, Union
+
+import numpy as np
+import torch
+
+from . import ops
+from .pipeline import HeadConfig, HeadPipeline
+
+ArrayLike = Union[np.ndarray, torch.Tensor]
+
+
+def _to_device(x: ArrayLike, device, dtype) -> torch.Tensor:
+    if isinstance(x, np.ndarray):
+        x = torch.from_numpy(np.ascontiguousarray(x))
+    return x.to(device=device, dtype=dtype, non_blocking=True).contiguous()
+
+
+class Detector:
+    """``conf_threshold`` / ``iou_threshold`` / ``image_size`` / ``class_names`` are the four
+    attributes the reference's post-processing reads."""
+
+    def __init__(self, class_names: Optional[Sequence[str]] = None, conf_threshold: float = 0.25,
+                 iou_threshold: float = 0.45, image_size: Tuple[int, int] = (640, 640),
+                 device: str = "cuda:0", config: Optional[HeadConfig] = None):
+        self.class_names = list(class_names) if class_names is not None else None
+        self.conf_threshold = conf_threshold
+        self.iou_threshold = iou_threshold
+        self.image_size = image_size
+        self.device = torch.device(device)
+        self.config = config or HeadConfig(conf_threshold=conf_threshold, iou_threshold=iou_threshold)
+        self._pipelines: Dict[tuple, HeadPipeline] = {}
+        self._vocabulary: Optional[torch.Tensor] = None
+        self._host_state = None
+
+    # ---- reference: YOLOCLIPDetector._nms (detector.py:225-256) ---------------------------
+    def _nms(self, boxes: ArrayLike, scores: ArrayLike, iou_threshold: float) -> List[int]:
+        """Greedy class-agnostic NMS; returns indices into ``boxes`` in descending-score order."""
+        n = int(boxes.shape[0])
+        if n == 0:
+            return []
+        b = _to_device(boxes, self.device, torch.float32).reshape(1, n, 4)
+        s = _to_device(scores, self.device, torch.float32).reshape(1, n)
+        res = ops.nms_batched(b, s, iou_thr=iou_threshold)
+        k = int(res.count[0].item())
+        return res.anchor[0, :k].tolist()
+
+    # ---- batched post-processing on device tensors ----------------------------------------
+    def postprocess_batch(self, outputs: Dict[str, torch.Tensor],
+                          orig_sizes: Sequence[Tuple[int, int]], scale_factors: Sequence[float],
+                          class_aware: bool = False, topk: int = 0, activation: str = "none",
+                          max_det: Optional[int] = None) -> ops.NmsResult:
+        """detector.py:184-208 for every image of ``outputs`` (keys ``boxes`` [B,A,4], ``scores``
+        [B,A], ``class_ids`` [B,A]).  ``orig_sizes`` are (height, width) pairs."""
+        dev = self.device
+        boxes = _to_device(outputs["boxes"], dev, torch.float32)
+        scores = _to_device(outputs["scores"], dev, torch.float32)
+        classes = _to_device(outputs["class_ids"], dev, torch.int32)
+        batch = scores.shape[0]
+        if activation == "sigmoid":
+            scores = torch.sigmoid(scores)
+        mask = _pack_mask(scores > self.conf_threshold)
+        scale = torch.from_numpy(np.asarray([np.float32(s) for s in scale_factors], dtype=np.float32)).to(dev)
+        wh = torch.tensor([[float(w), float(h)] for (h, w) in orig_sizes], dtype=torch.float32, device=dev)
+        assert scale.numel() == batch and wh.shape[0] == batch
+        return ops.nms_batched(boxes, scores, classes, mask, scale=scale, clip_wh=wh,
+                               iou_thr=self.iou_threshold, class_aware=class_aware, topk=topk,
+                               max_det=max_det)
+
+    # ---- reference: YOLOCLIPDetector.postprocess_detections (detector.py:163-223) ----------
+    def postprocess_detections(self, outputs: Dict[str, ArrayLike], orig_size: Tuple[int, int],
+                               scale_factor: float) -> List[Dict]:
+        """Image 0 of the batch only, exactly like the reference; returns its list of dicts
+        (``box`` int-truncated xyxy, ``score``, ``class_id``, ``class_name``)."""
+        first = {k: outputs[k][0:1] for k in ("boxes", "scores", "class_ids")}
+        res = self.postprocess_batch(first, [orig_size], [scale_factor])
+        return self.to_records(res, 0)
+
+    def to_records(self, res: ops.NmsResult, image: int) -> List[Dict]:
+        """detector.py:213-221: the detection dicts of one image."""
+        k = int(res.count[image].item())
+        boxes = res.boxes[image, :k].cpu().numpy()
+        scores = res.scores[image, :k].cpu().numpy()
+        classes = res.classes[image, :k].cpu().numpy()
+        records = []
+        for i in range(k):
+            cid = int(classes[i])
+            name = self.class_names[cid] if self.class_names is not None else f"Class {cid}"
+            records.append({"box": boxes[i].astype(int).tolist(), "score": float(scores[i]),
+                            "class_id": cid, "class_name": name})
+        return records
+
+    # ---- predict: conv outputs -> detections (detect.py:121-125 -> detector.py:310-319) -----
+    def pipeline_for(self, obj_embeds: Sequence[torch.Tensor], num_classes: int,
+                     per_image_text: bool) -> HeadPipeline:
+        shapes = tuple((e.shape[2], e.shape[3]) for e in obj_embeds)
+        key = (obj_embeds[0].shape[0], shapes, num_classes, per_image_text, obj_embeds[0].device)
+        if key not in self._pipelines:
+            self._pipelines[key] = HeadPipeline(key[0], shapes, num_classes, self.config,
+                                                device=obj_embeds[0].device,
+                                                per_image_text=per_image_text)
+        return self._pipelines[key]
+
+    def set_vocabulary(self, text: torch.Tensor) -> None:
+        """Offline vocabulary ``[C, D]`` (model/yolo_clip.py:225-263): kept on the device and
+        normalised once per pipeline instead of once per level per forward."""
+        self._vocabulary = text.to(self.device, torch.float32)
+        for pipe in self._pipelines.values():
+            if not pipe.per_image_text:
+                pipe.set_vocabulary(self._vocabulary)
+
+    def predict_host(self, obj_embeds: Sequence[torch.Tensor], box_preds: Sequence[torch.Tensor],
+                     chunk: int = 32) -> Dict[str, torch.Tensor]:
+        """``predict`` for HOST buffers (pinned CPU tensors, as a serving front-end holds them):
+        the batch is cut into chunks; chunk i+1 is copied host->device on a copy stream while
+        chunk i runs K1..K4 on the compute stream, and each chunk's detections are copied back
+        as soon as its NMS has finished.  Returns pinned host tensors ``boxes [B,max_det,4]``,
+        ``scores``, ``classes`` [B,max_det] and ``count`` [B]; needs ``set_vocabulary`` first."""
+        if self._vocabulary is None:
+            raise RuntimeError("ovdet: predict_host needs set_vocabulary() first")
+        batch = obj_embeds[0].shape[0]
+        chunk = min(chunk, batch)
+        if batch % chunk:
+            raise ValueError("ovdet: batch must be a multiple of the chunk size")
+        key = (batch, chunk, tuple(tuple(e.shape[1:]) for e in obj_embeds))
+        st = self._host_state
+        if st is None or st["key"] != key:
+            dev = self.device
+            shapes = tuple((e.shape[2], e.shape[3]) for e in obj_embeds)
+            pipe = HeadPipeline(chunk, shapes, self._vocabulary.shape[0], self.config, device=dev)
+            pipe.set_vocabulary(self._vocabulary)
+            md = pipe.max_det
+            st = {
+                "key": key, "pipe": pipe,
+                "copy": torch.cuda.Stream(dev), "compute": torch.cuda.Stream(dev),
+                "stage": [([torch.empty((chunk,) + tuple(e.shape[1:]), device=dev) for e in obj_embeds],
+                           [torch.empty((chunk,) + tuple(p.shape[1:]), device=dev) for p in box_preds])
+                          for _ in range(2)],
+                "out": {"boxes": torch.empty(batch, md, 4).pin_memory(),
+                        "scores": torch.empty(batch, md).pin_memory(),
+                        "classes": torch.empty(batch, md, dtype=torch.int32).pin_memory(),
+                        "count": torch.empty(batch, dtype=torch.int32).pin_memory()},
+            }
+            self._host_state = st
+        pipe, out = st["pipe"], st["out"]
+        copy_s, comp_s = st["copy"], st["compute"]
+        cur = torch.cuda.current_stream(self.device)
+        copy_s.wait_stream(cur)
+        comp_s.wait_stream(cur)
+        freed = [None, None]
+        for i in range(batch // chunk):
+            lo, hi = i * chunk, (i + 1) * chunk
+            objs, boxes = st["stage"][i & 1]
+            with torch.cuda.stream(copy_s):
+                if freed[i & 1] is not None:
+                    copy_s.wait_event(freed[i & 1])
+                for dst, src in zip(objs + boxes, list(obj_embeds) + list(box_preds)):
+                    dst.copy_(src[lo:hi], non_blocking=True)
+                copied = torch.cuda.Event()
+                copied.record(copy_s)
+            with torch.cuda.stream(comp_s):
+                comp_s.wait_event(copied)
+                res = pipe.run(objs, boxes)
+                done = torch.cuda.Event()
+                done.record(comp_s)
+                freed[i & 1] = done
+                out["boxes"][lo:hi].copy_(res.boxes, non_blocking=True)
+                out["scores"][lo:hi].copy_(res.scores, non_blocking=True)
+                out["classes"][lo:hi].copy_(res.classes, non_blocking=True)
+                out["count"][lo:hi].copy_(res.count, non_blocking=True)
+        cur.wait_stream(comp_s)
+        comp_s.synchronize()
+        return out
+
+    def predict(self, obj_embeds: Sequence[torch.Tensor], box_preds: Sequence[torch.Tensor],
+                text_embeddings: torch.Tensor, orig_sizes: Optional[Sequence[Tuple[int, int]]] = None,
+                scale_factors: Optional[Sequence[float]] = None) -> ops.NmsResult:
+        """Per-level ``obj_embed [B,D,H,W]`` / ``box_preds [B,4R,H,W]`` (what the head
+        convolutions emit) and text embeddings ``[C,D]`` or ``[B,C,D]`` -> per-image kept
+        boxes / scores / classes, every image of the batch."""
+        per_image = not ops.shared_text(text_embeddings)
+        pipe = self.pipeline_for(obj_embeds, text_embeddings.shape[-2], per_image)
+        if orig_sizes is not None:
+            pipe.set_geometry(orig_sizes, scale_factors if scale_factors is not None
+                              else [1.0] * len(orig_sizes))
+        return pipe.run(obj_embeds, box_preds, text_embeddings)
+
+
+def _pack_mask(passed: torch.Tensor) -> torch.Tensor:
+    """bool [B, A] -> int32 bit mask [B, ceil(A/32)] (bit a%32 of word a/32)."""
+    b, a = passed.shape
+    words = (a + 31) // 32
+    padded = torch.zeros(b, words * 32, dtype=torch.int64, device=passed.device)
+    padded[:, :a] = passed
+    weights = (1 << torch.arange(32, device=passed.device, dtype=torch.int64))
+    packed = (padded.view(b, words, 32) * weights).sum(-1)
+    packed = torch.where(packed >= 2 ** 31, packed - 2 ** 32, packed)
+    return packed.to(torch.int32).contiguous()

@@ -1,0 +1,280 @@
+"""Tensor-level wrappers over the C ABI (include/ovdet.h): one function per kernel family.
+
+Every function enqueues on torch's current stream of the input's device and returns without a
+host synchronisation.  Inputs must live on a CUDA device; there is no CPU path.
+"""
+from __future__ import annotations
+
+import ctypes
+from typing import List, Optional, Sequence, Tuple
+
+import torch
+
+from . import _cabi
+from ._cabi import check, lib
+
+
+def _ptr(t: Optional[torch.Tensor]):
+    return None if t is None else t.data_ptr()
+
+
+def _stream(t: torch.Tensor):
+    return torch.cuda.current_stream(t.device).cuda_stream
+
+
+def _require_cuda(t: torch.Tensor, name: str, dtype=None):
+    if not t.is_cuda:
+        raise RuntimeError(f"ovdet: `{name}` must be a CUDA tensor (no CPU fallback exists)")
+    if dtype is not None and t.dtype != dtype:
+        raise TypeError(f"ovdet: `{name}` must be {dtype}, got {t.dtype}")
+
+
+# --------------------------------------------------------------------------------------------
+# K1: L2 norm + tensor-core operands
+# --------------------------------------------------------------------------------------------
+def l2norm_regions(obj_embeds: Sequence[torch.Tensor], split: bool = False,
+                   operand: Optional[torch.Tensor] = None,
+                   inv_norm: Optional[torch.Tensor] = None) -> Tuple[torch.Tensor, torch.Tensor]:
+    """text_contrastive.py:134,137 for all levels at once.
+
+    obj_embeds: per level fp32 ``[B, D, H, W]`` (NCHW).  Returns the bf16 operand
+    ``[B, A, D * (2 if split else 1)]`` (A = sum H*W, levels concatenated P3|P4|P5 as
+    yolo_clip.py:205 does) and ``inv_norm [B, A]`` = 1 / max(||x||, 1e-12).
+    """
+    first = obj_embeds[0]
+    _require_cuda(first, "obj_embed", torch.float32)
+    batch, dim = first.shape[0], first.shape[1]
+    anchors = sum(e.shape[2] * e.shape[3] for e in obj_embeds)
+    kop = dim * (2 if split else 1)
+    if operand is None:
+        operand = torch.empty(batch, anchors, kop, device=first.device, dtype=torch.bfloat16)
+    if inv_norm is None:
+        inv_norm = torch.empty(batch, anchors, device=first.device, dtype=torch.float32)
+    assert operand.shape == (batch, anchors, kop) and operand.is_contiguous()
+    assert inv_norm.shape == (batch, anchors) and inv_norm.is_contiguous()
+    handle = lib()
+    offset = 0
+    with torch.cuda.device(first.device):
+        for e in obj_embeds:
+            _require_cuda(e, "obj_embed", torch.float32)
+            b, d, h, w = e.shape
+            assert b == batch and d == dim
+            if e.stride(3) != 1 or e.stride(2) != w:
+                e = e.contiguous()
+            check(handle.ovdet_l2norm_regions(e.data_ptr(), b, d, h * w, e.stride(0), e.stride(1),
+                                              operand.data_ptr(), anchors, offset, kop, int(split),
+                                              inv_norm.data_ptr(), _stream(e)),
+                  "ovdet_l2norm_regions")
+            offset += h * w
+    return operand, inv_norm
+
+
+def shared_text(text: torch.Tensor) -> bool:
+    """True when one vocabulary serves the whole batch: a ``[C, D]`` tensor, batch 1, or the
+    stride-0 ``expand`` the offline-vocabulary path builds (model/yolo_clip.py:123)."""
+    return text.dim() == 2 or text.shape[0] == 1 or text.stride(0) == 0
+
+
+def l2norm_text(text: torch.Tensor, split: bool = False,
+                operand: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """text_contrastive.py:138.  ``text`` is ``[C, D]`` or ``[B, C, D]`` (any batch / row stride,
+    as the neck emits it); a shared vocabulary is normalised once.  Returns the normalised
+    bf16 operand ``[Bt, C, kop]`` with Bt = 1 for a shared vocabulary."""
+    _require_cuda(text, "text_embed", torch.float32)
+    if text.dim() == 2:
+        text = text.unsqueeze(0)
+    elif shared_text(text):
+        text = text[:1]
+    if text.stride(2) != 1:
+        text = text.contiguous()
+    bt, classes, dim = text.shape
+    kop = dim * (2 if split else 1)
+    if operand is None:
+        operand = torch.empty(bt, classes, kop, device=text.device, dtype=torch.bfloat16)
+    assert operand.shape == (bt, classes, kop) and operand.is_contiguous()
+    with torch.cuda.device(text.device):
+        check(lib().ovdet_l2norm_text(text.data_ptr(), bt, classes, dim, text.stride(0),
+                                      text.stride(1), operand.data_ptr(), kop, int(split), None,
+                                      _stream(text)), "ovdet_l2norm_text")
+    return operand
+
+
+# --------------------------------------------------------------------------------------------
+# K2: similarity GEMM (+ fused class max / argmax)
+# --------------------------------------------------------------------------------------------
+def similarity(regions_op: torch.Tensor, text_op: torch.Tensor, inv_norm: Optional[torch.Tensor],
+               dim: int, alpha: float = 1.0, beta: float = 0.0, split: bool = False,
+               logits_dtype: Optional[torch.dtype] = torch.float32, want_max: bool = False,
+               logits: Optional[torch.Tensor] = None, row_max: Optional[torch.Tensor] = None,
+               row_arg: Optional[torch.Tensor] = None):
+    """text_contrastive.py:144,147 (+ yolo_clip.py:198-202 through the fused epilogue).
+
+    Returns ``(logits [B, A, C] or None, row_max [B, A] or None, row_arg [B, A] int32 or None)``.
+    """
+    _require_cuda(regions_op, "regions_op", torch.bfloat16)
+    _require_cuda(text_op, "text_op", torch.bfloat16)
+    batch, rows, kop = regions_op.shape
+    bt, classes, kop_t = text_op.shape
+    assert kop == kop_t == dim * (2 if split else 1)
+    assert bt in (1, batch)
+    text_batched = int(bt == batch and batch > 1)
+    dev = regions_op.device
+    if logits is None and logits_dtype is not None:
+        logits = torch.empty(batch, rows, classes, device=dev, dtype=logits_dtype)
+    if want_max and row_max is None:
+        row_max = torch.empty(batch, rows, device=dev, dtype=torch.float32)
+    if want_max and row_arg is None:
+        row_arg = torch.empty(batch, rows, device=dev, dtype=torch.int32)
+    ldt = _cabi.OVDET_F32
+    ldc = classes
+    if logits is not None:
+        assert logits.shape == (batch, rows, classes) and logits.stride(2) == 1
+        assert logits.stride(0) == rows * logits.stride(1)
+        ldc = logits.stride(1)
+        ldt = {torch.float32: _cabi.OVDET_F32, torch.bfloat16: _cabi.OVDET_BF16}[logits.dtype]
+    with torch.cuda.device(dev):
+        check(lib().ovdet_similarity(regions_op.data_ptr(), text_op.data_ptr(), _ptr(inv_norm),
+                                     batch, rows, classes, dim, int(split), text_batched,
+                                     float(alpha), float(beta), _ptr(logits), ldt, ldc,
+                                     _ptr(row_max), _ptr(row_arg), _stream(regions_op)),
+              "ovdet_similarity")
+    return logits, row_max, row_arg
+
+
+def rowmax(logits: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
+    """yolo_clip.py:198-202 on materialised ``[..., C]`` logits (class axis contiguous).
+    Ties resolve to the lowest class index."""
+    _require_cuda(logits, "logits")
+    assert logits.stride(-1) == 1
+    flat = logits.reshape(-1, logits.shape[-1])
+    rows, classes = flat.shape
+    ldt = {torch.float32: _cabi.OVDET_F32, torch.bfloat16: _cabi.OVDET_BF16}[flat.dtype]
+    out_max = torch.empty(rows, device=flat.device, dtype=torch.float32)
+    out_arg = torch.empty(rows, device=flat.device, dtype=torch.int32)
+    with torch.cuda.device(flat.device):
+        check(lib().ovdet_rowmax(flat.data_ptr(), ldt, rows, classes, flat.stride(0),
+                                 out_max.data_ptr(), out_arg.data_ptr(), _stream(flat)), "ovdet_rowmax")
+    return out_max.reshape(logits.shape[:-1]), out_arg.reshape(logits.shape[:-1])
+
+
+# --------------------------------------------------------------------------------------------
+# K3: DFL decode + activation + confidence threshold
+# --------------------------------------------------------------------------------------------
+class LevelTable:
+    """Host-side arrays describing the pyramid levels for ovdet_decode_filter."""
+
+    def __init__(self, box_preds: Sequence[torch.Tensor], strides: Sequence[int]):
+        n = len(box_preds)
+        if n > _cabi.MAX_LEVELS or n != len(strides):
+            raise ValueError("ovdet: unsupported number of levels")
+        self.keep = []
+        for p in box_preds:
+            _require_cuda(p, "box_preds", torch.float32)
+            b, ch, h, w = p.shape
+            if p.stride(3) != 1 or p.stride(2) != w or p.stride(1) != h * w:
+                p = p.contiguous()
+            self.keep.append(p)
+        self.n = n
+        self.batch = self.keep[0].shape[0]
+        self.channels = self.keep[0].shape[1]
+        self.anchors = sum(p.shape[2] * p.shape[3] for p in self.keep)
+        self.ptrs = (ctypes.c_void_p * n)(*[p.data_ptr() for p in self.keep])
+        self.heights = (ctypes.c_int32 * n)(*[p.shape[2] for p in self.keep])
+        self.widths = (ctypes.c_int32 * n)(*[p.shape[3] for p in self.keep])
+        self.strides = (ctypes.c_int32 * n)(*[int(s) for s in strides])
+        self.bstrides = (ctypes.c_int64 * n)(*[p.stride(0) for p in self.keep])
+
+
+def decode_filter(box_preds: Sequence[torch.Tensor], strides: Sequence[int],
+                  scores: Optional[torch.Tensor] = None, conf: float = 0.25,
+                  activation: str = "none", width_scale: float = 1.0, height_scale: float = 1.0,
+                  boxes: Optional[torch.Tensor] = None, scores_act: Optional[torch.Tensor] = None,
+                  pass_mask: Optional[torch.Tensor] = None, want_boxes: bool = True):
+    """box_head.py:150-218 (+ detector.py:184 when ``scores`` is given).
+
+    Returns ``(boxes [B, A, 4] fp32, scores_act or None, pass_mask [B, ceil(A/32)] int32 or None)``.
+    """
+    table = LevelTable(box_preds, strides)
+    dev = table.keep[0].device
+    batch, anchors = table.batch, table.anchors
+    if table.channels % 4:
+        raise ValueError("ovdet: box_preds channels must be 4 * (reg_max + 1)")
+    bins = table.channels // 4
+    act = {"none": _cabi.ACT_NONE, "sigmoid": _cabi.ACT_SIGMOID}[activation]
+    if boxes is None and want_boxes:
+        boxes = torch.empty(batch, anchors, 4, device=dev, dtype=torch.float32)
+    if scores is not None:
+        _require_cuda(scores, "scores", torch.float32)
+        assert scores.shape == (batch, anchors) and scores.is_contiguous()
+        if pass_mask is None:
+            pass_mask = torch.empty(batch, (anchors + 31) // 32, device=dev, dtype=torch.int32)
+        if act == _cabi.ACT_SIGMOID and scores_act is None:
+            scores_act = torch.empty_like(scores)
+    with torch.cuda.device(dev):
+        check(lib().ovdet_decode_filter(table.ptrs, table.heights, table.widths, table.strides,
+                                        table.bstrides, table.n, bins, batch, float(width_scale),
+                                        float(height_scale), _ptr(scores), float(conf), act,
+                                        _ptr(boxes), _ptr(scores_act), _ptr(pass_mask),
+                                        torch.cuda.current_stream(dev).cuda_stream),
+              "ovdet_decode_filter")
+    return boxes, scores_act, pass_mask
+
+
+# --------------------------------------------------------------------------------------------
+# K4: gather + rescale/clip + sort + top-k + NMS
+# --------------------------------------------------------------------------------------------
+class NmsResult:
+    __slots__ = ("boxes", "scores", "classes", "anchor", "keep", "count", "candidates")
+
+    def __init__(self, **kw):
+        for k, v in kw.items():
+            setattr(self, k, v)
+
+
+def nms_workspace_bytes(batch: int, anchors: int) -> int:
+    return int(lib().ovdet_nms_workspace_bytes(batch, anchors))
+
+
+def nms_batched(boxes: torch.Tensor, scores: torch.Tensor, classes: Optional[torch.Tensor] = None,
+                pass_mask: Optional[torch.Tensor] = None, scale: Optional[torch.Tensor] = None,
+                clip_wh: Optional[torch.Tensor] = None, iou_thr: float = 0.45,
+                class_aware: bool = False, topk: int = 0, max_det: Optional[int] = None,
+                out: Optional[NmsResult] = None, workspace: Optional[torch.Tensor] = None) -> NmsResult:
+    """detector.py:185-208 + _nms :225-256 + _compute_iou :258-287, for every image.
+
+    boxes ``[B, A, 4]`` fp32, scores ``[B, A]`` fp32, classes ``[B, A]`` int32 (optional),
+    pass_mask ``[B, ceil(A/32)]`` int32 bit mask (optional: all anchors), scale ``[B]`` fp32,
+    clip_wh ``[B, 2]`` fp32 (w, h).  Result rows are in kept order (score desc).
+    """
+    _require_cuda(boxes, "boxes", torch.float32)
+    _require_cuda(scores, "scores", torch.float32)
+    batch, anchors = scores.shape
+    assert boxes.shape == (batch, anchors, 4) and boxes.is_contiguous() and scores.is_contiguous()
+    if classes is not None:
+        _require_cuda(classes, "classes", torch.int32)
+        assert classes.shape == (batch, anchors) and classes.is_contiguous()
+    dev = boxes.device
+    if max_det is None:
+        max_det = max(anchors, 1)
+    if out is None:
+        out = NmsResult(
+            boxes=torch.zeros(batch, max_det, 4, device=dev, dtype=torch.float32),
+            scores=torch.zeros(batch, max_det, device=dev, dtype=torch.float32),
+            classes=torch.zeros(batch, max_det, device=dev, dtype=torch.int32),
+            anchor=torch.full((batch, max_det), -1, device=dev, dtype=torch.int32),
+            keep=torch.full((batch, max_det), -1, device=dev, dtype=torch.int32),
+            count=torch.zeros(batch, device=dev, dtype=torch.int32),
+            candidates=torch.zeros(batch, device=dev, dtype=torch.int32))
+    need = nms_workspace_bytes(batch, anchors)
+    if workspace is None:
+        workspace = torch.empty(max(need, 16), device=dev, dtype=torch.uint8)
+    with torch.cuda.device(dev):
+        check(lib().ovdet_nms_batched(boxes.data_ptr(), scores.data_ptr(), _ptr(classes),
+                                      _ptr(pass_mask), batch, anchors, _ptr(scale), _ptr(clip_wh),
+                                      float(iou_thr), int(class_aware), int(topk), int(max_det),
+                                      out.boxes.data_ptr(), out.scores.data_ptr(),
+                                      out.classes.data_ptr(), out.anchor.data_ptr(),
+                                      out.keep.data_ptr(), out.count.data_ptr(),
+                                      out.candidates.data_ptr(), workspace.data_ptr(),
+                                      workspace.numel(), _stream(boxes)), "ovdet_nms_batched")
+    return out

@@ -1,0 +1,151 @@
+"""The head + post-processing hot path as one pre-planned sequence of launches.
+
+``HeadPipeline`` owns every intermediate buffer (bf16 operands, inverse norms, scores, class
+ids, boxes, pass mask, NMS workspace and outputs) for a fixed problem shape, so a step performs
+no allocation and no host synchronisation: K1 (one launch per level) -> K2 (one GEMM, class
+max/argmax fused) -> K3 (decode + threshold) -> K4 (gather/sort/top-k/NMS).  This is what
+``Detector.predict`` and ``bench.py`` run.  Reference call sequence it replaces:
+model/yolo_clip.py:173-214 followed by inference/detector.py:163-223 for every image.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass, field
+from typing import Dict, List, Optional, Sequence, Tuple
+
+import torch
+
+from . import ops
+
+
+@dataclass(frozen=True)
+class HeadConfig:
+    """Defaults are the reference's inference defaults (config/default_config.py:86-95,
+    model/yolo_clip.py:39, model/heads/text_contrastive.py:44-45); the last five fields are
+    extensions that default to the reference behaviour."""
+    embed_dim: int = 512
+    reg_max: int = 16
+    strides: Tuple[int, ...] = (8, 16, 32)
+    cls_alpha: float = 1.0
+    cls_beta: float = 0.0
+    conf_threshold: float = 0.25
+    iou_threshold: float = 0.45
+    precision: str = "bf16"            # "bf16": one tensor-core pass; "fp32": 3-pass hi/lo split
+    logits_dtype: Optional[str] = None  # None: fused max only; "bf16" / "fp32": also materialise
+    activation: str = "none"           # reference applies no activation to the scores
+    topk: int = 0                      # 0 = every survivor goes to NMS (reference)
+    class_aware: bool = False          # reference NMS is class-agnostic
+    max_det: int = 0                   # 0 = capacity for every anchor (reference has no cap)
+
+
+class HeadPipeline:
+    def __init__(self, batch: int, level_shapes: Sequence[Tuple[int, int]], num_classes: int,
+                 config: HeadConfig = HeadConfig(), device="cuda", per_image_text: bool = False):
+        self.cfg = config
+        self.batch = batch
+        self.level_shapes = [tuple(s) for s in level_shapes]
+        self.anchors = sum(h * w for h, w in self.level_shapes)
+        self.num_classes = num_classes
+        self.device = torch.device(device)
+        self.per_image_text = per_image_text
+        self.split = config.precision == "fp32"
+        d, a, dev = config.embed_dim, self.anchors, self.device
+        kop = d * (2 if self.split else 1)
+        self.regions_op = torch.empty(batch, a, kop, device=dev, dtype=torch.bfloat16)
+        self.inv_norm = torch.empty(batch, a, device=dev, dtype=torch.float32)
+        self.text_op = torch.empty(batch if per_image_text else 1, num_classes, kop, device=dev,
+                                   dtype=torch.bfloat16)
+        self.scores = torch.empty(batch, a, device=dev, dtype=torch.float32)
+        self.class_ids = torch.empty(batch, a, device=dev, dtype=torch.int32)
+        self.logits = None
+        if config.logits_dtype is not None:
+            dt = {"bf16": torch.bfloat16, "fp32": torch.float32}[config.logits_dtype]
+            self.logits = torch.empty(batch, a, num_classes, device=dev, dtype=dt)
+        self.boxes = torch.empty(batch, a, 4, device=dev, dtype=torch.float32)
+        self.scores_act = (torch.empty(batch, a, device=dev, dtype=torch.float32)
+                           if config.activation == "sigmoid" else None)
+        self.pass_mask = torch.empty(batch, (a + 31) // 32, device=dev, dtype=torch.int32)
+        self.max_det = config.max_det if config.max_det > 0 else a
+        md = self.max_det
+        self.result = ops.NmsResult(
+            boxes=torch.zeros(batch, md, 4, device=dev, dtype=torch.float32),
+            scores=torch.zeros(batch, md, device=dev, dtype=torch.float32),
+            classes=torch.zeros(batch, md, device=dev, dtype=torch.int32),
+            anchor=torch.zeros(batch, md, device=dev, dtype=torch.int32),
+            keep=torch.zeros(batch, md, device=dev, dtype=torch.int32),
+            count=torch.zeros(batch, device=dev, dtype=torch.int32),
+            candidates=torch.zeros(batch, device=dev, dtype=torch.int32))
+        self.workspace = torch.empty(max(16, ops.nms_workspace_bytes(batch, a)), device=dev,
+                                     dtype=torch.uint8)
+        self.scale = torch.ones(batch, device=dev, dtype=torch.float32)
+        self.clip_wh = torch.zeros(batch, 2, device=dev, dtype=torch.float32)
+        self.use_geometry = False
+        self._vocab_ready = False
+        self.launches_per_step = len(self.level_shapes) + 3 + (1 if per_image_text else 0)
+
+    # -- one-off / per-call host parameters -------------------------------------------------
+    def set_vocabulary(self, text: torch.Tensor) -> None:
+        """Normalise a shared ``[C, D]`` vocabulary once (the reference re-normalises it three
+        times per forward, text_contrastive.py:138)."""
+        assert not self.per_image_text
+        ops.l2norm_text(text, split=self.split, operand=self.text_op)
+        self._vocab_ready = True
+
+    def set_geometry(self, orig_sizes: Sequence[Tuple[int, int]], scale_factors: Sequence[float]) -> None:
+        """Per-image ``(orig_h, orig_w)`` and letterbox scale (detector.py:193-202).  The scale
+        is rounded to float32 exactly as numpy's weak python-float promotion does."""
+        import numpy as np
+        scale = np.asarray([np.float32(s) for s in scale_factors], dtype=np.float32)
+        wh = np.asarray([[float(w), float(h)] for (h, w) in orig_sizes], dtype=np.float32)
+        self.scale.copy_(torch.from_numpy(scale))
+        self.clip_wh.copy_(torch.from_numpy(wh))
+        self.use_geometry = True
+
+    # -- the hot path -----------------------------------------------------------------------
+    def run(self, obj_embeds: Sequence[torch.Tensor], box_preds: Sequence[torch.Tensor],
+            text: Optional[torch.Tensor] = None, events: Optional[dict] = None) -> ops.NmsResult:
+        """One pass of the hot path.  ``events`` (optional dict) receives a pair of CUDA events
+        per stage, recorded on the launching stream, for per-kernel timing."""
+        cfg = self.cfg
+
+        def mark(name, begin):
+            if events is not None:
+                ev = torch.cuda.Event(enable_timing=True)
+                ev.record()
+                if begin:
+                    events[name] = [ev, None]
+                else:
+                    events[name][1] = ev
+
+        mark("l2norm", True)
+        ops.l2norm_regions(obj_embeds, split=self.split, operand=self.regions_op, inv_norm=self.inv_norm)
+        if self.per_image_text:
+            ops.l2norm_text(text, split=self.split, operand=self.text_op)
+        elif text is not None:
+            self.set_vocabulary(text)
+        elif not self._vocab_ready:
+            raise RuntimeError("ovdet: no vocabulary set (call set_vocabulary or pass text)")
+        mark("l2norm", False)
+        mark("similarity", True)
+        ops.similarity(self.regions_op, self.text_op, self.inv_norm, cfg.embed_dim, cfg.cls_alpha,
+                       cfg.cls_beta, split=self.split, logits_dtype=None, logits=self.logits,
+                       want_max=True, row_max=self.scores, row_arg=self.class_ids)
+        mark("similarity", False)
+        mark("decode", True)
+        ops.decode_filter(box_preds, cfg.strides, scores=self.scores, conf=cfg.conf_threshold,
+                          activation=cfg.activation, boxes=self.boxes, scores_act=self.scores_act,
+                          pass_mask=self.pass_mask)
+        mark("decode", False)
+        nms_scores = self.scores_act if self.scores_act is not None else self.scores
+        mark("nms", True)
+        res = ops.nms_batched(self.boxes, nms_scores, self.class_ids, self.pass_mask,
+                              scale=self.scale if self.use_geometry else None,
+                              clip_wh=self.clip_wh if self.use_geometry else None,
+                              iou_thr=cfg.iou_threshold, class_aware=cfg.class_aware,
+                              topk=cfg.topk, max_det=self.max_det, out=self.result,
+                              workspace=self.workspace)
+        mark("nms", False)
+        return res
+
+    def outputs(self) -> Dict[str, torch.Tensor]:
+        """The reference's forward-dict view of the intermediate tensors (yolo_clip.py:216-223)."""
+        return {"boxes": self.boxes, "scores": self.scores, "class_ids": self.class_ids.long()}

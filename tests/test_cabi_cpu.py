@@ -1,0 +1,96 @@
+"""CPU-side checks: the C-ABI library builds, loads and exports exactly what include/ovdet.h
+declares; argument validation and the no-fallback contract hold without a GPU."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def handle():
+    from ovdet import build, _cabi
+    build.build()
+    return _cabi.lib()
+
+
+def _declared():
+    text = open(os.path.join(ROOT, "include", "ovdet.h")).read()
+    return sorted(set(re.findall(r"OVDET_API[^;]*?\b(ovdet_\w+)\s*\(", text)))
+
+
+def test_header_symbols_exported(handle):
+    from ovdet import _cabi
+    names = _declared()
+    assert len(names) >= 11
+    for n in names:
+        assert hasattr(handle, n), f"{n} declared in ovdet.h but not exported"
+    assert sorted(_cabi.PROTOTYPES) == names          # the ctypes table covers the whole header
+
+
+def test_version_and_strerror(handle):
+    assert handle.ovdet_version() == 100
+    assert handle.ovdet_strerror(0) == b"ok"
+    assert b"no fallback" in handle.ovdet_strerror(-3)
+    assert handle.ovdet_strerror(-99) == b"unknown status"
+
+
+def test_argument_validation_without_gpu(handle):
+    # argument checks come before the device check, so they are testable on a CPU-only host
+    assert handle.ovdet_rowmax(None, 0, 1, 1, 1, None, None, None) == -1
+    assert handle.ovdet_nms_workspace_bytes(0, 100) == 0
+    assert handle.ovdet_nms_workspace_bytes(2, 8400) >= 2 * (16384 * 8 + 8400 * 20)
+    assert handle.ovdet_similarity(None, None, None, 1, 1, 1, 64, 0, 0, 1.0, 0.0, None, 0, 1,
+                                   None, None, None) == -1
+
+
+@pytest.mark.skipif(torch.cuda.is_available(), reason="CPU-only contract")
+def test_no_cpu_fallback(handle):
+    """Without a B200 every compute entry refuses to run; nothing silently falls back."""
+    from ovdet import ops
+    with pytest.raises(RuntimeError, match="CUDA tensor"):
+        ops.rowmax(torch.zeros(2, 3))
+    with pytest.raises(RuntimeError, match="CUDA tensor"):
+        ops.l2norm_text(torch.zeros(2, 64))
+    buf = (ctypes.c_float * 16)()
+    out = (ctypes.c_float * 4)()
+    rc = handle.ovdet_rowmax(ctypes.addressof(buf), 0, 4, 4, 4, ctypes.addressof(out), None, None)
+    assert rc in (-3, -4)                 # wrong arch / no CUDA device: an error, never a result
+
+
+def test_product_does_not_import_oracle():
+    pkg = os.path.join(ROOT, "real-time-zero-shot-open-vocabulary-object-detection-using-a-lightweight_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                src = open(os.path.join(dirpath, f)).read()
+                assert "oracle" not in src.replace("oracle-sized", ""), f"{f} mentions the oracle"
+
+
+def test_pack_mask_roundtrip():
+    from ovdet.detector import _pack_mask
+    rng = np.random.default_rng(0)
+    bits = torch.from_numpy(rng.random((3, 100)) > 0.5)
+    packed = _pack_mask(bits)
+    assert packed.dtype == torch.int32 and packed.shape == (3, 4)
+    m = packed.to(torch.int64) & 0xffffffff
+    un = ((m.unsqueeze(-1) >> torch.arange(32)) & 1).reshape(3, -1)[:, :100].bool()
+    assert torch.equal(un, bits)
+
+
+def test_module_state_dict_keys_match_reference_layout():
+    from ovdet.heads import BoxHead, TextContrastiveHead
+    head = TextContrastiveHead(64)
+    keys = set(head.state_dict())
+    assert "obj_embed_conv.0.conv.weight" in keys and "obj_embed_conv.2.bias" in keys
+    assert "box_conv.1.bn.running_mean" in keys
+    assert not any("precision" in k for k in keys)
+    box = BoxHead([64, 128, 256])
+    assert "box_convs.2.2.weight" in box.state_dict()
+    grid = box._create_grid(2, 3, 4, 8, torch.device("cpu"))
+    assert grid.shape == (2, 3, 4, 3) and grid.dtype == torch.int64
+    assert grid[0, 1, 2].tolist() == [2, 1, 8]
