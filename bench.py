@@ -61,7 +61,7 @@ class ClockSampler:
         try:
             self.proc = subprocess.Popen(
                 ["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.QUERY}",
-                 "--format=csv,noheader,nounits", "-lms", "100"],
+                 "--format=csv,noheader,nounits", "-lms", "50"],
                 stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             threading.Thread(target=self._pump, daemon=True).start()
         except OSError:
@@ -228,6 +228,11 @@ def run_ours(args):
         return statistics.mean(e[name][0].elapsed_time(e[name][1]) for e in stage_events)
     stages = {k: stage_ms(k) for k in ("l2norm", "similarity", "decode", "nms")}
 
+    if args.profile:
+        if rank == 0:
+            print(json.dumps({"profile_only": True, "value": value, "stages_ms": stages}), flush=True)
+        return
+
     # ---- end to end through the public API with HOST buffers ---------------------------------
     chunk = min(args.e2e_chunk, batch)
     assert batch % chunk == 0
@@ -342,13 +347,15 @@ def run_ours(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=100)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--batch", type=int, default=BATCH_PER_GPU, help="images per GPU per step")
     ap.add_argument("--e2e-chunk", type=int, default=32)
     ap.add_argument("--e2e-steps", type=int, default=5)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--profile", action="store_true",
+                    help="device-resident loop only (for ncu): no e2e, latency or CPU legs")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":
         args.warmup = 3
