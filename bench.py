@@ -10,8 +10,9 @@ conf 0.25, IoU 0.45; synthetic conv outputs (ovdet.synth) 
 shared vocabulary.  One process per GPU, the batch is the sharded unit, no collective on the
 data path; per-GPU work is fixed as N grows ("weak").
 
-One step = K1 (L2 norm + bf16 operand, 3 launches) -> K2 (tcgen05 GEMM + max/argmax) -> K3
-(DFL decode + threshold) -> K4 (gather / sort / NMS) over one batch.  `value` times the steps
+One step = K1+K2 fused (L2 norm + tcgen05 similarity GEMM + class max/argmax straight from the
+fp32 NCHW conv outputs, 1 launch) -> K3 (DFL decode + threshold) -> K4 (gather / sort / NMS) over
+one batch (`--no-fused`: K1 as 3 launches writing a bf16 operand, then the K2 GEMM).  `value` times the steps
 with the inputs resident in HBM; `e2e` times Detector.predict on pinned HOST buffers with the
 H2D copies and the D2H of the detections inside the timed region.
 """
@@ -182,7 +183,7 @@ def run_ours(args):
     shapes = [(IMAGE_SIZE // s, IMAGE_SIZE // s) for s in STRIDES]
     anchors = sum(h * w for h, w in shapes)
 
-    cfg = HeadConfig(precision="bf16", max_det=MAX_DET)
+    cfg = HeadConfig(precision="bf16", max_det=MAX_DET, fused=not args.no_fused)
     inp = synth.make_inputs(batch=batch, image_size=IMAGE_SIZE, num_classes=NUM_CLASSES,
                             embed_dim=EMBED_DIM, device=dev, seed=1234 + rank)
     pipe = HeadPipeline(batch, shapes, NUM_CLASSES, cfg, device=dev)
@@ -309,6 +310,10 @@ def run_ours(args):
         peaks = measured_peaks()
         flops = 2.0 * batch * anchors * NUM_CLASSES * EMBED_DIM
         achieved = flops / (stages["similarity"] * 1e-3) / 1e12
+        fused = pipe.last_path == "fused"
+        launches = (3 if fused else len(shapes) + 3)
+        kernel = ("sim_fused_kernel (K1+K2: fp32 NCHW in, L2 norm, tcgen05 GEMM, class max/argmax)" if fused
+                  else "sim_gemm_kernel (K2)")
         k1_bytes = batch * anchors * (EMBED_DIM * 4 + EMBED_DIM * 2 + 4)
         k3_bytes = batch * anchors * (68 * 4 + 4 + 16) + batch * ((anchors + 31) // 32) * 4
         line = {
@@ -318,6 +323,7 @@ def run_ours(args):
             "config": {"workload": workload_name(batch), "global_batch": batch * n_gpus,
                        "anchors": anchors, "classes": NUM_CLASSES, "embed_dim": EMBED_DIM,
                        "precision": "bf16 operands, fp32 accumulate, fused class max/argmax",
+                       "path": pipe.last_path,
                        "conf": cfg.conf_threshold, "iou": cfg.iou_threshold, "max_det": MAX_DET,
                        "parallelism": f"batch-sharded x{n_gpus}, vocabulary replicated, no collective",
                        "l2": f"inputs are {input_bytes / 1e9:.2f} GB per step per GPU (> 126 MB L2), no flush needed",
@@ -326,14 +332,17 @@ def run_ours(args):
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": input_bytes,
                     "d2h_bytes_per_step": d2h_bytes, "steps": e2e_steps, "chunk_images": chunk,
                     "api": "ovdet.detector.Detector.predict_host (pinned host buffers in, detections out)"},
-            "gpu_launches": pipe.launches_per_step * args.steps,
-            "roofline": {"bound": "tensor", "kernel": "sim_gemm_kernel (K2)", "achieved": achieved,
+            "gpu_launches": launches * args.steps,
+            "roofline": {"bound": "tensor", "kernel": kernel, "achieved": achieved,
                          "peak": peaks["tflops"], "unit": "TFLOP/s", "frac": achieved / peaks["tflops"],
                          "traffic": None, "peak_source": peaks["source"] + " (bf16_tflops_sustained)",
                          "ms_per_launch": stages["similarity"]},
             "stages_ms": stages,
             "stage_rooflines": {
-                "l2norm_hbm_frac": k1_bytes / (stages["l2norm"] * 1e-3) / 1e9 / peaks["hbm_gbs"],
+                "l2norm_hbm_frac": (None if fused else
+                                    k1_bytes / (stages["l2norm"] * 1e-3) / 1e9 / peaks["hbm_gbs"]),
+                "similarity_hbm_frac_fp32_input": batch * anchors * EMBED_DIM * 4 / (stages["similarity"] * 1e-3)
+                                                  / 1e9 / peaks["hbm_gbs"],
                 "decode_hbm_frac": k3_bytes / (stages["decode"] * 1e-3) / 1e9 / peaks["hbm_gbs"]},
             "latency_ms_p50_batch1": p50,
             "clocks": clocks,
@@ -354,6 +363,7 @@ def main():
     ap.add_argument("--e2e-chunk", type=int, default=32)
     ap.add_argument("--e2e-steps", type=int, default=5)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-fused", action="store_true", help="two-kernel K1 -> K2 path instead of the fused kernel")
     ap.add_argument("--profile", action="store_true",
                     help="device-resident loop only (for ncu): no e2e, latency or CPU legs")
     args = ap.parse_args()

@@ -112,6 +112,29 @@ OVDET_API int ovdet_similarity(const void* regions_op, const void* text_op, cons
                      void* logits, int logits_dtype, int64_t ldc,
                      float* row_max, int32_t* row_arg, void* stream);
 
+/* K1+K2 fused  L2 norm of the region embeddings + similarity + class max/argmax in one kernel
+ * that reads the fp32 NCHW conv outputs of ALL levels directly (no bf16 operand round trip
+ * through HBM; the converted 128-anchor tile stays in tensor memory for the whole vocabulary).
+ * Replaces: model/heads/text_contrastive.py:134-147 for every level + model/yolo_clip.py:198-206.
+ *
+ *   obj_embeds   HOST array of num_levels (<= 4) device pointers, level l is fp32
+ *                [batch, dim, hw[l]] with element (b,d,a) at p[b*stride_b[l] + d*stride_d[l] + a];
+ *                pointers 16-byte aligned, strides multiples of 4 elements (TMA), else
+ *                OVDET_ERR_UNSUPPORTED_SHAPE (use ovdet_l2norm_regions + ovdet_similarity)
+ *   text_op      bf16 [text_batch, classes, dim] from ovdet_l2norm_text (split = 0)
+ *   dim          multiple of 64, <= 512;  one bf16 tensor-core pass (|dlogit| <~ 8e-3)
+ *   logits       optional [batch, anchors, ldc], anchors = sum hw, levels concatenated in order
+ *   row_max / row_arg   optional fp32 / int32 [batch, anchors]
+ *   inv_norm     optional fp32 [batch, anchors] out: 1 / max(||x||_2, 1e-12)
+ */
+OVDET_API int ovdet_similarity_fused(const float* const* obj_embeds, const int64_t* hw,
+                                     const int64_t* stride_b, const int64_t* stride_d,
+                                     int num_levels, int64_t batch, int64_t dim,
+                                     const void* text_op, int64_t classes, int text_batched,
+                                     float alpha, float beta, void* logits, int logits_dtype,
+                                     int64_t ldc, float* row_max, int32_t* row_arg,
+                                     float* inv_norm, void* stream);
+
 /* K2b  max/argmax over classes of materialised logits (any producer).
  * Replaces: model/yolo_clip.py:198-202 (similarity.max(dim=1)); ties -> lowest class index.
  *   logits [rows, ldc] fp32 or bf16, columns [0,classes) are read. */

@@ -176,6 +176,7 @@ sim_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a,
     // ================================ epilogue ===============================================
     const int lg = warp & 3;                         // TMEM lane group this warp may access
     float* stage = epi_stage + (warp - 2) * 32 * STAGE_PITCH;
+    const bool want_max = p.row_max != nullptr;
     uint32_t acc_it = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
       const int b = tile / p.m_tiles;
@@ -185,37 +186,50 @@ sim_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a,
       const long long grow = (long long)b * p.rows + row;
       const float inv = (row_ok && p.inv_norm_r) ? p.inv_norm_r[grow] : (row_ok ? 1.f : 0.f);
       const float scale = p.alpha * inv;
-      float best = -INFINITY;
-      int best_idx = 0;
+      const float beta = p.beta;
+      // four independent (max, argmax) chains (column % 4) keep the compare/select dependency
+      // chain short; they are merged, lowest index winning ties, once per M tile
+      float bv[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+      int bi[4] = {0, 0, 0, 0};
       for (int nt = 0; nt < p.n_tiles; ++nt, ++acc_it) {
         const int n0 = nt * p.box_n;
         const int n_valid = min(p.box_n, p.classes - n0);
+        const int nchunks = (n_valid + 31) >> 5;
         const int as = acc_it & 1;
         const uint32_t aph = (acc_it >> 1) & 1u;
         ptx::mbar_wait(tmem_full_bar(as), aph);
         ptx::tc_fence_after();
         const uint32_t t_row = tmem_base + ((uint32_t)(lg * 32) << 16) + (uint32_t)(as * BLOCK_N);
-        for (int c0 = 0; c0 < n_valid; c0 += 32) {
-          uint32_t r[32];
-          ptx::tmem_ld_32x32(t_row + (uint32_t)c0, r);
-          ptx::tmem_ld_wait();
-          float v[32];
+
+        auto consume = [&](uint32_t (&r)[32], int c) {
+          const int c0 = c << 5;
+          const int valid = n_valid - c0;              // > 0
 #pragma unroll
-          for (int j = 0; j < 32; ++j) v[j] = fmaf(scale, __uint_as_float(r[j]), p.beta);
-          if (p.row_max != nullptr) {
+          for (int j = 0; j < 32; ++j) r[j] = __float_as_uint(fmaf(scale, __uint_as_float(r[j]), beta));
+          if (want_max) {
+            const int col = n0 + c0;
+            if (valid >= 32) {
 #pragma unroll
-            for (int j = 0; j < 32; ++j) {
-              if (c0 + j < n_valid && v[j] > best) { best = v[j]; best_idx = n0 + c0 + j; }
+              for (int j = 0; j < 32; ++j) {
+                const float v = __uint_as_float(r[j]);
+                if (v > bv[j & 3]) { bv[j & 3] = v; bi[j & 3] = col + j; }
+              }
+            } else {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) {
+                const float v = __uint_as_float(r[j]);
+                if (j < valid && v > bv[j & 3]) { bv[j & 3] = v; bi[j & 3] = col + j; }
+              }
             }
           }
           if (p.logits != nullptr) {
             // registers (thread = row) -> smem transpose -> one coalesced row segment per
             // warp store instruction
 #pragma unroll
-            for (int j = 0; j < 32; ++j) stage[lane * STAGE_PITCH + j] = v[j];
+            for (int j = 0; j < 32; ++j) stage[lane * STAGE_PITCH + j] = __uint_as_float(r[j]);
             __syncwarp();
             const int col = n0 + c0 + lane;
-            const bool col_ok = (c0 + lane) < n_valid;
+            const bool col_ok = lane < valid;
             const int rows_here = min(32, p.rows - (m0 + lg * 32));
             const long long out_row0 = (long long)b * p.rows + m0 + lg * 32;
             if (p.logits_bf16) {
@@ -229,13 +243,33 @@ sim_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a,
             }
             __syncwarp();
           }
+        };
+
+        // software pipeline over 32-column chunks: the TMEM load of chunk c+1 is in flight while
+        // chunk c is consumed
+        uint32_t ra[32], rb[32];
+        ptx::tmem_ld_32x32(t_row, ra);
+        for (int c = 0; c < nchunks; c += 2) {
+          ptx::tmem_ld_wait();
+          if (c + 1 < nchunks) ptx::tmem_ld_32x32(t_row + (uint32_t)((c + 1) << 5), rb);
+          consume(ra, c);
+          if (c + 1 < nchunks) {
+            ptx::tmem_ld_wait();
+            if (c + 2 < nchunks) ptx::tmem_ld_32x32(t_row + (uint32_t)((c + 2) << 5), ra);
+            consume(rb, c + 1);
+          }
         }
         // all TMEM reads of this accumulator stage are complete (wait::ld above)
         ptx::tc_fence_before();
         __syncwarp();
         if (lane == 0) ptx::mbar_arrive(tmem_empty_bar(as));
       }
-      if (p.row_max != nullptr && row_ok) {
+      if (want_max && row_ok) {
+        float best = bv[0];
+        int best_idx = bi[0];
+#pragma unroll
+        for (int q = 1; q < 4; ++q)
+          if (bv[q] > best || (bv[q] == best && bi[q] < best_idx)) { best = bv[q]; best_idx = bi[q]; }
         p.row_max[grow] = best;
         if (p.row_arg != nullptr) p.row_arg[grow] = best_idx;
       }

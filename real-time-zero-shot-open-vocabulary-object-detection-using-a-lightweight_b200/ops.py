@@ -141,6 +141,66 @@ def similarity(regions_op: torch.Tensor, text_op: torch.Tensor, inv_norm: Option
     return logits, row_max, row_arg
 
 
+def fused_supported(obj_embeds: Sequence[torch.Tensor]) -> bool:
+    """Shapes the fused K1+K2 kernel takes (TMA alignment, <= 4 levels, dim <= 512)."""
+    if len(obj_embeds) > 4:
+        return False
+    for e in obj_embeds:
+        b, d, h, w = e.shape
+        if e.dtype != torch.float32 or d % 64 or d > 512:
+            return False
+        if e.stride(3) != 1 or e.stride(2) != w:
+            return False
+        if e.stride(1) % 4 or e.stride(0) % 4 or e.data_ptr() % 16 or e.stride(1) < h * w:
+            return False
+    return True
+
+
+def similarity_fused(obj_embeds: Sequence[torch.Tensor], text_op: torch.Tensor, alpha: float = 1.0,
+                     beta: float = 0.0, logits_dtype: Optional[torch.dtype] = None,
+                     want_max: bool = True, logits: Optional[torch.Tensor] = None,
+                     row_max: Optional[torch.Tensor] = None, row_arg: Optional[torch.Tensor] = None,
+                     inv_norm: Optional[torch.Tensor] = None):
+    """text_contrastive.py:134-147 for all levels + yolo_clip.py:198-206 in one launch, reading
+    the fp32 NCHW ``obj_embeds`` directly.  ``text_op`` comes from ``l2norm_text(split=False)``.
+    Returns ``(logits [B, A, C] or None, row_max, row_arg)``."""
+    first = obj_embeds[0]
+    _require_cuda(first, "obj_embed", torch.float32)
+    _require_cuda(text_op, "text_op", torch.bfloat16)
+    if not fused_supported(obj_embeds):
+        raise ValueError("ovdet: shapes/strides not supported by the fused kernel "
+                         "(use l2norm_regions + similarity)")
+    batch, dim = first.shape[0], first.shape[1]
+    n = len(obj_embeds)
+    anchors = sum(e.shape[2] * e.shape[3] for e in obj_embeds)
+    bt, classes, kop = text_op.shape
+    assert kop == dim and bt in (1, batch)
+    dev = first.device
+    if logits is None and logits_dtype is not None:
+        logits = torch.empty(batch, anchors, classes, device=dev, dtype=logits_dtype)
+    if want_max and row_max is None:
+        row_max = torch.empty(batch, anchors, device=dev, dtype=torch.float32)
+    if want_max and row_arg is None:
+        row_arg = torch.empty(batch, anchors, device=dev, dtype=torch.int32)
+    ldt, ldc = _cabi.OVDET_F32, classes
+    if logits is not None:
+        assert logits.shape == (batch, anchors, classes) and logits.stride(2) == 1
+        assert logits.stride(0) == anchors * logits.stride(1)
+        ldc = logits.stride(1)
+        ldt = {torch.float32: _cabi.OVDET_F32, torch.bfloat16: _cabi.OVDET_BF16}[logits.dtype]
+    ptrs = (ctypes.c_void_p * n)(*[e.data_ptr() for e in obj_embeds])
+    hw = (ctypes.c_int64 * n)(*[e.shape[2] * e.shape[3] for e in obj_embeds])
+    sb = (ctypes.c_int64 * n)(*[e.stride(0) for e in obj_embeds])
+    sd = (ctypes.c_int64 * n)(*[e.stride(1) for e in obj_embeds])
+    with torch.cuda.device(dev):
+        check(lib().ovdet_similarity_fused(ptrs, hw, sb, sd, n, batch, dim, text_op.data_ptr(),
+                                           classes, int(bt == batch and batch > 1), float(alpha),
+                                           float(beta), _ptr(logits), ldt, ldc, _ptr(row_max),
+                                           _ptr(row_arg), _ptr(inv_norm), _stream(first)),
+              "ovdet_similarity_fused")
+    return logits, row_max, row_arg
+
+
 def rowmax(logits: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
     """yolo_clip.py:198-202 on materialised ``[..., C]`` logits (class axis contiguous).
     Ties resolve to the lowest class index."""

@@ -2,9 +2,11 @@
 
 ``HeadPipeline`` owns every intermediate buffer (bf16 operands, inverse norms, scores, class
 ids, boxes, pass mask, NMS workspace and outputs) for a fixed problem shape, so a step performs
-no allocation and no host synchronisation: K1 (one launch per level) -> K2 (one GEMM, class
-max/argmax fused) -> K3 (decode + threshold) -> K4 (gather/sort/top-k/NMS).  This is what
-``Detector.predict`` and ``bench.py`` run.  Reference call sequence it replaces:
+no allocation and no host synchronisation.  bf16 precision: K1+K2 fused (one launch reads the
+fp32 NCHW conv outputs of every level, normalises, multiplies, class max/argmax) -> K3 (decode +
+threshold) -> K4 (gather/sort/top-k/NMS): 3 launches.  fp32 precision (3-pass hi/lo split) or
+inputs the fused kernel's TMA cannot address: K1 (one launch per level) -> K2 -> K3 -> K4.  This
+is what ``Detector.predict`` and ``bench.py`` run.  Reference call sequence it replaces:
 model/yolo_clip.py:173-214 followed by inference/detector.py:163-223 for every image.
 """
 from __future__ import annotations
@@ -35,6 +37,7 @@ class HeadConfig:
     topk: int = 0                      # 0 = every survivor goes to NMS (reference)
     class_aware: bool = False          # reference NMS is class-agnostic
     max_det: int = 0                   # 0 = capacity for every anchor (reference has no cap)
+    fused: bool = True                 # bf16 only: K1+K2 in one kernel when the inputs allow it
 
 
 class HeadPipeline:
@@ -50,7 +53,9 @@ class HeadPipeline:
         self.split = config.precision == "fp32"
         d, a, dev = config.embed_dim, self.anchors, self.device
         kop = d * (2 if self.split else 1)
-        self.regions_op = torch.empty(batch, a, kop, device=dev, dtype=torch.bfloat16)
+        self.want_fused = config.fused and not self.split and d % 64 == 0 and d <= 512
+        self._kop = kop
+        self.regions_op = None             # bf16 operand of the two-kernel path, allocated on first use
         self.inv_norm = torch.empty(batch, a, device=dev, dtype=torch.float32)
         self.text_op = torch.empty(batch if per_image_text else 1, num_classes, kop, device=dev,
                                    dtype=torch.bfloat16)
@@ -80,7 +85,9 @@ class HeadPipeline:
         self.clip_wh = torch.zeros(batch, 2, device=dev, dtype=torch.float32)
         self.use_geometry = False
         self._vocab_ready = False
-        self.launches_per_step = len(self.level_shapes) + 3 + (1 if per_image_text else 0)
+        self.last_path = None              # "fused" | "split": what the previous run() launched
+        self.launches_per_step = ((3 if self.want_fused else len(self.level_shapes) + 3)
+                                  + (1 if per_image_text else 0))
 
     # -- one-off / per-call host parameters -------------------------------------------------
     def set_vocabulary(self, text: torch.Tensor) -> None:
@@ -116,8 +123,14 @@ class HeadPipeline:
                 else:
                     events[name][1] = ev
 
+        fused = self.want_fused and ops.fused_supported(obj_embeds)
+        self.last_path = "fused" if fused else "split"
         mark("l2norm", True)
-        ops.l2norm_regions(obj_embeds, split=self.split, operand=self.regions_op, inv_norm=self.inv_norm)
+        if not fused:
+            if self.regions_op is None:
+                self.regions_op = torch.empty(self.batch, self.anchors, self._kop, device=self.device,
+                                              dtype=torch.bfloat16)
+            ops.l2norm_regions(obj_embeds, split=self.split, operand=self.regions_op, inv_norm=self.inv_norm)
         if self.per_image_text:
             ops.l2norm_text(text, split=self.split, operand=self.text_op)
         elif text is not None:
@@ -126,9 +139,14 @@ class HeadPipeline:
             raise RuntimeError("ovdet: no vocabulary set (call set_vocabulary or pass text)")
         mark("l2norm", False)
         mark("similarity", True)
-        ops.similarity(self.regions_op, self.text_op, self.inv_norm, cfg.embed_dim, cfg.cls_alpha,
-                       cfg.cls_beta, split=self.split, logits_dtype=None, logits=self.logits,
-                       want_max=True, row_max=self.scores, row_arg=self.class_ids)
+        if fused:
+            ops.similarity_fused(obj_embeds, self.text_op, cfg.cls_alpha, cfg.cls_beta, logits_dtype=None,
+                                 logits=self.logits, want_max=True, row_max=self.scores,
+                                 row_arg=self.class_ids, inv_norm=self.inv_norm)
+        else:
+            ops.similarity(self.regions_op, self.text_op, self.inv_norm, cfg.embed_dim, cfg.cls_alpha,
+                           cfg.cls_beta, split=self.split, logits_dtype=None, logits=self.logits,
+                           want_max=True, row_max=self.scores, row_arg=self.class_ids)
         mark("similarity", False)
         mark("decode", True)
         ops.decode_filter(box_preds, cfg.strides, scores=self.scores, conf=cfg.conf_threshold,

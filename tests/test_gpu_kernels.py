@@ -397,3 +397,51 @@ def test_full_size_properties(ov, cuda_device):
     for i in (0, 63):
         k = int(cnt[i])
         assert again.anchor[i, :k].tolist() == list(range(k))
+
+
+# ------------------------------------------------------------------------------------------
+# K1+K2 fused (fp32 NCHW in, A operand resident in tensor memory)
+# ------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("classes,batched,dim", [(80, False, 512), (1203, False, 512), (300, True, 512),
+                                                 (17, True, 256), (129, False, 64)])
+def test_similarity_fused_vs_oracle(ov, cuda_device, classes, batched, dim):
+    from ovdet import ops
+    torch.manual_seed(classes + 1)
+    b = 3
+    shapes = [(20, 20), (10, 12), (4, 5)]       # 400 | 120 | 20 anchors: full, ragged and tiny tiles
+    embs = [torch.randn(b, dim, h, w) * (0.5 + l) for l, (h, w) in enumerate(shapes)]
+    embs[2][1, :, 1, 1] = 0.0                   # a zero vector: eps clamp, logit = beta
+    text = torch.randn(b, classes, dim) if batched else torch.randn(classes, dim).unsqueeze(0).expand(b, -1, -1)
+    alpha, beta = 1.7, -0.2
+    ref = torch.cat([ref_port.compute_similarity(e, text, alpha, beta).flatten(2).transpose(1, 2)
+                     for e in embs], dim=1)
+    dev_embs = [e.to(cuda_device) for e in embs]
+    assert ops.fused_supported(dev_embs)
+    top = ops.l2norm_text(text.to(cuda_device) if batched else text[0].to(cuda_device))
+    inv = torch.empty(b, ref.shape[1], device=cuda_device)
+    logits, rmax, rarg = ops.similarity_fused(dev_embs, top, alpha, beta, logits_dtype=torch.float32,
+                                              want_max=True, inv_norm=inv)
+    torch.cuda.synchronize()
+    assert_logits_close(logits, ref, "bf16", alpha)
+    m, a = logits.max(dim=-1)
+    assert torch.equal(rmax, m) and torch.equal(rarg.long(), a)
+    flat = torch.cat([e.flatten(2).transpose(1, 2) for e in embs], dim=1)
+    ref_inv = 1.0 / flat.norm(dim=-1).clamp_min(1e-12)
+    nz = flat.norm(dim=-1) > 0
+    torch.testing.assert_close(inv.cpu()[nz], ref_inv[nz], rtol=3e-6, atol=0)
+    # the two-kernel path computes the same bf16 products: near-identical logits
+    rop, inv2 = ops.l2norm_regions(dev_embs)
+    l2, _, _ = ops.similarity(rop, top, inv2, dim, alpha, beta, logits_dtype=torch.float32)
+    assert (logits - l2).abs().max() <= 2e-5 * max(1.0, abs(alpha))
+    # max-only launch gives the same answer
+    _, m0, a0 = ops.similarity_fused(dev_embs, top, alpha, beta, logits_dtype=None, want_max=True)
+    assert torch.equal(m0, rmax) and torch.equal(a0, rarg)
+
+
+def test_fused_unsupported_shape_is_an_error(ov, cuda_device):
+    from ovdet import ops
+    embs = [torch.randn(1, 64, 5, 5, device=cuda_device)]      # hw = 25: row stride not 16-byte aligned
+    assert not ops.fused_supported(embs)
+    top = ops.l2norm_text(torch.randn(3, 64, device=cuda_device))
+    with pytest.raises(ValueError):
+        ops.similarity_fused(embs, top)
