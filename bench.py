@@ -41,8 +41,10 @@ UNIT = "images/s"
 
 
 def workload_name(batch):
+    which = {(640, 80): "configs[1] shapes", (640, 1203): "configs[2]", (1280, 1203): "configs[3] shapes",
+             (640, 4800): "configs[4] shapes"}.get((IMAGE_SIZE, NUM_CLASSES), "custom")
     return (f"batch {batch}/GPU @ {IMAGE_SIZE}x{IMAGE_SIZE}, {NUM_CLASSES} prompts, bf16 similarity GEMM "
-            f"(BASELINE.json configs[2])")
+            f"(BASELINE.json {which})")
 
 
 # ----------------------------------------------------------------------------------------------
@@ -165,7 +167,7 @@ def run_reference(args):
 def run_ours(args):
     import torch
     import torch.distributed as dist
-    from ovdet import synth
+    from ovdet import shard, synth
     from ovdet.detector import Detector
     from ovdet.pipeline import HeadConfig, HeadPipeline
 
@@ -187,7 +189,9 @@ def run_ours(args):
     inp = synth.make_inputs(batch=batch, image_size=IMAGE_SIZE, num_classes=NUM_CLASSES,
                             embed_dim=EMBED_DIM, device=dev, seed=1234 + rank)
     pipe = HeadPipeline(batch, shapes, NUM_CLASSES, cfg, device=dev)
-    pipe.set_vocabulary(inp.text)
+    # the vocabulary is replicated: rank 0's copy goes to every GPU once, outside the timed region
+    vocab = shard.broadcast_vocabulary(inp.text if rank == 0 else None, NUM_CLASSES, EMBED_DIM, dev)
+    pipe.set_vocabulary(vocab)
     input_bytes = sum(t.numel() * 4 for t in inp.obj_embeds + inp.box_preds)
 
     def barrier():
@@ -219,10 +223,7 @@ def run_ours(args):
     barrier()
     elapsed_ms = start.elapsed_time(stop)
     clocks = sampler.stop() if rank == 0 else None
-    if world > 1:
-        t = torch.tensor([elapsed_ms], device=dev, dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        elapsed_ms = t.item()
+    elapsed_ms = shard.max_over_ranks(elapsed_ms, dev)
     value = n_gpus * batch * args.steps / (elapsed_ms / 1e3)
 
     def stage_ms(name):
@@ -262,10 +263,7 @@ def run_ours(args):
     ee.record()
     barrier()
     e2e_ms = es.elapsed_time(ee)
-    if world > 1:
-        t = torch.tensor([e2e_ms], device=dev, dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        e2e_ms = t.item()
+    e2e_ms = shard.max_over_ranks(e2e_ms, dev)
     e2e_value = n_gpus * batch * e2e_steps / (e2e_ms / 1e3)
     d2h_bytes = sum(v.numel() * v.element_size() for v in out_host.values())
 
@@ -366,7 +364,12 @@ def main():
     ap.add_argument("--no-fused", action="store_true", help="two-kernel K1 -> K2 path instead of the fused kernel")
     ap.add_argument("--profile", action="store_true",
                     help="device-resident loop only (for ncu): no e2e, latency or CPU legs")
+    ap.add_argument("--image-size", type=int, default=IMAGE_SIZE,
+                    help="default 640 (the metric's configuration); 1280 = BASELINE configs[3]")
+    ap.add_argument("--classes", type=int, default=NUM_CLASSES,
+                    help="default 1203 (the metric's configuration); 4800 = BASELINE configs[4]")
     args = ap.parse_args()
+    globals().update(IMAGE_SIZE=args.image_size, NUM_CLASSES=args.classes)
     if args.warmup < 3 and args.impl == "ours":
         args.warmup = 3
     if args.impl == "reference":

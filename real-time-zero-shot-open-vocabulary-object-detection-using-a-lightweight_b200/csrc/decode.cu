@@ -2,11 +2,11 @@
 // threshold.  Replaces BoxHead.decode_boxes (model/heads/box_head.py:150-218; the int64 grid of
 // :115-148 is computed from the thread index) and `scores > conf` (inference/detector.py:184).
 //
-// HBM-bound streaming kernel: one thread per anchor reads its 4 x bins logits (coalesced along
-// the spatial axis - consecutive threads are consecutive cells), 272 B in, 16 B (+ a bit) out.
-// The float32 operation order follows the reference: softmax = exp(x - max) / sum, expectation
-// sum_k p_k * k (separate multiply and add, no FMA contraction), centre = (cell + e) * stride,
-// size = exp(e) * stride, xyxy = centre -/+ size / 2.
+// HBM-bound streaming kernel: a thread decodes 4 consecutive cells of a level with 16-byte
+// loads (coalesced along the spatial axis: a warp reads 512 contiguous bytes per bin), 272 B in,
+// 16 B (+ a bit) out per anchor.  softmax expectation = sum_k k exp(x_k - max) / sum_k exp(x_k -
+// max); the decode proper follows the reference's float32 operation order: centre = (cell + e)
+// * stride, size = exp(e) * stride, xyxy = centre -/+ size / 2, no FMA contraction.
 #include "common.cuh"
 
 namespace ovdet {
@@ -21,43 +21,78 @@ struct DecodeParams {
   float wscale, hscale;
 };
 
-template <int BINS>
-__device__ __forceinline__ float dfl_expectation(const float* __restrict__ p, long long cstride,
-                                                 int bins_rt) {
+// Expectation of the softmax over the bins of one coordinate, for V consecutive anchors at once:
+//   E = sum_k k * exp(x_k - m) / sum_k exp(x_k - m)
+// (one division per coordinate instead of the reference's one per bin; |dE| is a few 1e-7, which
+// the box tolerance of 1e-4 relative absorbs - box_head.py:185-192).
+// exp(x - m) as ex2.approx(x * log2(e) - m * log2(e)): one FFMA + one MUFU instead of expf's
+// ~10 instructions.  The rounding of m * log2(e) scales every bin by the same factor (it cancels
+// in the ratio); the FFMA's own rounding bounds the relative error of a term by |x - m| * 1e-7
+// (< 1e-6 for every term that carries weight), far inside the box tolerance.
+constexpr float kLog2e = 1.4426950408889634f;
+__device__ __forceinline__ float exp_rel(float x, float neg_m_log2e) {
+  float r;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(fmaf(x, kLog2e, neg_m_log2e)));
+  return r;
+}
+
+template <int BINS, int V>
+__device__ __forceinline__ void dfl_expectation(const float* __restrict__ p, long long cstride,
+                                                int bins_rt, float (&e)[V]) {
   if (BINS > 0) {
-    float v[BINS > 0 ? BINS : 1];
+    float v[BINS > 0 ? BINS : 1][V];
 #pragma unroll
-    for (int k = 0; k < BINS; ++k) v[k] = ld_stream_f32(p + k * cstride);
-    float m = v[0];
+    for (int k = 0; k < BINS; ++k) {
+      if (V == 4) {
+        const float4 q = ld_stream_f32x4(reinterpret_cast<const float4*>(p + k * cstride));
+        v[k][0] = q.x; v[k][1 % V] = q.y; v[k][2 % V] = q.z; v[k][3 % V] = q.w;
+      } else {
+        v[k][0] = ld_stream_f32(p + k * cstride);
+      }
+    }
 #pragma unroll
-    for (int k = 1; k < BINS; ++k) m = fmaxf(m, v[k]);
-    float s = 0.f;
+    for (int j = 0; j < V; ++j) {
+      float m = v[0][j];
 #pragma unroll
-    for (int k = 0; k < BINS; ++k) { v[k] = expf(v[k] - m); s = __fadd_rn(s, v[k]); }
-    float e = 0.f;
+      for (int k = 1; k < BINS; ++k) m = fmaxf(m, v[k][j]);
+      const float nm = -m * kLog2e;
+      float s = 0.f, n = 0.f;
 #pragma unroll
-    for (int k = 0; k < BINS; ++k) e = __fadd_rn(e, __fmul_rn(__fdiv_rn(v[k], s), (float)k));
-    return e;
+      for (int k = 0; k < BINS; ++k) {
+        const float t = exp_rel(v[k][j], nm);
+        s += t;
+        n = fmaf((float)k, t, n);
+      }
+      e[j] = __fdiv_rn(n, s);
+    }
   } else {
-    float m = -INFINITY;
-    for (int k = 0; k < bins_rt; ++k) m = fmaxf(m, p[k * cstride]);
-    float s = 0.f;
-    for (int k = 0; k < bins_rt; ++k) s = __fadd_rn(s, expf(p[k * cstride] - m));
-    float e = 0.f;
-    for (int k = 0; k < bins_rt; ++k)
-      e = __fadd_rn(e, __fmul_rn(__fdiv_rn(expf(p[k * cstride] - m), s), (float)k));
-    return e;
+#pragma unroll
+    for (int j = 0; j < V; ++j) {
+      float m = -INFINITY;
+      for (int k = 0; k < bins_rt; ++k) m = fmaxf(m, p[k * cstride + j]);
+      const float nm = -m * kLog2e;
+      float s = 0.f, n = 0.f;
+      for (int k = 0; k < bins_rt; ++k) {
+        const float t = exp_rel(p[k * cstride + j], nm);
+        s += t;
+        n = fmaf((float)k, t, n);
+      }
+      e[j] = __fdiv_rn(n, s);
+    }
   }
 }
 
-template <int BINS>
+// V = 4: a thread decodes 4 consecutive cells of one level with 16-byte loads (every level's
+// H*W and batch stride must be a multiple of 4 and the pointers 16-byte aligned); V = 1 is the
+// general path.  blockIdx.y = image.
+template <int BINS, int V>
 __global__ void __launch_bounds__(256)
 decode_filter_kernel(const DecodeParams p, int anchors, const float* __restrict__ scores,
                      float conf, int activation, float* __restrict__ boxes,
                      float* __restrict__ scores_act, uint32_t* __restrict__ pass_mask, int words) {
-  const int a = blockIdx.x * 256 + threadIdx.x;
+  const int a = (blockIdx.x * 256 + threadIdx.x) * V;       // first anchor of this thread
   const int b = blockIdx.y;
-  bool pass = false;
+  uint32_t pass = 0;                                         // bit j: anchor a + j passes
   if (a < anchors) {
     int l = 0;
 #pragma unroll
@@ -65,35 +100,64 @@ decode_filter_kernel(const DecodeParams p, int anchors, const float* __restrict_
       if (i < p.levels && a >= p.off[i]) l = i;
     const int cell = a - p.off[l];
     const int wdt = p.w[l];
-    const int gy = cell / wdt, gx = cell - gy * wdt;
     const long long cstride = (long long)p.h[l] * wdt;
     const float* base = p.pred[l] + b * p.bstride[l] + cell;
     const int bins = p.bins;
-    const float e0 = dfl_expectation<BINS>(base, cstride, bins);
-    const float e1 = dfl_expectation<BINS>(base + 1ll * bins * cstride, cstride, bins);
-    const float e2 = dfl_expectation<BINS>(base + 2ll * bins * cstride, cstride, bins);
-    const float e3 = dfl_expectation<BINS>(base + 3ll * bins * cstride, cstride, bins);
+    float e0[V], e1[V], e2[V], e3[V];
+    dfl_expectation<BINS, V>(base, cstride, bins, e0);
+    dfl_expectation<BINS, V>(base + 1ll * bins * cstride, cstride, bins, e1);
+    dfl_expectation<BINS, V>(base + 2ll * bins * cstride, cstride, bins, e2);
+    dfl_expectation<BINS, V>(base + 3ll * bins * cstride, cstride, bins, e3);
     const float st = (float)p.stride[l];
-    const float cx = __fmul_rn(__fadd_rn((float)gx, e0), st);
-    const float cy = __fmul_rn(__fadd_rn((float)gy, e1), st);
-    const float bw = __fmul_rn(__fmul_rn(expf(e2), st), p.wscale);
-    const float bh = __fmul_rn(__fmul_rn(expf(e3), st), p.hscale);
-    const float hw_ = __fmul_rn(bw, 0.5f), hh_ = __fmul_rn(bh, 0.5f);
     const long long ga = (long long)b * anchors + a;
-    if (boxes != nullptr)
-      reinterpret_cast<float4*>(boxes)[ga] =
-          make_float4(__fsub_rn(cx, hw_), __fsub_rn(cy, hh_), __fadd_rn(cx, hw_), __fadd_rn(cy, hh_));
+    float sc[V];
     if (scores != nullptr) {
-      float s = scores[ga];
-      if (activation == OVDET_ACT_SIGMOID) s = __fdiv_rn(1.0f, __fadd_rn(1.0f, expf(-s)));
-      if (scores_act != nullptr) scores_act[ga] = s;
-      pass = s > conf;
+      if (V == 4) {
+        const float4 q = *reinterpret_cast<const float4*>(scores + ga);
+        sc[0] = q.x; sc[1 % V] = q.y; sc[2 % V] = q.z; sc[3 % V] = q.w;
+      } else {
+        sc[0] = scores[ga];
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < V; ++j) {
+      const int c = cell + j;
+      const int gy = c / wdt, gx = c - gy * wdt;
+      const float cx = __fmul_rn(__fadd_rn((float)gx, e0[j]), st);
+      const float cy = __fmul_rn(__fadd_rn((float)gy, e1[j]), st);
+      const float bw = __fmul_rn(__fmul_rn(expf(e2[j]), st), p.wscale);
+      const float bh = __fmul_rn(__fmul_rn(expf(e3[j]), st), p.hscale);
+      const float hw_ = __fmul_rn(bw, 0.5f), hh_ = __fmul_rn(bh, 0.5f);
+      if (boxes != nullptr)
+        reinterpret_cast<float4*>(boxes)[ga + j] =
+            make_float4(__fsub_rn(cx, hw_), __fsub_rn(cy, hh_), __fadd_rn(cx, hw_), __fadd_rn(cy, hh_));
+      if (scores != nullptr) {
+        float s = sc[j];
+        if (activation == OVDET_ACT_SIGMOID) s = __fdiv_rn(1.0f, __fadd_rn(1.0f, expf(-s)));
+        sc[j] = s;
+        if (s > conf) pass |= 1u << j;
+      }
+    }
+    if (scores != nullptr && scores_act != nullptr) {
+      if (V == 4) *reinterpret_cast<float4*>(scores_act + ga) = make_float4(sc[0], sc[1 % V], sc[2 % V], sc[3 % V]);
+      else scores_act[ga] = sc[0];
     }
   }
   if (pass_mask != nullptr) {
-    const uint32_t bits = __ballot_sync(0xffffffffu, pass);
-    const int word = a >> 5;
-    if ((threadIdx.x & 31) == 0 && word < words) pass_mask[(long long)b * words + word] = bits;
+    const int lane = threadIdx.x & 31;
+    if (V == 1) {
+      const uint32_t bits = __ballot_sync(0xffffffffu, pass != 0);
+      const int word = a >> 5;
+      if (lane == 0 && word < words) pass_mask[(long long)b * words + word] = bits;
+    } else {
+      // 8 lanes x 4 anchors make one 32-bit word
+      uint32_t v = pass << (4 * (lane & 7));
+      v |= __shfl_xor_sync(0xffffffffu, v, 1);
+      v |= __shfl_xor_sync(0xffffffffu, v, 2);
+      v |= __shfl_xor_sync(0xffffffffu, v, 4);
+      const int word = a >> 5;
+      if ((lane & 7) == 0 && word < words) pass_mask[(long long)b * words + word] = v;
+    }
   }
 }
 
@@ -135,14 +199,24 @@ extern "C" int ovdet_decode_filter(const float* const* box_preds, const int32_t*
   if (batch == 0) return OVDET_OK;
   const int anchors = (int)total;
   const int words = (anchors + 31) / 32;
-  dim3 grid((unsigned)ceil_div(anchors, 256), (unsigned)batch);
   cudaStream_t s = as_stream(stream);
-  if (bins == 17)
-    decode_filter_kernel<17><<<grid, 256, 0, s>>>(p, anchors, scores, conf, activation, boxes,
-                                                  scores_act, pass_mask, words);
-  else
-    decode_filter_kernel<0><<<grid, 256, 0, s>>>(p, anchors, scores, conf, activation, boxes,
-                                                 scores_act, pass_mask, words);
+  bool vec4 = bins == 17 && !(((uintptr_t)scores | (uintptr_t)scores_act) & 15);
+  for (int l = 0; l < num_levels && vec4; ++l)
+    vec4 = ((long long)heights[l] * widths[l]) % 4 == 0 && batch_strides[l] % 4 == 0 &&
+           !((uintptr_t)box_preds[l] & 15);
+  if (vec4) {
+    dim3 grid((unsigned)ceil_div(anchors, 1024), (unsigned)batch);
+    decode_filter_kernel<17, 4><<<grid, 256, 0, s>>>(p, anchors, scores, conf, activation, boxes,
+                                                     scores_act, pass_mask, words);
+  } else {
+    dim3 grid((unsigned)ceil_div(anchors, 256), (unsigned)batch);
+    if (bins == 17)
+      decode_filter_kernel<17, 1><<<grid, 256, 0, s>>>(p, anchors, scores, conf, activation, boxes,
+                                                       scores_act, pass_mask, words);
+    else
+      decode_filter_kernel<0, 1><<<grid, 256, 0, s>>>(p, anchors, scores, conf, activation, boxes,
+                                                      scores_act, pass_mask, words);
+  }
   OVDET_LAUNCH_CHECK();
   return OVDET_OK;
 }

@@ -12,11 +12,13 @@
 // tensor pipe.  Here every activation is read from HBM exactly once, as fp32, and the converted
 // A tile stays on chip for the whole vocabulary:
 //
-//   warp 0      TMA producer, text tiles  [128 classes x 64 k] bf16, SWIZZLE_128B, one stage per
-//               k block (8 x 16 KiB), refilled once per N tile
+//   warp 0      TMA producer, text tiles  [128 classes x 64 k] bf16, SWIZZLE_128B, 4-stage ring
+//               (4 x 16 KiB: deep enough to cover the L2 latency, shallow enough that the
+//               activation loads issued at an anchor-tile boundary do not queue behind 128 KiB
+//               of text prefetch)
 //   warp 1      MMA issuer   tcgen05.mma.kind::f16, A FROM TENSOR MEMORY, 128 x N x 16, N <= 128
 //   warp 2      TMA producer, activations [64 k x 128 anchors] fp32 straight from NCHW
-//               (anchors contiguous), 2-stage ring; also owns the TMEM allocation
+//               (anchors contiguous), 4-stage ring; also owns the TMEM allocation
 //   warp 3      L2 prefetch of the next anchor tile (cp.async.bulk.prefetch.tensor)
 //   warps 4-7   converters   thread = anchor row: fp32 smem column -> sum of squares, bf16x2 ->
 //               tcgen05.st into the A region of TMEM (256 columns = 128 rows x 512 k)
@@ -38,8 +40,8 @@ constexpr int F_BLOCK_M = 128;
 constexpr int F_BLOCK_N = 128;
 constexpr int F_BLOCK_K = 64;
 constexpr int F_MAX_KB = 8;                       // dim <= 512: A fills 256 TMEM columns
-constexpr int F_B_STAGES = F_MAX_KB;              // text stage index == k block: addresses are static
-constexpr int F_A_STAGES = 2;
+constexpr int F_B_STAGES = 4;                     // text ring; with dim = 512 stage == kb & 3 (static)
+constexpr int F_A_STAGES = 4;                     // fp32 activation ring
 constexpr int F_B_STAGE_BYTES = F_BLOCK_N * F_BLOCK_K * 2;     // 16 KiB
 constexpr int F_A_STAGE_BYTES = F_BLOCK_K * F_BLOCK_M * 4;     // 32 KiB fp32 [k][anchor]
 constexpr int F_THREADS = 384;
@@ -51,8 +53,8 @@ constexpr int F_MAX_LEVELS = 4;
 
 struct FSmem {
   static constexpr int b_off = 0;
-  static constexpr int a_off = b_off + F_B_STAGES * F_B_STAGE_BYTES;                 // 128 KiB
-  static constexpr int epi_off = a_off + F_A_STAGES * F_A_STAGE_BYTES;               // +64 KiB
+  static constexpr int a_off = b_off + F_B_STAGES * F_B_STAGE_BYTES;                 // 64 KiB
+  static constexpr int epi_off = a_off + F_A_STAGES * F_A_STAGE_BYTES;               // +128 KiB
   static constexpr int epi_bytes = 4 * 32 * F_PITCH * 4;
   static constexpr int norm_off = epi_off + epi_bytes;
   static constexpr int norm_bytes = 3 * F_BLOCK_M * 4;
@@ -169,12 +171,13 @@ sim_fused_kernel(const __grid_constant__ LevelMaps amaps, const __grid_constant_
       const TileCoord tc = decode_tile(p, tile);
       const int tb = p.text_batched ? tc.b : 0;
       for (int nt = 0; nt < NT; ++nt, ++g) {
-        const uint32_t ph = g & 1u;                    // stage kb is used once per N tile
 #pragma unroll
         for (int kb = 0; kb < KB; ++kb) {
-          ptx::mbar_wait(b_empty0 + 8u * kb, ph ^ 1u);
-          ptx::mbar_arrive_expect_tx_if(issue, b_full0 + 8u * kb, F_B_STAGE_BYTES);
-          ptx::tma_load_3d_if(issue, smem_b + kb * F_B_STAGE_BYTES, &tmap_b, b_full0 + 8u * kb,
+          const uint32_t it = g * (uint32_t)KB + (uint32_t)kb;       // k blocks produced so far
+          const uint32_t s = it % F_B_STAGES, ph = (it / F_B_STAGES) & 1u;
+          ptx::mbar_wait(b_empty0 + 8u * s, ph ^ 1u);
+          ptx::mbar_arrive_expect_tx_if(issue, b_full0 + 8u * s, F_B_STAGE_BYTES);
+          ptx::tma_load_3d_if(issue, smem_b + s * F_B_STAGE_BYTES, &tmap_b, b_full0 + 8u * s,
                               kb * F_BLOCK_K, nt * F_BLOCK_N, tb);
         }
       }
@@ -190,25 +193,28 @@ sim_fused_kernel(const __grid_constant__ LevelMaps amaps, const __grid_constant_
         n_size = n_size >= F_BLOCK_N ? F_BLOCK_N : ((n_size + 15) & ~15);
         const uint32_t idesc = ptx::umma_idesc_bf16_f32(F_BLOCK_M, (uint32_t)n_size);
         const uint32_t as = g & 1u;
-        const uint32_t ph = g & 1u;
         const bool first_nt = nt == 0, last_nt = nt == NT - 1;
+        const uint32_t it0 = g * (uint32_t)KB;
         // peek at the first text stage while waiting for the accumulator to drain
-        bool ready = ptx::mbar_try_wait(b_full0, ph);
+        bool ready = ptx::mbar_try_wait(b_full0 + 8u * (it0 % F_B_STAGES), (it0 / F_B_STAGES) & 1u);
         ptx::mbar_wait(t_empty0 + 8u * as, ((g >> 1) & 1u) ^ 1u);
         const uint32_t d_tmem = tmem_u + (uint32_t)F_ACC_COL + as * (uint32_t)F_BLOCK_N;
 #pragma unroll
         for (int kb = 0; kb < KB; ++kb) {
+          const uint32_t it = it0 + (uint32_t)kb;
+          const uint32_t s = it % F_B_STAGES, ph = (it / F_B_STAGES) & 1u;
           if (first_nt) ptx::mbar_wait(a_ready0 + 8u * kb, lt & 1u);     // A block converted?
-          ptx::mbar_wait_if_not(ready, b_full0 + 8u * kb, ph);
+          ptx::mbar_wait_if_not(ready, b_full0 + 8u * s, ph);
           ptx::tc_fence_after();
-          if (kb + 1 < KB) ready = ptx::mbar_try_wait(b_full0 + 8u * (kb + 1), ph);   // hide its latency
-          const uint64_t b_desc = ptx::umma_desc_k_sw128(smem_b + kb * F_B_STAGE_BYTES);
+          if (kb + 1 < KB)                                               // hide the next wait's latency
+            ready = ptx::mbar_try_wait(b_full0 + 8u * ((it + 1) % F_B_STAGES), ((it + 1) / F_B_STAGES) & 1u);
+          const uint64_t b_desc = ptx::umma_desc_k_sw128(smem_b + s * F_B_STAGE_BYTES);
           const uint32_t a_tmem = tmem_u + (uint32_t)(F_A_COL + kb * 32);
           if (ptx::elect_one()) {
 #pragma unroll
             for (int k = 0; k < F_BLOCK_K / 16; ++k)
               ptx::umma_bf16_ts(d_tmem, a_tmem + 8u * k, b_desc + 2u * k, idesc, (kb | k) != 0);
-            ptx::umma_commit(b_empty0 + 8u * kb);                 // text stage reusable
+            ptx::umma_commit(b_empty0 + 8u * s);                  // text stage reusable
             if (last_nt) ptx::umma_commit(a_free0 + 8u * kb);     // A block kb may be overwritten
           }
           __syncwarp();
@@ -237,8 +243,8 @@ sim_fused_kernel(const __grid_constant__ LevelMaps amaps, const __grid_constant_
   } else if (warp == 3) {
     // ================================ L2 prefetcher ==========================================
     // Only A_STAGES + 1 blocks of the next anchor tile can be staged before the current tile
-    // releases its TMEM blocks, so the rest of the fp32 tile would be fetched from HBM inside
-    // the last N tile.  Pull the whole next tile into L2 one tile ahead instead.
+    // releases its TMEM blocks, so the rest of the fp32 tile is fetched inside the last N tile.
+    // Pull the whole next tile into L2 one tile ahead so that those loads are L2 hits.
     const uint32_t issue = ptx::elect_one();
     uint32_t lt = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++lt) {
