@@ -107,6 +107,22 @@ def measured_peaks():
     return {"tflops": 1400.0, "tflops_burst": 1590.0, "hbm_gbs": 6650.0, "source": "fallback"}
 
 
+def ncu_traffic(kernel_substr: str, batch: int):
+    """DRAM bytes per launch (dram__bytes_read.sum + dram__bytes_write.sum) of the dominant kernel
+    from the committed `ncu --set full` capture of this same workload (profiles/, batch 256);
+    None when the run's shape differs from the captured one."""
+    path = os.path.join(ROOT, "profiles", "r1_ncu_full_pipeline_b256_v3.json")
+    if batch != 256 or (IMAGE_SIZE, NUM_CLASSES) != (640, 1203) or not os.path.exists(path):
+        return None
+    scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+    with open(path) as f:
+        for rec in json.load(f)["launches"]:
+            if kernel_substr in rec["kernel"]:
+                rd, wr = rec["dram__bytes_read.sum"], rec["dram__bytes_write.sum"]
+                return rd["value"] * scale[rd["unit"]] + wr["value"] * scale[wr["unit"]]
+    return None
+
+
 # ----------------------------------------------------------------------------------------------
 # reference CPU arm / cpu_baseline leg (the only places that execute oracle/)
 # ----------------------------------------------------------------------------------------------
@@ -333,7 +349,10 @@ def run_ours(args):
             "gpu_launches": launches * args.steps,
             "roofline": {"bound": "tensor", "kernel": kernel, "achieved": achieved,
                          "peak": peaks["tflops"], "unit": "TFLOP/s", "frac": achieved / peaks["tflops"],
-                         "traffic": None, "peak_source": peaks["source"] + " (bf16_tflops_sustained)",
+                         "traffic": ncu_traffic("sim_fused" if fused else "sim_gemm", batch),
+                         "traffic_source": "profiles/r1_ncu_full_pipeline_b256_v3.json (ncu --set full, bytes per launch)",
+                         "algorithmic_bytes": batch * anchors * (EMBED_DIM * 4 + 12) + NUM_CLASSES * EMBED_DIM * 2,
+                         "peak_source": peaks["source"] + " (bf16_tflops_sustained)",
                          "ms_per_launch": stages["similarity"]},
             "stages_ms": stages,
             "stage_rooflines": {

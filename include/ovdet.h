@@ -197,6 +197,30 @@ OVDET_API int ovdet_nms_batched(const float* boxes, const float* scores, const i
                       int32_t* out_candidates, void* workspace, size_t workspace_bytes,
                       void* stream);
 
+/* ------------------------------------------------------------------------------------------
+ * P1  letterbox pre-processing ("next" row f-4 of SURVEY.md section 8).
+ * Replaces: inference/detector.py:139-156 - cv2.resize(image, (resized_w, resized_h)) with the
+ *           default INTER_LINEAR, paste at the top-left of a zero canvas, astype(float32) / 255,
+ *           HWC -> CHW.  Bit-exact with OpenCV's 8-bit fixed-point bilinear resize (including
+ *           the 2x-decimation INTER_AREA fast path cv::resize switches to).
+ *
+ *   images      HOST array of `count` DEVICE pointers, image i is uint8 [heights[i], widths[i], 3]
+ *               (RGB, interleaved) with rows row_strides[i] BYTES apart
+ *   resized_h/w HOST arrays: size of the resized image, int(orig * scale) as the caller computed it
+ *               (detector.py:141-142); must fit the canvas
+ *   out         fp32 [count, 3, out_h, out_w]
+ * ---------------------------------------------------------------------------------------- */
+OVDET_API int ovdet_letterbox_u8(const uint8_t* const* images, const int32_t* heights,
+                                 const int32_t* widths, const int64_t* row_strides,
+                                 const int32_t* resized_h, const int32_t* resized_w, int count,
+                                 int out_h, int out_w, float* out, void* stream);
+
+/* P2  int-truncated boxes of the kept detections (detector.py:216: boxes[i].astype(int)).
+ *   boxes fp32 [batch, max_det, 4] and count int32 [batch] as written by ovdet_nms_batched;
+ *   out int32 [batch, max_det, 4], rows >= count[b] are zero.  Both 16-byte aligned. */
+OVDET_API int ovdet_pack_boxes_i32(const float* boxes, const int32_t* count, int64_t batch,
+                                   int64_t max_det, int32_t* out, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -183,6 +183,63 @@ def forward_tail_case():
     save("forward_tail_64", **arrays)
 
 
+def preprocess_cases():
+    """Reference YOLOCLIPDetector.preprocess_image (live cv2.resize) on seeded uint8 images:
+    up-scaling, down-scaling, an exact 2x decimation and a 1:1 copy; small canvases keep the
+    fixture small.  Also checks the numpy restatement of cv2.resize on 300 random shapes."""
+    import cv2
+    from oracle import ref_port
+    rng = np.random.default_rng(15)
+    cases = {"up": ((37, 53), (64, 64)), "down": ((150, 91), (64, 64)), "half": ((128, 96), (64, 64)),
+             "same": ((64, 40), (64, 64)), "wide": ((45, 301), (96, 160))}
+    arrays = {}
+    for name, ((h, w), size) in cases.items():
+        img = rng.integers(0, 256, (h, w, 3), dtype=np.uint8)
+        det = _bare_detector(image_size=size)
+        det.device = "cpu"
+        tensor, orig, scale = det.preprocess_image(img)
+        arrays[f"{name}_img"] = img
+        arrays[f"{name}_out"] = tensor.numpy()
+        arrays[f"{name}_meta"] = np.array([size[0], size[1], scale], dtype=np.float64)
+        got, _, s2 = ref_port.preprocess_image(img, size)
+        assert s2 == scale and np.array_equal(got.numpy(), tensor.numpy()), name
+    save("preprocess_cases", **arrays)
+    bad = 0
+    for t in range(300):
+        sh, sw = (int(v) for v in rng.integers(2, 900, 2))
+        if t % 10 == 0:
+            sh, sw = 2 * int(rng.integers(2, 300)), 2 * int(rng.integers(2, 300))
+            dh, dw = sh // 2, sw // 2
+        else:
+            _, dh, dw = ref_port.letterbox_geometry(sh, sw, (640, 640))
+            if dh < 1 or dw < 1:
+                continue
+        img = rng.integers(0, 256, (sh, sw, 3), dtype=np.uint8)
+        bad += not np.array_equal(cv2.resize(img, (dw, dh)), ref_port.cv2_resize_linear_u8(img, dw, dh))
+    assert bad == 0, f"{bad} resize mismatches against the installed cv2"
+    print("cv2.resize restatement: 300 random shapes bit-exact")
+
+
+def vocabulary_case():
+    """Reference VocabBuilder.build_offline_vocabulary -> JSON file (stub CLIP encoder), and the
+    matrix YOLOCLIP.load_offline_vocabulary stacks from it."""
+    import json
+    import tempfile
+    torch.manual_seed(16)
+    names = ["traffic light", "person", "zebra"]
+    model = YOLOCLIP(backbone_variant="n", num_classes=3, offline_mode=True).eval()
+    with tempfile.TemporaryDirectory() as tmp:
+        path = os.path.join(tmp, "v", "vocab.json")
+        model.set_offline_vocabulary(names, save_path=path)
+        model2 = YOLOCLIP(backbone_variant="n", num_classes=3, offline_mode=True).eval()
+        model2.load_offline_vocabulary(path)
+        with open(path) as f:
+            text = f.read()
+    with open(os.path.join(OUT, "vocab_3cls.json"), "w") as f:
+        f.write(text)
+    save("vocab_3cls", matrix=model2.offline_vocabulary.cpu().numpy(), names=np.array(names))
+
+
 if __name__ == "__main__":
     os.makedirs(OUT, exist_ok=True)
     similarity_cases()
@@ -190,3 +247,5 @@ if __name__ == "__main__":
     nms_cases()
     postprocess_case()
     forward_tail_case()
+    preprocess_cases()
+    vocabulary_case()

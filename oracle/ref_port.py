@@ -232,3 +232,86 @@ def postprocess_batch(outputs: Dict[str, torch.Tensor], orig_sizes, scale_factor
         scale = scale_factors[i] if isinstance(scale_factors, (tuple, list, np.ndarray)) else scale_factors
         results.append(postprocess_image(boxes[i], scores[i], class_ids[i], tuple(size), float(scale), **kw))
     return results
+
+
+# --------------------------------------------------------------------------------------
+# "Next" rows: pre-processing, result records, vocabulary format
+# --------------------------------------------------------------------------------------
+def cv2_resize_linear_u8(src: np.ndarray, dst_w: int, dst_h: int) -> np.ndarray:
+    """``cv2.resize(src, (dst_w, dst_h))`` for uint8 HWC input with the default INTER_LINEAR.
+
+    Third-party algorithm: OpenCV (``opencv-python``; the reference's requirements.txt leaves
+    it unpinned, 4.13.0 is installed) ``modules/imgproc/src/resize.cpp``: fixed-point bilinear
+    interpolation with INTER_RESIZE_COEF_BITS = 11 (``HResizeLinear`` / ``VResizeLinear``), and
+    ``cv::resize`` switching to the INTER_AREA fast path for an exact 2x decimation.  OpenCV is
+    not part of /root/reference; this restatement is pinned against the installed cv2 by
+    ``oracle/make_golden.py`` (300 random shapes, bit-exact) and by the committed fixtures.
+    Call site in the reference: inference/detector.py:144.
+    """
+    sh, sw = src.shape[:2]
+    if sw == 2 * dst_w and sh == 2 * dst_h:                       # is_area_fast, iscale == 2
+        s = src.astype(np.int32)
+        out = (s[0::2, 0::2] + s[0::2, 1::2] + s[1::2, 0::2] + s[1::2, 1::2] + 2) >> 2
+        return out.astype(np.uint8)
+    scale_x = 1.0 / (dst_w / sw)
+    scale_y = 1.0 / (dst_h / sh)
+
+    def coeffs(dn, sn, scale, clamp_frac):
+        d = np.arange(dn, dtype=np.float64)
+        f = ((d + 0.5) * scale - 0.5).astype(np.float32)
+        s = np.floor(f).astype(np.int32)
+        f = (f - s.astype(np.float32)).astype(np.float32)
+        if clamp_frac:                                            # columns: fx = 0 at the borders
+            lo, hi = s < 0, s >= sn - 1
+            f[lo], s[lo] = 0, 0
+            f[hi], s[hi] = 0, sn - 1
+        a0 = np.rint((np.float32(1.0) - f) * np.float32(2048)).astype(np.int32)
+        a1 = np.rint(f * np.float32(2048)).astype(np.int32)
+        return np.clip(s, 0, sn - 1), np.clip(s + 1, 0, sn - 1), a0, a1
+
+    sx0, sx1, ax0, ax1 = coeffs(dst_w, sw, scale_x, True)
+    sy0, sy1, ay0, ay1 = coeffs(dst_h, sh, scale_y, False)        # rows: indices clamp, fy stays
+    s = src.astype(np.int32)
+    rows = s[:, sx0, :] * ax0[None, :, None] + s[:, sx1, :] * ax1[None, :, None]
+    r0, r1 = rows[sy0], rows[sy1]
+    out = (((ay0[:, None, None] * (r0 >> 4)) >> 16) + ((ay1[:, None, None] * (r1 >> 4)) >> 16) + 2) >> 2
+    return np.clip(out, 0, 255).astype(np.uint8)
+
+
+def letterbox_geometry(orig_h: int, orig_w: int, image_size: Tuple[int, int]) -> Tuple[float, int, int]:
+    """inference/detector.py:139-142: scale factor (python float) and resized size."""
+    input_h, input_w = image_size
+    scale_factor = min(input_h / orig_h, input_w / orig_w)
+    return scale_factor, int(orig_h * scale_factor), int(orig_w * scale_factor)
+
+
+def preprocess_image(image: np.ndarray, image_size: Tuple[int, int] = (640, 640)):
+    """inference/detector.py:119-161 for an RGB uint8 HWC array: returns the ``[1, 3, H, W]``
+    float32 tensor, the original image and the scale factor."""
+    orig_h, orig_w = image.shape[:2]
+    input_h, input_w = image_size
+    scale_factor, rh, rw = letterbox_geometry(orig_h, orig_w, image_size)
+    resized = cv2_resize_linear_u8(image, rw, rh)                              # :144
+    canvas = np.zeros((input_h, input_w, 3), dtype=np.uint8)                    # :147
+    canvas[:rh, :rw, :] = resized                                               # :150
+    canvas = canvas.astype(np.float32) / 255.0                                  # :153
+    canvas = canvas.transpose(2, 0, 1)                                          # :156
+    return torch.from_numpy(np.ascontiguousarray(canvas)).unsqueeze(0), image.copy(), scale_factor
+
+
+def load_offline_vocabulary(path: str) -> Tuple[List[str], torch.Tensor]:
+    """clip/vocab_builder.py:110-130 + model/yolo_clip.py:244-263: JSON ``{class_name:
+    [floats]}`` -> class names in file order and the stacked ``[C, D]`` float32 matrix."""
+    import json
+    with open(path, "r") as f:
+        vocab = json.load(f)
+    names = list(vocab.keys())
+    return names, torch.stack([torch.tensor(vocab[n]) for n in names])
+
+
+def save_offline_vocabulary(path: str, class_names: Sequence[str], embeddings: torch.Tensor) -> None:
+    """clip/vocab_builder.py:90-104: ``json.dump({name: embedding.tolist()})``."""
+    import json
+    save = {n: embeddings[i].cpu().numpy().tolist() for i, n in enumerate(class_names)}
+    with open(path, "w") as f:
+        json.dump(save, f)

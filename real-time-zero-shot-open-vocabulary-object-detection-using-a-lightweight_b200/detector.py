@@ -34,7 +34,7 @@ class Detector:
 
     def __init__(self, class_names: Optional[Sequence[str]] = None, conf_threshold: float = 0.25,
                  iou_threshold: float = 0.45, image_size: Tuple[int, int] = (640, 640),
-                 device: str = "cuda:0", config: Optional[HeadConfig] = None):
+                 device: str = "cuda:0", config: Optional[HeadConfig] = None, feature_fn=None):
         self.class_names = list(class_names) if class_names is not None else None
         self.conf_threshold = conf_threshold
         self.iou_threshold = iou_threshold
@@ -44,6 +44,7 @@ class Detector:
         self._pipelines: Dict[tuple, HeadPipeline] = {}
         self._vocabulary: Optional[torch.Tensor] = None
         self._host_state = None
+        self.feature_fn = feature_fn
 
     # ---- reference: YOLOCLIPDetector._nms (detector.py:225-256) ---------------------------
     def _nms(self, boxes: ArrayLike, scores: ArrayLike, iou_threshold: float) -> List[int]:
@@ -89,18 +90,63 @@ class Detector:
         return self.to_records(res, 0)
 
     def to_records(self, res: ops.NmsResult, image: int) -> List[Dict]:
-        """detector.py:213-221: the detection dicts of one image."""
+        """detector.py:213-221: the detection dicts of one image (``box`` truncated to int on
+        the device, one D2H copy per field)."""
         k = int(res.count[image].item())
-        boxes = res.boxes[image, :k].cpu().numpy()
+        boxes = ops.pack_boxes_i32(res.boxes, res.count)[image, :k].cpu().numpy()
         scores = res.scores[image, :k].cpu().numpy()
         classes = res.classes[image, :k].cpu().numpy()
         records = []
         for i in range(k):
             cid = int(classes[i])
             name = self.class_names[cid] if self.class_names is not None else f"Class {cid}"
-            records.append({"box": boxes[i].astype(int).tolist(), "score": float(scores[i]),
+            records.append({"box": boxes[i].tolist(), "score": float(scores[i]),
                             "class_id": cid, "class_name": name})
         return records
+
+    # ---- reference: YOLOCLIPDetector.preprocess_image (detector.py:119-161) -----------------
+    def preprocess_image(self, image: Union[str, ArrayLike]):
+        """Letterbox one image: path or RGB uint8 ``[H, W, 3]`` array / tensor -> (``[1, 3, H, W]``
+        fp32 tensor on the device, the original image, scale factor).  Decoding a file stays on
+        the host (cv2, like the reference); resize / pad / normalise / transpose run in P1."""
+        if isinstance(image, str):
+            import cv2                                   # host image decode only (detector.py:133-134)
+            image = cv2.cvtColor(cv2.imread(image), cv2.COLOR_BGR2RGB)
+        orig = image
+        dev_img = _to_device(image, self.device, torch.uint8)
+        tensor, scales = ops.letterbox([dev_img], self.image_size)
+        if isinstance(orig, np.ndarray):
+            orig = orig.copy()
+        return tensor, orig, scales[0]
+
+    def preprocess_batch(self, images: Sequence[ArrayLike]):
+        """``preprocess_image`` for a list of images of any sizes in one launch: returns the
+        ``[N, 3, H, W]`` batch, the (height, width) of every original and the scale factors."""
+        dev = [_to_device(im, self.device, torch.uint8) for im in images]
+        tensor, scales = ops.letterbox(dev, self.image_size)
+        return tensor, [(int(im.shape[0]), int(im.shape[1])) for im in dev], scales
+
+    # ---- reference: YOLOCLIPDetector.detect (detector.py:289-325) ---------------------------
+    def detect(self, image: Union[str, ArrayLike], text_prompts=None) -> List[Dict]:
+        """preprocess -> model -> post-process for one image, like the reference.  The
+        convolutional model (backbone, neck, head convolutions: out of scope here, SURVEY.md
+        section 2) is the callable given as ``feature_fn``: it maps the ``[1, 3, H, W]`` tensor
+        (and the prompts) to ``(obj_embeds, box_preds, text_embeddings)``."""
+        if self.feature_fn is None:
+            raise RuntimeError("ovdet: Detector.detect needs a feature_fn (the convolutional model)")
+        tensor, orig, scale = self.preprocess_image(image)
+        h, w = orig.shape[:2]
+        with torch.no_grad():
+            obj_embeds, box_preds, text = self.feature_fn(tensor, text_prompts)
+        res = self.predict(obj_embeds, box_preds, text, [(h, w)], [scale])
+        return self.to_records(res, 0)
+
+    def load_offline_vocabulary(self, path: str) -> None:
+        """model/yolo_clip.py:244-263: read the JSON vocabulary; class names come from it."""
+        from .vocabulary import Vocabulary
+        vocab = Vocabulary.load(path)
+        self.class_names = vocab.class_names
+        self.set_vocabulary(vocab.embeddings)
 
     # ---- predict: conv outputs -> detections (detect.py:121-125 -> detector.py:310-319) -----
     def pipeline_for(self, obj_embeds: Sequence[torch.Tensor], num_classes: int,

@@ -338,3 +338,64 @@ def nms_batched(boxes: torch.Tensor, scores: torch.Tensor, classes: Optional[tor
                                       out.candidates.data_ptr(), workspace.data_ptr(),
                                       workspace.numel(), _stream(boxes)), "ovdet_nms_batched")
     return out
+
+
+# --------------------------------------------------------------------------------------------
+# P1 / P2: letterbox pre-processing and int-truncated box records ("next" rows)
+# --------------------------------------------------------------------------------------------
+def letterbox_geometry(orig_h: int, orig_w: int, image_size: Tuple[int, int]) -> Tuple[float, int, int]:
+    """inference/detector.py:139-142 (python-float arithmetic, as the reference does it)."""
+    input_h, input_w = image_size
+    scale_factor = min(input_h / orig_h, input_w / orig_w)
+    return scale_factor, int(orig_h * scale_factor), int(orig_w * scale_factor)
+
+
+def letterbox(images: Sequence[torch.Tensor], image_size: Tuple[int, int] = (640, 640),
+              out: Optional[torch.Tensor] = None) -> Tuple[torch.Tensor, List[float]]:
+    """inference/detector.py:139-156 for a list of uint8 ``[H, W, 3]`` RGB CUDA tensors (any
+    sizes): bilinear resize exactly as cv2.resize does it, top-left paste on a zero canvas,
+    /255, HWC -> CHW.  Returns the ``[N, 3, H, W]`` fp32 batch and the per-image scale factors."""
+    n = len(images)
+    out_h, out_w = image_size
+    dev = images[0].device
+    keep, scales, rhs, rws = [], [], [], []
+    for im in images:
+        _require_cuda(im, "image", torch.uint8)
+        if im.dim() != 3 or im.shape[2] != 3:
+            raise ValueError("ovdet: images must be uint8 [H, W, 3]")
+        if im.stride(2) != 1 or im.stride(1) != 3:
+            im = im.contiguous()
+        keep.append(im)
+        s, rh, rw = letterbox_geometry(im.shape[0], im.shape[1], image_size)
+        if rh < 1 or rw < 1:
+            raise ValueError("ovdet: image collapses to zero size on the canvas")
+        scales.append(s)
+        rhs.append(rh)
+        rws.append(rw)
+    if out is None:
+        out = torch.empty(n, 3, out_h, out_w, device=dev, dtype=torch.float32)
+    assert out.shape == (n, 3, out_h, out_w) and out.is_contiguous() and out.dtype == torch.float32
+    ptrs = (ctypes.c_void_p * n)(*[im.data_ptr() for im in keep])
+    hs = (ctypes.c_int32 * n)(*[im.shape[0] for im in keep])
+    ws = (ctypes.c_int32 * n)(*[im.shape[1] for im in keep])
+    st = (ctypes.c_int64 * n)(*[im.stride(0) for im in keep])
+    with torch.cuda.device(dev):
+        check(lib().ovdet_letterbox_u8(ptrs, hs, ws, st, (ctypes.c_int32 * n)(*rhs),
+                                       (ctypes.c_int32 * n)(*rws), n, out_h, out_w, out.data_ptr(),
+                                       torch.cuda.current_stream(dev).cuda_stream), "ovdet_letterbox_u8")
+    return out, scales
+
+
+def pack_boxes_i32(boxes: torch.Tensor, count: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """detector.py:216 ``boxes[i].astype(int)`` for the kept rows of an ``NmsResult``:
+    ``boxes [B, max_det, 4]`` fp32 -> int32 (toward zero); rows past ``count[b]`` are zero."""
+    _require_cuda(boxes, "boxes", torch.float32)
+    _require_cuda(count, "count", torch.int32)
+    batch, max_det, _ = boxes.shape
+    assert boxes.is_contiguous() and count.shape == (batch,)
+    if out is None:
+        out = torch.empty(batch, max_det, 4, device=boxes.device, dtype=torch.int32)
+    with torch.cuda.device(boxes.device):
+        check(lib().ovdet_pack_boxes_i32(boxes.data_ptr(), count.data_ptr(), batch, max_det,
+                                         out.data_ptr(), _stream(boxes)), "ovdet_pack_boxes_i32")
+    return out

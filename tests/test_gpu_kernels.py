@@ -445,3 +445,87 @@ def test_fused_unsupported_shape_is_an_error(ov, cuda_device):
     top = ops.l2norm_text(torch.randn(3, 64, device=cuda_device))
     with pytest.raises(ValueError):
         ops.similarity_fused(embs, top)
+
+
+# ------------------------------------------------------------------------------------------
+# P1 / P2 ("next" rows): letterbox pre-processing and int-truncated records
+# ------------------------------------------------------------------------------------------
+def test_letterbox_golden_bit_exact(ov, cuda_device, golden_dir):
+    from ovdet.detector import Detector
+    g = _load(golden_dir, "preprocess_cases")
+    for name in ("up", "down", "half", "same", "wide"):
+        h, w, scale = g[f"{name}_meta"]
+        det = Detector(image_size=(int(h), int(w)), device=str(cuda_device))
+        tensor, orig, s = det.preprocess_image(g[f"{name}_img"])
+        assert s == scale and tensor.shape == (1, 3, int(h), int(w))
+        np.testing.assert_array_equal(tensor.cpu().numpy(), g[f"{name}_out"])
+        np.testing.assert_array_equal(orig, g[f"{name}_img"])
+
+
+def test_letterbox_batch_vs_oracle_bit_exact(ov, cuda_device):
+    from ovdet import ops
+    rng = np.random.default_rng(21)
+    shapes = [(480, 640), (1280, 1280), (375, 500), (1, 9), (2000, 31), (640, 640), (90, 1300)]
+    shapes += [tuple(int(v) for v in rng.integers(2, 1500, 2)) for _ in range(14)]   # > 16: two launches
+    imgs = [rng.integers(0, 256, (h, w, 3), dtype=np.uint8) for h, w in shapes]
+    out, scales = ops.letterbox([torch.from_numpy(i).to(cuda_device) for i in imgs], (640, 640))
+    torch.cuda.synchronize()
+    for i, img in enumerate(imgs):
+        want, _, s = ref_port.preprocess_image(img, (640, 640))
+        assert s == scales[i]
+        np.testing.assert_array_equal(out[i].cpu().numpy(), want[0].numpy(), err_msg=str(shapes[i]))
+    # a strided view (row pitch > 3 * width) is read in place
+    big = torch.from_numpy(rng.integers(0, 256, (300, 500, 3), dtype=np.uint8)).to(cuda_device)
+    view = big[10:250, 20:400]
+    got, _ = ops.letterbox([view], (320, 320))
+    want, _, _ = ref_port.preprocess_image(view.cpu().numpy(), (320, 320))
+    np.testing.assert_array_equal(got.cpu().numpy(), want.numpy())
+
+
+def test_pack_boxes_and_records(ov, cuda_device):
+    from ovdet import ops
+    from ovdet.detector import Detector
+    boxes = torch.tensor([[[1.9, 2.1, 639.99, 0.0], [5.5, 6.5, 7.5, 8.5], [9.0, 9.0, 9.0, 9.0]],
+                          [[0.2, 0.9, 3.7, 4.0], [1.0, 1.0, 1.0, 1.0], [2.0, 2.0, 2.0, 2.0]]], device=cuda_device)
+    count = torch.tensor([2, 1], device=cuda_device, dtype=torch.int32)
+    packed = ops.pack_boxes_i32(boxes, count)
+    want = boxes.cpu().numpy().astype(int)
+    want[0, 2:] = 0
+    want[1, 1:] = 0
+    np.testing.assert_array_equal(packed.cpu().numpy(), want)
+    det = Detector(class_names=["a", "b"], device=str(cuda_device))
+    res = ops.NmsResult(boxes=boxes, scores=torch.full((2, 3), 0.5, device=cuda_device),
+                        classes=torch.ones(2, 3, device=cuda_device, dtype=torch.int32), count=count)
+    rec = det.to_records(res, 0)
+    assert [r["box"] for r in rec] == [[1, 2, 639, 0], [5, 6, 7, 8]] and rec[0]["class_name"] == "b"
+
+
+def test_vocabulary_operand_and_detect(ov, cuda_device, golden_dir):
+    """JSON vocabulary -> cached operand -> Detector.detect on an image through a stand-in
+    convolutional model; equals the oracle fed with the same conv outputs."""
+    from ovdet import ops, synth
+    from ovdet.detector import Detector
+    from ovdet.vocabulary import Vocabulary
+    vocab = Vocabulary.load(os.path.join(golden_dir, "vocab_3cls.json"))
+    op = vocab.operand(cuda_device)
+    assert op.shape == (1, 3, 512) and op.dtype == torch.bfloat16 and vocab.operand(cuda_device) is op
+    ref = torch.nn.functional.normalize(vocab.embeddings, dim=-1)
+    assert (op[0].float().cpu() - ref).abs().max() < 4e-3
+    inp = synth.make_inputs(batch=1, image_size=160, num_classes=3, seed=9)
+    feats = ([e.to(cuda_device) for e in inp.obj_embeds], [p.to(cuda_device) for p in inp.box_preds],
+             inp.text.to(cuda_device))
+    det = Detector(image_size=(160, 160), device=str(cuda_device), feature_fn=lambda x, prompts: feats)
+    det.load_offline_vocabulary(os.path.join(golden_dir, "vocab_3cls.json"))
+    assert det.class_names == ["traffic light", "person", "zebra"]
+    img = np.random.default_rng(3).integers(0, 256, (120, 200, 3), dtype=np.uint8)
+    records = det.detect(img)
+    pipe = next(iter(det._pipelines.values()))
+    fed = {"boxes": pipe.boxes.cpu(), "scores": pipe.scores.cpu(), "class_ids": pipe.class_ids.cpu().long()}
+    scale, _, _ = ref_port.letterbox_geometry(120, 200, (160, 160))
+    want = ref_port.postprocess_image(fed["boxes"][0].numpy(), fed["scores"][0].numpy(),
+                                      fed["class_ids"][0].numpy(), (120, 200), scale,
+                                      class_names=det.class_names)["detections"]
+    assert len(records) == len(want) > 0
+    for a, b in zip(records, want):
+        assert a["box"] == b["box"] and a["class_id"] == b["class_id"] and a["class_name"] == b["class_name"]
+        assert a["score"] == b["score"]

@@ -88,3 +88,35 @@ def test_forward_tail(golden_dir):
     assert set(g["keys"]) == {"boxes", "scores", "class_ids", "obj_embeddings",
                               "text_embeddings", "box_preds"}
     assert out["boxes"].shape == (2, 84, 4)        # 64 | 16 | 4 anchors: P3 | P4 | P5
+
+
+# ------------------------------------------------------------------------------------------
+# "next" rows: pre-processing and vocabulary format
+# ------------------------------------------------------------------------------------------
+def test_preprocess_matches_live_reference_fixture(golden_dir):
+    g = np.load(os.path.join(golden_dir, "preprocess_cases.npz"))
+    for name in ("up", "down", "half", "same", "wide"):
+        h, w, scale = g[f"{name}_meta"]
+        out, orig, s = ref_port.preprocess_image(g[f"{name}_img"], (int(h), int(w)))
+        assert s == scale
+        np.testing.assert_array_equal(out.numpy(), g[f"{name}_out"])
+        np.testing.assert_array_equal(orig, g[f"{name}_img"])
+
+
+def test_vocabulary_format(golden_dir, tmp_path):
+    g = np.load(os.path.join(golden_dir, "vocab_3cls.npz"))
+    names, matrix = ref_port.load_offline_vocabulary(os.path.join(golden_dir, "vocab_3cls.json"))
+    assert names == list(g["names"])
+    np.testing.assert_array_equal(matrix.numpy(), g["matrix"])
+    # the product's reader / writer speak the same format (pure host code, no GPU needed)
+    from ovdet.vocabulary import Vocabulary, load_offline_vocabulary
+    names2, matrix2 = load_offline_vocabulary(os.path.join(golden_dir, "vocab_3cls.json"))
+    assert names2 == names and torch.equal(matrix2, matrix)
+    out = str(tmp_path / "sub" / "v.json")
+    Vocabulary(names2, matrix2).save(out)
+    with open(out) as a, open(os.path.join(golden_dir, "vocab_3cls.json")) as b:
+        assert a.read() == b.read()                      # byte-identical to the reference's file
+    ref_out = str(tmp_path / "ref.json")
+    ref_port.save_offline_vocabulary(ref_out, names, matrix)
+    with open(ref_out) as a, open(out) as b:
+        assert a.read() == b.read()
