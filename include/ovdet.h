@@ -221,6 +221,34 @@ OVDET_API int ovdet_letterbox_u8(const uint8_t* const* images, const int32_t* he
 OVDET_API int ovdet_pack_boxes_i32(const float* boxes, const int32_t* count, int64_t batch,
                                    int64_t max_det, int32_t* out, void* stream);
 
+/* ------------------------------------------------------------------------------------------
+ * N1  max-sigmoid text attention of the neck's text-guided CSP layer ("next" row f-1).
+ * Replaces: model/repvl_pan.py:77-95 - permute, matmul(y, text'^T), max over classes, sigmoid,
+ *           y * weight, permute back - in two launches (tcgen05 GEMM with the class max fused in
+ *           its epilogue, then a streaming scale).
+ *
+ * ovdet_cast_text: fp32 text rows [batch, classes, dim] (element strides stride_b / stride_c,
+ *   unit stride along dim) -> RAW (not normalised) bf16 operand [batch, classes, kop], zero padded
+ *   to dpad = ceil(dim / 64) * 64 columns per segment; split3 = 0: kop = dpad, [hi];
+ *   split3 = 1: kop = 3 * dpad, [hi | lo | hi] for the fp32-accurate three-pass product.
+ * ovdet_max_sigmoid_attention:
+ *   y        fp32 [batch, channels, hw], element (b, c, a) at y[b*stride_b + c*stride_c + a];
+ *            hw and the strides multiples of 4, pointers 16-byte aligned, channels <= 512
+ *            (<= 128 with precise), else OVDET_ERR_UNSUPPORTED_SHAPE
+ *   text_op  from ovdet_cast_text(dim = channels, split3 = precise); text_batched: one table per
+ *            image, else one shared table
+ *   row_max  fp32 [batch, hw] out: max_c <y[:, a], t'_c>  (kept: it is also the attention logit)
+ *   out      fp32, same indexing as y with out_stride_b / out_stride_c; may alias y
+ * ---------------------------------------------------------------------------------------- */
+OVDET_API int ovdet_cast_text(const float* t, int64_t batch, int64_t classes, int64_t dim,
+                              int64_t stride_b, int64_t stride_c, void* operand, int64_t kop,
+                              int split3, void* stream);
+OVDET_API int ovdet_max_sigmoid_attention(const float* y, int64_t batch, int64_t channels, int64_t hw,
+                                          int64_t stride_b, int64_t stride_c, const void* text_op,
+                                          int64_t classes, int text_batched, int precise,
+                                          float* row_max, float* out, int64_t out_stride_b,
+                                          int64_t out_stride_c, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

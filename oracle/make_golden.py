@@ -220,6 +220,32 @@ def preprocess_cases():
     print("cv2.resize restatement: 300 random shapes bit-exact")
 
 
+def tcsp_case():
+    """Live reference TextGuidedCSPLayer (random weights, eval mode) on a small feature map: the
+    layer's input/output, its state dict and the intermediate entering / leaving the attention."""
+    from yolo_clip_detector.model.repvl_pan import TextGuidedCSPLayer
+    torch.manual_seed(17)
+    layer = TextGuidedCSPLayer(in_channels=48, out_channels=64, text_dim=512, n_bottlenecks=1).eval()
+    for m in layer.modules():                      # non-trivial BN statistics
+        if isinstance(m, torch.nn.BatchNorm2d):
+            m.running_mean.normal_(0, 0.2)
+            m.running_var.uniform_(0.5, 1.5)
+            m.weight.data.uniform_(0.5, 1.5)
+            m.bias.data.normal_(0, 0.2)
+    x = torch.randn(2, 48, 12, 10)
+    text = torch.randn(2, 9, 512)
+    captured = {}
+    hook = layer.bottlenecks[0].register_forward_hook(lambda m, i, o: captured.__setitem__("y", o.detach()))
+    with torch.no_grad():
+        out = layer(x, text)
+        proj = layer.text_proj(text)
+    hook.remove()
+    arrays = {"x": x.numpy(), "text": text.numpy(), "out": out.numpy(), "y_temp": captured["y"].numpy(),
+              "proj": proj.numpy()}
+    arrays.update({"sd/" + k: v.numpy() for k, v in layer.state_dict().items()})
+    save("tcsp_layer", **arrays)
+
+
 def vocabulary_case():
     """Reference VocabBuilder.build_offline_vocabulary -> JSON file (stub CLIP encoder), and the
     matrix YOLOCLIP.load_offline_vocabulary stacks from it."""
@@ -249,3 +275,4 @@ if __name__ == "__main__":
     forward_tail_case()
     preprocess_cases()
     vocabulary_case()
+    tcsp_case()

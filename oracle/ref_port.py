@@ -315,3 +315,15 @@ def save_offline_vocabulary(path: str, class_names: Sequence[str], embeddings: t
     save = {n: embeddings[i].cpu().numpy().tolist() for i, n in enumerate(class_names)}
     with open(path, "w") as f:
         json.dump(save, f)
+
+
+def max_sigmoid_attention(y: torch.Tensor, projected_text: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
+    """model/repvl_pan.py:80-95 for one bottleneck iteration: ``y [B, c, H, W]``,
+    ``projected_text [B, C, c]`` -> (attended ``[B, c, H, W]``, max scores ``[B, HW]``)."""
+    b, c, h, w = y.shape
+    y_r = y.permute(0, 2, 3, 1).reshape(b, h * w, c)                           # :81
+    scores = torch.matmul(y_r, projected_text.transpose(-1, -2))               # :85
+    max_scores, _ = torch.max(scores, dim=-1, keepdim=True)                    # :88
+    weights = torch.sigmoid(max_scores)                                        # :89
+    attended = y_r * weights                                                   # :92
+    return attended.reshape(b, h, w, c).permute(0, 3, 1, 2), max_scores.squeeze(-1)   # :95

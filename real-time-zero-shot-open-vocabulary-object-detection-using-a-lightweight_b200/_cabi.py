@@ -47,6 +47,11 @@ PROTOTYPES = {
     "ovdet_letterbox_u8": (c_int, [POINTER(c_void_p), POINTER(c_int32), POINTER(c_int32),
                                    POINTER(c_int64), POINTER(c_int32), POINTER(c_int32), c_int,
                                    c_int, c_int, c_void_p, c_void_p]),
+    "ovdet_cast_text": (c_int, [c_void_p, c_int64, c_int64, c_int64, c_int64, c_int64, c_void_p, c_int64,
+                                c_int, c_void_p]),
+    "ovdet_max_sigmoid_attention": (c_int, [c_void_p, c_int64, c_int64, c_int64, c_int64, c_int64, c_void_p,
+                                            c_int64, c_int, c_int, c_void_p, c_void_p, c_int64, c_int64,
+                                            c_void_p]),
     "ovdet_pack_boxes_i32": (c_int, [c_void_p, c_void_p, c_int64, c_int64, c_void_p, c_void_p]),
 }
 

@@ -121,6 +121,29 @@ l2norm_text_kernel(const float* __restrict__ t, int64_t total_rows, int classes,
   }
 }
 
+// Raw (un-normalised) text rows -> bf16 operand, zero padded to `dpad` columns per segment.
+// segments == 1: [hi]; segments == 3: [hi | lo | hi] with lo = bf16(x - hi), the layout the
+// three-pass (fp32-accurate) mode of the fused kernel multiplies against [hi | hi | lo].
+__global__ void __launch_bounds__(256)
+cast_text_kernel(const float* __restrict__ t, int64_t total_rows, int classes, int dim, int dpad,
+                 int segments, int64_t stride_b, int64_t stride_c, __nv_bfloat16* __restrict__ operand) {
+  const int64_t row = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (row >= total_rows) return;
+  const int64_t b = row / classes, c = row % classes;
+  const float* src = t + b * stride_b + c * stride_c;
+  __nv_bfloat16* dst = operand + row * (int64_t)dpad * segments;
+  for (int i = lane; i < dpad; i += 32) {
+    const float f = i < dim ? src[i] : 0.f;
+    const __nv_bfloat16 h = __float2bfloat16_rn(f);
+    dst[i] = h;
+    if (segments == 3) {
+      dst[dpad + i] = __float2bfloat16_rn(f - __bfloat162float(h));
+      dst[2 * dpad + i] = h;
+    }
+  }
+}
+
 template <int ANCH, bool SPLIT>
 static int launch_regions(const float* x, int64_t batch, int dim, int hw, int64_t stride_b,
                           int64_t stride_d, __nv_bfloat16* operand, int64_t rows_per_batch,
@@ -177,6 +200,24 @@ extern "C" int ovdet_l2norm_text(const float* t, int64_t batch, int64_t classes,
   else
     l2norm_text_kernel<false><<<grid, 256, 0, as_stream(stream)>>>(t, total, (int)classes, (int)dim,
                                                                    stride_b, stride_c, op, (int)kop, inv_norm);
+  OVDET_LAUNCH_CHECK();
+  return OVDET_OK;
+}
+
+extern "C" int ovdet_cast_text(const float* t, int64_t batch, int64_t classes, int64_t dim,
+                               int64_t stride_b, int64_t stride_c, void* operand, int64_t kop,
+                               int split3, void* stream) {
+  using namespace ovdet;
+  if (!t || !operand || batch < 0 || classes < 0 || dim <= 0) return OVDET_ERR_INVALID_ARG;
+  const int64_t dpad = ceil_div<int64_t>(dim, 64) * 64;
+  if (kop != dpad * (split3 ? 3 : 1)) return OVDET_ERR_INVALID_ARG;
+  if (dim > 512) return OVDET_ERR_UNSUPPORTED_SHAPE;
+  if (int rc = check_device()) return rc;
+  const int64_t total = batch * classes;
+  if (total == 0) return OVDET_OK;
+  cast_text_kernel<<<(unsigned)ceil_div<int64_t>(total, 8), 256, 0, as_stream(stream)>>>(
+      t, total, (int)classes, (int)dim, (int)dpad, split3 ? 3 : 1, stride_b, stride_c,
+      static_cast<__nv_bfloat16*>(operand));
   OVDET_LAUNCH_CHECK();
   return OVDET_OK;
 }

@@ -78,7 +78,9 @@ struct FusedParams {
   int tile_start[F_MAX_LEVELS + 1];
   int anchors;                     // per image, all levels
   int classes;
-  int kb;                          // dim / 64
+  int kb;                          // k blocks of 64 the MMA walks (3 * kb_in with split3)
+  int kb_in;                       // fp32 input blocks per anchor tile: ceil(dim / 64)
+  int normalize;                   // 1: scale rows by 1 / max(||x||, 1e-12) (cosine); 0: raw dot product
   int n_tiles;
   int text_batched;
   float alpha, beta;
@@ -108,7 +110,12 @@ __device__ __forceinline__ TileCoord decode_tile(const FusedParams& p, int tile)
   return t;
 }
 
-template <int KB_T>      // 8: dim == 512, every k-block loop unrolled; 0: run-time dim / 64
+// KB_T  8: dim == 512, every k-block loop unrolled; 0: run-time block count.
+// SPLIT3 (dim <= 128): fp32-accurate product from three bf16 passes.  x = hi + lo with
+// hi = bf16(x), lo = bf16(x - hi); the activation blocks are written to tensor memory as
+// [hi | hi | lo] and the text operand is laid out [hi | lo | hi] (ovdet_cast_text), so the plain
+// block loop accumulates hi*hi + hi*lo + lo*hi (the lo*lo term is < 2^-16 relative).
+template <int KB_T, bool SPLIT3>
 __global__ void __launch_bounds__(F_THREADS, 1)
 sim_fused_kernel(const __grid_constant__ LevelMaps amaps, const __grid_constant__ CUtensorMap tmap_b,
                  const FusedParams p) {
@@ -159,6 +166,7 @@ sim_fused_kernel(const __grid_constant__ LevelMaps amaps, const __grid_constant_
 
   const int total_tiles = p.tile_start[p.levels];
   const int KB = KB_T ? KB_T : p.kb;
+  const int KB_IN = KB_T ? KB_T : p.kb_in;
   const int NT = p.n_tiles;
 
   // Producer / issuer warps run warp-uniform control flow; `issue` is 1 in one elected lane and
@@ -231,7 +239,7 @@ sim_fused_kernel(const __grid_constant__ LevelMaps amaps, const __grid_constant_
       const TileCoord tc = decode_tile(p, tile);
       const CUtensorMap* map = &amaps.m[tc.level];
 #pragma unroll
-      for (int kb = 0; kb < KB; ++kb, ++ia) {
+      for (int kb = 0; kb < KB_IN; ++kb, ++ia) {
         const uint32_t s = ia % F_A_STAGES;
         const uint32_t ph = (ia / F_A_STAGES) & 1u;
         ptx::mbar_wait(as_empty0 + 8u * s, ph ^ 1u);
@@ -254,7 +262,7 @@ sim_fused_kernel(const __grid_constant__ LevelMaps amaps, const __grid_constant_
       const TileCoord tc = decode_tile(p, next);
       const CUtensorMap* map = &amaps.m[tc.level];
 #pragma unroll
-      for (int kb = 0; kb < KB; ++kb)
+      for (int kb = 0; kb < KB_IN; ++kb)
         ptx::tma_prefetch_l2_3d_if(issue, map, tc.m0, kb * F_BLOCK_K, tc.b);
     }
   } else if (warp >= 4 && warp < 8) {
@@ -265,12 +273,23 @@ sim_fused_kernel(const __grid_constant__ LevelMaps amaps, const __grid_constant_
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++lt) {
       const TileCoord tc = decode_tile(p, tile);
       float ss0 = 0.f, ss1 = 0.f, ss2 = 0.f, ss3 = 0.f;
+      // block `t` of the A region: wait until the previous tile's MMAs have read it, store, publish
+      auto publish = [&](int t, const uint32_t (&regs)[32]) {
+        ptx::mbar_wait(a_free0 + 8u * t, (lt & 1u) ^ 1u);
+        ptx::tc_fence_after();
+        ptx::tmem_st_32x32(tmem_base + ((uint32_t)(lg * 32) << 16) + (uint32_t)(F_A_COL + t * 32), regs);
+        ptx::tmem_st_wait();
+        ptx::tc_fence_before();
+        __syncwarp();
+        if (lane == 0) ptx::mbar_arrive(a_ready0 + 8u * t);
+      };
 #pragma unroll
-      for (int kb = 0; kb < KB; ++kb, ++ia) {
+      for (int kb = 0; kb < KB_IN; ++kb, ++ia) {
         const uint32_t s = ia % F_A_STAGES;
         ptx::mbar_wait(as_full0 + 8u * s, (ia / F_A_STAGES) & 1u);
         const float* col = a_stage_ptr + s * (F_A_STAGE_BYTES / 4) + arow;
         uint32_t packed[32];
+        uint32_t packed_lo[32];                            // dead (eliminated) unless SPLIT3
 #pragma unroll
         for (int k = 0; k < 64; k += 4) {
           const float x0 = col[(k + 0) * F_BLOCK_M], x1 = col[(k + 1) * F_BLOCK_M];
@@ -279,17 +298,21 @@ sim_fused_kernel(const __grid_constant__ LevelMaps amaps, const __grid_constant_
           ss2 = fmaf(x2, x2, ss2); ss3 = fmaf(x3, x3, ss3);
           packed[(k >> 1) + 0] = pack_bf16x2(x0, x1);
           packed[(k >> 1) + 1] = pack_bf16x2(x2, x3);
+          if constexpr (SPLIT3) {
+            const uint32_t h01 = packed[(k >> 1) + 0], h23 = packed[(k >> 1) + 1];
+            packed_lo[(k >> 1) + 0] = pack_bf16x2(x0 - __uint_as_float(h01 << 16),
+                                                  x1 - __uint_as_float(h01 & 0xffff0000u));
+            packed_lo[(k >> 1) + 1] = pack_bf16x2(x2 - __uint_as_float(h23 << 16),
+                                                  x3 - __uint_as_float(h23 & 0xffff0000u));
+          }
         }
         __syncwarp();
         if (lane == 0) ptx::mbar_arrive(as_empty0 + 8u * s);   // staging slot may be refilled
-        // the MMAs of the previous tile that read A block kb must have retired
-        ptx::mbar_wait(a_free0 + 8u * kb, (lt & 1u) ^ 1u);
-        ptx::tc_fence_after();
-        ptx::tmem_st_32x32(tmem_base + ((uint32_t)(lg * 32) << 16) + (uint32_t)(F_A_COL + kb * 32), packed);
-        ptx::tmem_st_wait();
-        ptx::tc_fence_before();
-        __syncwarp();
-        if (lane == 0) ptx::mbar_arrive(a_ready0 + 8u * kb);
+        publish(kb, packed);
+        if constexpr (SPLIT3) {
+          publish(KB_IN + kb, packed);
+          publish(2 * KB_IN + kb, packed_lo);
+        }
       }
       const float inv = 1.0f / fmaxf(sqrtf((ss0 + ss1) + (ss2 + ss3)), 1e-12f);
       const int slot = lt % 3;
@@ -311,7 +334,7 @@ sim_fused_kernel(const __grid_constant__ LevelMaps amaps, const __grid_constant_
       const long long grow = tc.out_row0 + r_in_tile;
       const int slot = lt % 3;
       ptx::mbar_wait(n_ready0 + 8u * slot, (lt / 3) & 1u);
-      const float scale = p.alpha * norm_s[slot * F_BLOCK_M + r_in_tile];
+      const float scale = p.normalize ? p.alpha * norm_s[slot * F_BLOCK_M + r_in_tile] : p.alpha;
       const float beta = p.beta;
       float bv[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
       int bi[4] = {0, 0, 0, 0};
@@ -420,16 +443,15 @@ EncodeTiledFn fused_encode_fn() {
 }
 
 }  // namespace
-}  // namespace ovdet
 
-extern "C" int ovdet_similarity_fused(const float* const* obj_embeds, const int64_t* hw,
-                                      const int64_t* stride_b, const int64_t* stride_d,
-                                      int num_levels, int64_t batch, int64_t dim,
-                                      const void* text_op, int64_t classes, int text_batched,
-                                      float alpha, float beta, void* logits, int logits_dtype,
-                                      int64_t ldc, float* row_max, int32_t* row_arg,
-                                      float* inv_norm, void* stream) {
-  using namespace ovdet;
+// Shared launcher.  `dim` is the real embedding length; it is padded to a multiple of 64 by the
+// TMA zero fill on the activation side and by zero columns in the text operand, whose row length
+// is kop = (split3 ? 3 : 1) * ceil(dim / 64) * 64.
+int fused_launch(const float* const* obj_embeds, const int64_t* hw, const int64_t* stride_b,
+                 const int64_t* stride_d, int num_levels, int64_t batch, int64_t dim,
+                 const void* text_op, int64_t classes, int text_batched, int normalize, int split3,
+                 float alpha, float beta, void* logits, int logits_dtype, int64_t ldc,
+                 float* row_max, int32_t* row_arg, float* inv_norm, void* stream) {
   if (!obj_embeds || !hw || !stride_b || !stride_d || !text_op || batch < 0 || classes <= 0 || dim <= 0)
     return OVDET_ERR_INVALID_ARG;
   if (num_levels <= 0) return OVDET_ERR_INVALID_ARG;
@@ -437,8 +459,9 @@ extern "C" int ovdet_similarity_fused(const float* const* obj_embeds, const int6
   if (row_arg && !row_max) return OVDET_ERR_INVALID_ARG;
   if (logits && (ldc < classes || (logits_dtype != OVDET_F32 && logits_dtype != OVDET_BF16)))
     return OVDET_ERR_INVALID_ARG;
-  if (num_levels > F_MAX_LEVELS || dim % F_BLOCK_K != 0 || dim > F_MAX_KB * F_BLOCK_K || batch > 65535)
-    return OVDET_ERR_UNSUPPORTED_SHAPE;
+  const int kb_in = (int)ceil_div<int64_t>(dim, F_BLOCK_K);
+  const int kb = kb_in * (split3 ? 3 : 1);
+  if (num_levels > F_MAX_LEVELS || kb > F_MAX_KB || batch > 65535) return OVDET_ERR_UNSUPPORTED_SHAPE;
   if ((uintptr_t)text_op & 15) return OVDET_ERR_INVALID_ARG;
   EncodeTiledFn enc = nullptr;
   FusedParams p{};
@@ -476,8 +499,9 @@ extern "C" int ovdet_similarity_fused(const float* const* obj_embeds, const int6
   CUtensorMap map_b;
   {
     const int64_t tb = text_batched ? batch : 1;
-    cuuint64_t dims[3] = {(cuuint64_t)dim, (cuuint64_t)classes, (cuuint64_t)tb};
-    cuuint64_t strides[2] = {(cuuint64_t)dim * 2, (cuuint64_t)classes * (cuuint64_t)dim * 2};
+    const int64_t kop = (int64_t)kb * F_BLOCK_K;
+    cuuint64_t dims[3] = {(cuuint64_t)kop, (cuuint64_t)classes, (cuuint64_t)tb};
+    cuuint64_t strides[2] = {(cuuint64_t)kop * 2, (cuuint64_t)classes * (cuuint64_t)kop * 2};
     cuuint32_t box[3] = {(cuuint32_t)F_BLOCK_K, (cuuint32_t)F_BLOCK_N, 1};
     cuuint32_t estr[3] = {1, 1, 1};
     CUresult r = enc(&map_b, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(text_op), dims, strides,
@@ -490,7 +514,9 @@ extern "C" int ovdet_similarity_fused(const float* const* obj_embeds, const int6
   p.tile_start[num_levels] = (int)tiles;
   p.anchors = (int)anchors;
   p.classes = (int)classes;
-  p.kb = (int)(dim / F_BLOCK_K);
+  p.kb = kb;
+  p.kb_in = kb_in;
+  p.normalize = normalize ? 1 : 0;
   p.n_tiles = (int)ceil_div<int64_t>(classes, F_BLOCK_N);
   p.text_batched = text_batched ? 1 : 0;
   p.alpha = alpha;
@@ -505,15 +531,33 @@ extern "C" int ovdet_similarity_fused(const float* const* obj_embeds, const int6
 
   static bool attr_set = false;
   if (!attr_set) {
-    OVDET_CUDA_TRY(cudaFuncSetAttribute(sim_fused_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, F_SMEM_BYTES));
-    OVDET_CUDA_TRY(cudaFuncSetAttribute(sim_fused_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, F_SMEM_BYTES));
+    OVDET_CUDA_TRY(cudaFuncSetAttribute(sim_fused_kernel<8, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, F_SMEM_BYTES));
+    OVDET_CUDA_TRY(cudaFuncSetAttribute(sim_fused_kernel<0, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, F_SMEM_BYTES));
+    OVDET_CUDA_TRY(cudaFuncSetAttribute(sim_fused_kernel<0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, F_SMEM_BYTES));
     attr_set = true;
   }
   const int grid = (int)(tiles < sm_count() ? tiles : sm_count());
-  if (p.kb == 8)
-    sim_fused_kernel<8><<<grid, F_THREADS, F_SMEM_BYTES, as_stream(stream)>>>(maps, map_b, p);
+  if (split3)
+    sim_fused_kernel<0, true><<<grid, F_THREADS, F_SMEM_BYTES, as_stream(stream)>>>(maps, map_b, p);
+  else if (p.kb == 8)
+    sim_fused_kernel<8, false><<<grid, F_THREADS, F_SMEM_BYTES, as_stream(stream)>>>(maps, map_b, p);
   else
-    sim_fused_kernel<0><<<grid, F_THREADS, F_SMEM_BYTES, as_stream(stream)>>>(maps, map_b, p);
+    sim_fused_kernel<0, false><<<grid, F_THREADS, F_SMEM_BYTES, as_stream(stream)>>>(maps, map_b, p);
   OVDET_LAUNCH_CHECK();
   return OVDET_OK;
+}
+
+}  // namespace ovdet
+
+extern "C" int ovdet_similarity_fused(const float* const* obj_embeds, const int64_t* hw,
+                                      const int64_t* stride_b, const int64_t* stride_d,
+                                      int num_levels, int64_t batch, int64_t dim,
+                                      const void* text_op, int64_t classes, int text_batched,
+                                      float alpha, float beta, void* logits, int logits_dtype,
+                                      int64_t ldc, float* row_max, int32_t* row_arg,
+                                      float* inv_norm, void* stream) {
+  if (dim % 64 != 0) return OVDET_ERR_UNSUPPORTED_SHAPE;   // the text operand has exactly `dim` columns
+  return ovdet::fused_launch(obj_embeds, hw, stride_b, stride_d, num_levels, batch, dim, text_op, classes,
+                             text_batched, /*normalize=*/1, /*split3=*/0, alpha, beta, logits, logits_dtype,
+                             ldc, row_max, row_arg, inv_norm, stream);
 }

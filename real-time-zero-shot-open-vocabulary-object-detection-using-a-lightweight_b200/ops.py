@@ -399,3 +399,51 @@ def pack_boxes_i32(boxes: torch.Tensor, count: torch.Tensor, out: Optional[torch
         check(lib().ovdet_pack_boxes_i32(boxes.data_ptr(), count.data_ptr(), batch, max_det,
                                          out.data_ptr(), _stream(boxes)), "ovdet_pack_boxes_i32")
     return out
+
+
+# --------------------------------------------------------------------------------------------
+# N1: max-sigmoid text attention of the neck ("next" row)
+# --------------------------------------------------------------------------------------------
+def cast_text(text: torch.Tensor, split3: bool = False) -> torch.Tensor:
+    """Raw (un-normalised) bf16 operand of projected text ``[C, c]`` or ``[B, C, c]``:
+    ``[Bt, C, kop]`` with the columns zero padded to a multiple of 64 (x3 for ``split3``)."""
+    _require_cuda(text, "text", torch.float32)
+    if text.dim() == 2:
+        text = text.unsqueeze(0)
+    elif shared_text(text):
+        text = text[:1]
+    if text.stride(2) != 1:
+        text = text.contiguous()
+    bt, classes, dim = text.shape
+    kop = (dim + 63) // 64 * 64 * (3 if split3 else 1)
+    operand = torch.empty(bt, classes, kop, device=text.device, dtype=torch.bfloat16)
+    with torch.cuda.device(text.device):
+        check(lib().ovdet_cast_text(text.data_ptr(), bt, classes, dim, text.stride(0), text.stride(1),
+                                    operand.data_ptr(), kop, int(split3), _stream(text)), "ovdet_cast_text")
+    return operand
+
+
+def max_sigmoid_attention(y: torch.Tensor, projected_text: torch.Tensor, precise: bool = True,
+                          out: Optional[torch.Tensor] = None, return_scores: bool = False):
+    """model/repvl_pan.py:80-95: ``y [B, c, H, W]`` fp32 (NCHW), ``projected_text [B, C, c]`` (or a
+    shared ``[C, c]``) -> ``y * sigmoid(max_C(y^T t'))``, same shape and layout as ``y``."""
+    _require_cuda(y, "y", torch.float32)
+    b, c, h, w = y.shape
+    if y.stride(3) != 1 or y.stride(2) != w:
+        y = y.contiguous()
+    if (h * w) % 4 or y.stride(0) % 4 or y.stride(1) % 4 or y.data_ptr() % 16:
+        raise ValueError("ovdet: max_sigmoid_attention needs H*W and the strides to be multiples of 4")
+    text_op = cast_text(projected_text, split3=precise)
+    bt = text_op.shape[0]
+    assert bt in (1, b) and projected_text.shape[-1] == c
+    if out is None:
+        out = torch.empty_like(y, memory_format=torch.contiguous_format)
+    assert out.shape == y.shape and out.stride(3) == 1 and out.stride(2) == w
+    row_max = torch.empty(b, h * w, device=y.device, dtype=torch.float32)
+    with torch.cuda.device(y.device):
+        check(lib().ovdet_max_sigmoid_attention(y.data_ptr(), b, c, h * w, y.stride(0), y.stride(1),
+                                                text_op.data_ptr(), text_op.shape[1],
+                                                int(bt == b and b > 1), int(precise), row_max.data_ptr(),
+                                                out.data_ptr(), out.stride(0), out.stride(1), _stream(y)),
+              "ovdet_max_sigmoid_attention")
+    return (out, row_max) if return_scores else out

@@ -529,3 +529,56 @@ def test_vocabulary_operand_and_detect(ov, cuda_device, golden_dir):
     for a, b in zip(records, want):
         assert a["box"] == b["box"] and a["class_id"] == b["class_id"] and a["class_name"] == b["class_name"]
         assert a["score"] == b["score"]
+
+
+# ------------------------------------------------------------------------------------------
+# N1 ("next" row): max-sigmoid text attention of the neck
+# ------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("c,classes,shape,batched", [(32, 5, (20, 20), True), (64, 80, (12, 10), False),
+                                                     (128, 300, (8, 8), True), (64, 1203, (40, 40), False)])
+def test_max_sigmoid_attention_vs_oracle(ov, cuda_device, c, classes, shape, batched):
+    from ovdet import ops
+    torch.manual_seed(c + classes)
+    b = 3
+    y = torch.randn(b, c, *shape) * 0.7
+    y[1, :, 0, 1] = 0.0                                          # zero activation: weight = sigmoid(0)
+    text = torch.randn(b, classes, c) * 0.5 if batched else (torch.randn(classes, c) * 0.5)
+    tb = text if batched else text.unsqueeze(0).expand(b, -1, -1)
+    want, want_max = ref_port.max_sigmoid_attention(y, tb)
+    yd = y.to(cuda_device)
+    td = text.to(cuda_device)
+    out, smax = ops.max_sigmoid_attention(yd, td, precise=True, return_scores=True)
+    torch.cuda.synchronize()
+    # fp32 tolerance (north_star: 1e-3 relative); the three-pass product measures ~1e-6
+    scale = want_max.abs().max().item()
+    assert (smax.cpu() - want_max).abs().max().item() <= 2e-5 * max(scale, 1.0)
+    torch.testing.assert_close(out.cpu(), want.contiguous(), rtol=2e-5, atol=2e-6)
+    assert out.shape == y.shape and out.is_contiguous()
+    # one bf16 pass: stated separately, |dscore| <= 8e-3 * |y| |t'| ; the weight moves by <= 1/4 of that
+    out16, smax16 = ops.max_sigmoid_attention(yd, td, precise=False, return_scores=True)
+    bound = 8e-3 * (y.flatten(2).norm(dim=1).max() * tb.norm(dim=-1).max()).item()
+    assert (smax16.cpu() - want_max).abs().max().item() <= bound
+    assert (out16.cpu() - want).abs().max().item() <= 0.25 * bound * y.abs().max().item() + 1e-6
+
+
+def test_tcsp_layer_golden(ov, cuda_device, golden_dir):
+    from ovdet.neck import TextGuidedCSPLayer
+    g = _load(golden_dir, "tcsp_layer")
+    layer = TextGuidedCSPLayer(48, 64, 512, n_bottlenecks=1).eval()
+    layer.load_state_dict({k[3:]: torch.from_numpy(g[k]) for k in g.files if k.startswith("sd/")}, strict=True)
+    layer = layer.to(cuda_device)
+    x, text = torch.from_numpy(g["x"]).to(cuda_device), torch.from_numpy(g["text"]).to(cuda_device)
+    tf32 = torch.backends.cudnn.allow_tf32
+    torch.backends.cudnn.allow_tf32 = False          # the (out-of-scope) convolutions in plain fp32
+    try:
+        with torch.no_grad():
+            out = layer(x, text)
+    finally:
+        torch.backends.cudnn.allow_tf32 = tf32
+    torch.testing.assert_close(out.cpu(), torch.from_numpy(g["out"]), rtol=1e-4, atol=2e-5)
+    # shared vocabulary (stride-0 expand) gives the same result as the materialised batch
+    shared = text[:1].expand(2, -1, -1)
+    with torch.no_grad():
+        a = layer(x, shared)
+        bb = layer(x, shared.contiguous())
+    torch.testing.assert_close(a, bb, rtol=1e-5, atol=1e-6)

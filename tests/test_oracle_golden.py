@@ -120,3 +120,22 @@ def test_vocabulary_format(golden_dir, tmp_path):
     ref_port.save_offline_vocabulary(ref_out, names, matrix)
     with open(ref_out) as a, open(out) as b:
         assert a.read() == b.read()
+
+
+def test_tcsp_attention_restatement(golden_dir):
+    """Oracle attention (repvl_pan.py:80-95) inside the reference layer's own convolutions
+    reproduces the live reference output; the drop-in layer loads the reference state dict."""
+    from ovdet.neck import TextGuidedCSPLayer
+    g = np.load(os.path.join(golden_dir, "tcsp_layer.npz"))
+    layer = TextGuidedCSPLayer(48, 64, 512, n_bottlenecks=1).eval()
+    sd = {k[3:]: torch.from_numpy(g[k]) for k in g.files if k.startswith("sd/")}
+    layer.load_state_dict(sd, strict=True)
+    x, text = torch.from_numpy(g["x"]), torch.from_numpy(g["text"])
+    with torch.no_grad():
+        y_temp = layer.bottlenecks[0](layer.cv1(x))
+        proj = layer.text_proj(text)
+        torch.testing.assert_close(y_temp, torch.from_numpy(g["y_temp"]), rtol=1e-5, atol=1e-5)
+        torch.testing.assert_close(proj, torch.from_numpy(g["proj"]), rtol=1e-5, atol=1e-5)
+        y1, _ = ref_port.max_sigmoid_attention(torch.from_numpy(g["y_temp"]), torch.from_numpy(g["proj"]))
+        out = layer.cv3(torch.cat((y1, layer.cv2(x)), dim=1))
+    torch.testing.assert_close(out, torch.from_numpy(g["out"]), rtol=1e-5, atol=1e-5)

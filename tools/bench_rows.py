@@ -31,3 +31,20 @@ for (h, w), n in (((1080, 1920), 64), ((480, 640), 64), ((1280, 1280), 64), ((48
     print(json.dumps({"row": "P1 letterbox", "images": n, "source": [h, w], "ms": ms,
                       "images_per_s": n / ms * 1e3, "GBps": bytes_ / ms / 1e6,
                       "hbm_frac": bytes_ / ms / 1e6 / peaks["hbm_gbs"]}))
+
+# N1 max-sigmoid attention: the three T-CSP layer shapes of the `n` neck at 640^2, C = 1203
+for (c, hw_side), n in (((32, 80), 64), ((64, 40), 64), ((128, 20), 64)):
+    y = torch.randn(n, c, hw_side, hw_side, device=dev)
+    t = torch.randn(1203, c, device=dev)
+    out = torch.empty_like(y)
+    for precise in (True, False):
+        ms = timeit(lambda: ops.max_sigmoid_attention(y, t, precise=precise, out=out), iters=20)
+        hw = hw_side * hw_side
+        flops = 2.0 * n * hw * 1203 * c
+        bytes_ = n * hw * c * 4 * 3 + n * hw * 8          # y read by the GEMM and by the scale, out written
+        print(json.dumps({"row": "N1 max-sigmoid attention", "images": n, "channels": c, "hw": hw, "classes": 1203,
+                          "precise": precise, "ms": ms, "TFLOPs": flops / ms / 1e9,
+                          "GBps": bytes_ / ms / 1e6, "hbm_frac": bytes_ / ms / 1e6 / peaks["hbm_gbs"]}))
+    ref = lambda: torch.sigmoid(torch.matmul(y.flatten(2).transpose(1, 2), t.t()).max(dim=-1, keepdim=True)[0])
+    ms_t = timeit(ref, iters=5)
+    print(json.dumps({"row": "N1 torch (matmul+max+sigmoid only, same GPU)", "channels": c, "ms": ms_t}))
