@@ -338,6 +338,12 @@ sim_fused_kernel(const __grid_constant__ LevelMaps amaps, const __grid_constant_
       const float beta = p.beta;
       float bv[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
       int bi[4] = {0, 0, 0, 0};
+      // Max without argmax or logits (the attention row): the row scale is >= 0, so
+      // max_c fma(scale, acc_c, beta) == fma(scale, max_c acc_c, beta) exactly (rounding is
+      // monotone) and the running maximum is taken over the raw accumulators, one FMNMX3 per
+      // two values instead of FFMA + compare + two selects per value.
+      const bool max_only = want_max && p.row_arg == nullptr && p.logits == nullptr && p.alpha >= 0.f;
+      float raw_best = -INFINITY;
       for (int nt = 0; nt < NT; ++nt, ++acc_it) {
         const int n0 = nt * F_BLOCK_N;
         const int n_valid = min(F_BLOCK_N, p.classes - n0);
@@ -350,6 +356,22 @@ sim_fused_kernel(const __grid_constant__ LevelMaps amaps, const __grid_constant_
         auto consume = [&](uint32_t (&r)[32], int c) {
           const int c0 = c << 5;
           const int valid = n_valid - c0;
+          if (max_only) {
+            float m0 = raw_best, m1 = -INFINITY;
+            if (valid >= 32) {
+#pragma unroll
+              for (int j = 0; j < 32; j += 4) {
+                m0 = fmaxf(m0, fmaxf(__uint_as_float(r[j]), __uint_as_float(r[j + 1])));
+                m1 = fmaxf(m1, fmaxf(__uint_as_float(r[j + 2]), __uint_as_float(r[j + 3])));
+              }
+            } else {
+#pragma unroll
+              for (int j = 0; j < 32; ++j)
+                if (j < valid) m0 = fmaxf(m0, __uint_as_float(r[j]));
+            }
+            raw_best = fmaxf(m0, m1);
+            return;
+          }
 #pragma unroll
           for (int j = 0; j < 32; ++j) r[j] = __float_as_uint(fmaf(scale, __uint_as_float(r[j]), beta));
           if (want_max) {
@@ -405,7 +427,9 @@ sim_fused_kernel(const __grid_constant__ LevelMaps amaps, const __grid_constant_
         __syncwarp();
         if (lane == 0) ptx::mbar_arrive(t_empty0 + 8u * as);
       }
-      if (want_max && row_ok) {
+      if (max_only) {
+        if (row_ok) p.row_max[grow] = fmaf(scale, raw_best, beta);
+      } else if (want_max && row_ok) {
         float best = bv[0];
         int best_idx = bi[0];
 #pragma unroll

@@ -160,10 +160,11 @@ def similarity_fused(obj_embeds: Sequence[torch.Tensor], text_op: torch.Tensor, 
                      beta: float = 0.0, logits_dtype: Optional[torch.dtype] = None,
                      want_max: bool = True, logits: Optional[torch.Tensor] = None,
                      row_max: Optional[torch.Tensor] = None, row_arg: Optional[torch.Tensor] = None,
-                     inv_norm: Optional[torch.Tensor] = None):
+                     inv_norm: Optional[torch.Tensor] = None, want_arg: bool = True):
     """text_contrastive.py:134-147 for all levels + yolo_clip.py:198-206 in one launch, reading
     the fp32 NCHW ``obj_embeds`` directly.  ``text_op`` comes from ``l2norm_text(split=False)``.
-    Returns ``(logits [B, A, C] or None, row_max, row_arg)``."""
+    Returns ``(logits [B, A, C] or None, row_max, row_arg)``; ``want_arg=False`` skips the
+    argmax (scores only)."""
     first = obj_embeds[0]
     _require_cuda(first, "obj_embed", torch.float32)
     _require_cuda(text_op, "text_op", torch.bfloat16)
@@ -180,7 +181,7 @@ def similarity_fused(obj_embeds: Sequence[torch.Tensor], text_op: torch.Tensor, 
         logits = torch.empty(batch, anchors, classes, device=dev, dtype=logits_dtype)
     if want_max and row_max is None:
         row_max = torch.empty(batch, anchors, device=dev, dtype=torch.float32)
-    if want_max and row_arg is None:
+    if want_max and want_arg and row_arg is None:
         row_arg = torch.empty(batch, anchors, device=dev, dtype=torch.int32)
     ldt, ldc = _cabi.OVDET_F32, classes
     if logits is not None:

@@ -436,6 +436,9 @@ def test_similarity_fused_vs_oracle(ov, cuda_device, classes, batched, dim):
     # max-only launch gives the same answer
     _, m0, a0 = ops.similarity_fused(dev_embs, top, alpha, beta, logits_dtype=None, want_max=True)
     assert torch.equal(m0, rmax) and torch.equal(a0, rarg)
+    # scores only (no argmax): the raw-accumulator fast path gives bit-identical maxima
+    _, m1, a1 = ops.similarity_fused(dev_embs, top, alpha, beta, logits_dtype=None, want_max=True, want_arg=False)
+    assert a1 is None and torch.equal(m1, rmax)
 
 
 def test_fused_unsupported_shape_is_an_error(ov, cuda_device):
