@@ -207,6 +207,101 @@ __device__ __forceinline__ void mbar_wait_if_not(bool ready, uint32_t bar, uint3
   if (!ready) mbar_wait(bar, parity);
 }
 
+// ---- CTA pair (cta_group::2) / cluster ------------------------------------------------------
+// A cluster of two CTAs on one TPC issues ONE tcgen05.mma for a 256-row tile: the leader (cluster
+// rank 0) issues, each CTA supplies its own 128 rows of A (tensor memory) and N/2 rows of B
+// (shared memory, same offset in both CTAs) and receives its own 128 accumulator rows.
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {      // every thread of every CTA of the cluster
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// shared::cluster address of `addr` (a shared::cta address of this CTA's layout) in CTA `rank`
+__device__ __forceinline__ uint32_t map_to_cta(uint32_t addr, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
+  return r;
+}
+// Arrive on an mbarrier of another CTA of the cluster.  Default semantics (release at CTA scope):
+// `.release.cluster` compiles to a full memory barrier (ERRBAR) in front of every arrive, which
+// cost the epilogue warps ~30 % of their time; what these arrives order - tcgen05.ld / tcgen05.st
+// against the peer's MMAs - is ordered by the tcgen05 fences, not by the generic proxy.
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait_cluster(uint32_t bar, uint32_t parity) {
+  uint32_t done;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+  return done != 0;
+}
+__device__ __forceinline__ void mbar_wait_cluster(uint32_t bar, uint32_t parity) {
+  if (mbar_try_wait_cluster(bar, parity)) return;
+  const long long t0 = clock64();
+  while (!mbar_try_wait_cluster(bar, parity)) {
+    if (clock64() - t0 > OVDET_MBAR_TIMEOUT_CYCLES) __trap();
+  }
+}
+// TMA load whose completion is signalled on an mbarrier that may live in the PEER CTA of the pair
+// (`bar_cluster` is a shared::cluster address); the data lands in this CTA's shared memory.
+__device__ __forceinline__ void tma_load_3d_pair_if(uint32_t issue, uint32_t dst, const CUtensorMap* m,
+                                                    uint32_t bar_cluster, int c0, int c1, int c2) {
+  asm volatile(
+      "{\n\t.reg .pred q;\n\t"
+      "setp.ne.b32 q, %6, 0;\n\t"
+      "@q cp.async.bulk.tensor.3d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes"
+      " [%0], [%1, {%3, %4, %5}], [%2];\n\t}"
+      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(m)), "r"(bar_cluster), "r"(c0), "r"(c1), "r"(c2), "r"(issue)
+      : "memory");
+}
+template <int CG> __device__ __forceinline__ void tmem_alloc_cg(uint32_t dst_smem, uint32_t cols) {
+  if constexpr (CG == 1)
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem), "r"(cols) : "memory");
+  else
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem), "r"(cols) : "memory");
+}
+template <int CG> __device__ __forceinline__ void tmem_relinquish_cg() {
+  if constexpr (CG == 1) asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  else asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+template <int CG> __device__ __forceinline__ void tmem_dealloc_cg(uint32_t taddr, uint32_t cols) {
+  if constexpr (CG == 1)
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(cols) : "memory");
+  else
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(cols) : "memory");
+}
+template <int CG>
+__device__ __forceinline__ void umma_bf16_ts_cg(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc,
+                                                uint32_t idesc, uint32_t accumulate) {
+  if constexpr (CG == 1)
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}"
+        ::"r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
+  else
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], [%1], %2, %3, p;\n\t}"
+        ::"r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
+}
+// Arrive (once every previously issued MMA of this thread has finished) on the mbarrier at offset
+// `bar` of this CTA (CG == 1) or of BOTH CTAs of the pair (CG == 2, multicast).
+template <int CG> __device__ __forceinline__ void umma_commit_cg(uint32_t bar) {
+  if constexpr (CG == 1) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+  } else {
+    const uint16_t mask = 3;
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+                 ::"r"(bar), "h"(mask) : "memory");
+  }
+}
+
 // ---- UMMA descriptors ----------------------------------------------------------------------
 // Shared-memory matrix descriptor for a K-major bf16 tile stored as rows of 128 bytes
 // (64 elements) with the 128-byte swizzle TMA applies (CU_TENSOR_MAP_SWIZZLE_128B): 8-row

@@ -19,7 +19,7 @@
 //   warp 1      MMA issuer   tcgen05.mma.kind::f16, A FROM TENSOR MEMORY, 128 x N x 16, N <= 128
 //   warp 2      TMA producer, activations [64 k x 128 anchors] fp32 straight from NCHW
 //               (anchors contiguous), 4-stage ring; also owns the TMEM allocation
-//   warp 3      L2 prefetch of the next anchor tile (cp.async.bulk.prefetch.tensor)
+//   warp 3      (idle; optional L2 prefetch of the next anchor tile, off by default)
 //   warps 4-7   converters   thread = anchor row: fp32 smem column -> sum of squares, bf16x2 ->
 //               tcgen05.st into the A region of TMEM (256 columns = 128 rows x 512 k)
 //   warps 8-11  epilogue     tcgen05.ld -> alpha/||x|| scale, +beta, running max/argmax and/or
@@ -29,6 +29,16 @@
 // MMAs of tile n+1), columns [256,512) = the A operand.  A block kb of the NEXT anchor tile is
 // converted as soon as the last N tile of the current one has consumed block kb (per-block
 // mbarriers), so the conversion and the fp32 stream hide behind the MMAs.
+//
+// CTA pairs (CG = 2, the dim = 512 similarity): the kernel runs as clusters of two CTAs on one
+// TPC.  The leader's warp 1 issues tcgen05.mma.cta_group::2 for a 256-anchor x 128-class tile;
+// each CTA converts its own 128 anchors into its own tensor memory, stages only HALF of every
+// text tile (64 classes) in its shared memory and drains its own 128 accumulator rows.  This
+// halves the text bytes every SM pulls from L2 - the bound of the single-CTA kernel (27 GB of
+// L2 -> SM traffic per launch, 12.9 TB/s).  Cross-CTA protocol: both CTAs' text loads complete
+// on the leader's `b_full` (cp.async.bulk.tensor .cta_group::2); tcgen05.commit multicasts
+// `b_empty` / `a_free` / `t_full` to both CTAs; the converter and epilogue warps of the second
+// CTA arrive remotely on the leader's `a_ready` / `t_empty`.
 #include "common.cuh"
 #include "ptx.cuh"
 #include <cstdlib>
@@ -40,9 +50,7 @@ constexpr int F_BLOCK_M = 128;
 constexpr int F_BLOCK_N = 128;
 constexpr int F_BLOCK_K = 64;
 constexpr int F_MAX_KB = 8;                       // dim <= 512: A fills 256 TMEM columns
-constexpr int F_B_STAGES = 4;                     // text ring; with dim = 512 stage == kb & 3 (static)
 constexpr int F_A_STAGES = 4;                     // fp32 activation ring
-constexpr int F_B_STAGE_BYTES = F_BLOCK_N * F_BLOCK_K * 2;     // 16 KiB
 constexpr int F_A_STAGE_BYTES = F_BLOCK_K * F_BLOCK_M * 4;     // 32 KiB fp32 [k][anchor]
 constexpr int F_THREADS = 384;
 constexpr int F_TMEM_COLS = 512;
@@ -51,21 +59,33 @@ constexpr int F_A_COL = 256;
 constexpr int F_PITCH = 33;
 constexpr int F_MAX_LEVELS = 4;
 
+// CG = CTAs per MMA (tcgen05 cta_group): 1 = one CTA per 128-anchor tile; 2 = a CTA PAIR on one
+// 256-anchor tile, each CTA staging HALF of every text tile (64 classes x 64 k = 8 KiB), which
+// halves the L2 -> SM text traffic that bounds the single-CTA kernel.  The text ring always holds
+// 64 KiB (4 x 16 KiB): deep enough to cover the L2 latency, shallow enough that the activation
+// loads issued at an anchor-tile boundary do not queue behind it.  With CG = 2 a stage holds TWO
+// k blocks (two 8 KiB boxes on one barrier), so the single MMA-issuing thread - which now has
+// half the time per k block - synchronises once per 8 MMAs instead of once per 4.
+template <int CG>
 struct FSmem {
+  static constexpr int kps = CG;                                     // k blocks per text stage
+  static constexpr int b_sub_bytes = (F_BLOCK_N / CG) * F_BLOCK_K * 2;  // one TMA box: [N / CG rows x 64 k]
+  static constexpr int b_stages = 4;
+  static constexpr int b_stage_bytes = kps * b_sub_bytes;            // 16 KiB
   static constexpr int b_off = 0;
-  static constexpr int a_off = b_off + F_B_STAGES * F_B_STAGE_BYTES;                 // 64 KiB
+  static constexpr int a_off = b_off + b_stages * b_stage_bytes;                     // 64 KiB
   static constexpr int epi_off = a_off + F_A_STAGES * F_A_STAGE_BYTES;               // +128 KiB
   static constexpr int epi_bytes = 4 * 32 * F_PITCH * 4;
   static constexpr int norm_off = epi_off + epi_bytes;
   static constexpr int norm_bytes = 3 * F_BLOCK_M * 4;
   static constexpr int bar_off = norm_off + norm_bytes;
   // b_full, b_empty, as_full, as_empty, a_ready, a_free, tmem_full, tmem_empty, norm_ready
-  static constexpr int num_bars = 2 * F_B_STAGES + 2 * F_A_STAGES + 2 * F_MAX_KB + 2 + 2 + 3;
+  static constexpr int num_bars = 2 * b_stages + 2 * F_A_STAGES + 2 * F_MAX_KB + 2 + 2 + 3;
   static constexpr int tmem_ptr_off = bar_off + num_bars * 8;
   static constexpr int total = tmem_ptr_off + 16;
+  static constexpr int bytes = total + 1024;
 };
-constexpr int F_SMEM_BYTES = FSmem::total + 1024;
-static_assert(F_SMEM_BYTES <= 227 * 1024, "shared memory budget");
+static_assert(FSmem<1>::bytes <= 227 * 1024 && FSmem<2>::bytes <= 227 * 1024, "shared memory budget");
 
 struct LevelMaps { CUtensorMap m[F_MAX_LEVELS]; };
 
@@ -93,9 +113,16 @@ struct FusedParams {
   int dbg;
 };
 
+// With CG == 2 the two CTAs of a pair take tiles 2i and 2i+1; `mt` is then rounded up to an even
+// count per (level, image) when the text is per-image, so that a pair never straddles two images
+// (both CTAs multiply against the same text tile).  A tile index past the end, or an M tile that
+// starts past the level's last anchor, has rows <= 0: it loads zeros (TMA out-of-bounds fill)
+// and writes nothing.
 struct TileCoord { int b, level, m0, rows; long long out_row0; };
 
 __device__ __forceinline__ TileCoord decode_tile(const FusedParams& p, int tile) {
+  const bool past_end = tile >= p.tile_start[p.levels];
+  if (past_end) tile = p.tile_start[p.levels] - 1;
   int l = 0;
 #pragma unroll
   for (int i = 1; i < F_MAX_LEVELS; ++i)
@@ -105,7 +132,7 @@ __device__ __forceinline__ TileCoord decode_tile(const FusedParams& p, int tile)
   t.level = l;
   t.b = r / p.mt[l];
   t.m0 = (r - t.b * p.mt[l]) * F_BLOCK_M;
-  t.rows = min(F_BLOCK_M, p.hw[l] - t.m0);
+  t.rows = past_end ? 0 : min(F_BLOCK_M, p.hw[l] - t.m0);
   t.out_row0 = (long long)t.b * p.anchors + p.off[l] + t.m0;
   return t;
 }
@@ -115,10 +142,19 @@ __device__ __forceinline__ TileCoord decode_tile(const FusedParams& p, int tile)
 // hi = bf16(x), lo = bf16(x - hi); the activation blocks are written to tensor memory as
 // [hi | hi | lo] and the text operand is laid out [hi | lo | hi] (ovdet_cast_text), so the plain
 // block loop accumulates hi*hi + hi*lo + lo*hi (the lo*lo term is < 2^-16 relative).
-template <int KB_T, bool SPLIT3>
+template <int KB_T, bool SPLIT3, int CG>
 __global__ void __launch_bounds__(F_THREADS, 1)
 sim_fused_kernel(const __grid_constant__ LevelMaps amaps, const __grid_constant__ CUtensorMap tmap_b,
                  const FusedParams p) {
+  using FSmem = ovdet::FSmem<CG>;
+  constexpr int F_B_STAGES = FSmem::b_stages;
+  constexpr int F_B_STAGE_BYTES = FSmem::b_stage_bytes;
+  constexpr int KPS = FSmem::kps;
+  constexpr int F_B_SUB_BYTES = FSmem::b_sub_bytes;
+  static_assert(CG == 1 || KB_T % KPS == 0, "CTA pairs need a compile-time, even k-block count");
+  // cluster rank: 0 = leader (issues the MMAs, owns the barriers the pair synchronises on)
+  const uint32_t rank = CG == 2 ? ptx::cluster_ctarank() : 0u;
+  const int pair0 = blockIdx.x / CG, pair_stride = gridDim.x / CG;
   extern __shared__ unsigned char smem_dyn[];
   const uint32_t raw = ptx::smem_u32(smem_dyn);
   const uint32_t base = (raw + 1023u) & ~1023u;
@@ -150,21 +186,28 @@ sim_fused_kernel(const __grid_constant__ LevelMaps amaps, const __grid_constant_
     for (int l = 0; l < p.levels; ++l) ptx::prefetch_tmap(&amaps.m[l]);
     for (int s = 0; s < F_B_STAGES; ++s) { ptx::mbar_init(b_full0 + 8u * s, 1); ptx::mbar_init(b_empty0 + 8u * s, 1); }
     for (int s = 0; s < F_A_STAGES; ++s) { ptx::mbar_init(as_full0 + 8u * s, 1); ptx::mbar_init(as_empty0 + 8u * s, 4); }
-    for (int k = 0; k < F_MAX_KB; ++k) { ptx::mbar_init(a_ready0 + 8u * k, 4); ptx::mbar_init(a_free0 + 8u * k, 1); }
-    for (int s = 0; s < 2; ++s) { ptx::mbar_init(t_full0 + 8u * s, 1); ptx::mbar_init(t_empty0 + 8u * s, 4); }
+    // a_ready / t_empty collect the converter / epilogue warps of BOTH CTAs on the leader
+    for (int k = 0; k < F_MAX_KB; ++k) { ptx::mbar_init(a_ready0 + 8u * k, 4 * CG); ptx::mbar_init(a_free0 + 8u * k, 1); }
+    for (int s = 0; s < 2; ++s) { ptx::mbar_init(t_full0 + 8u * s, 1); ptx::mbar_init(t_empty0 + 8u * s, 4 * CG); }
     for (int s = 0; s < 3; ++s) ptx::mbar_init(n_ready0 + 8u * s, 4);
     ptx::fence_mbar_init();
   }
   if (warp == 2) {
-    ptx::tmem_alloc(base + FSmem::tmem_ptr_off, F_TMEM_COLS);
-    ptx::tmem_relinquish();
+    ptx::tmem_alloc_cg<CG>(base + FSmem::tmem_ptr_off, F_TMEM_COLS);
+    ptx::tmem_relinquish_cg<CG>();
   }
   ptx::tc_fence_before();
-  __syncthreads();
+  if constexpr (CG == 2) ptx::cluster_sync_all();      // peer barriers are initialised before any remote arrive
+  else __syncthreads();
   ptx::tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_smem;
 
   const int total_tiles = p.tile_start[p.levels];
+  const int total_pairs = (total_tiles + CG - 1) / CG;
+  // barriers of the leader CTA that both CTAs arrive on (shared::cluster addresses)
+  const uint32_t lead_b_full0 = CG == 2 ? ptx::map_to_cta(b_full0, 0) : b_full0;
+  const uint32_t lead_a_ready0 = CG == 2 ? ptx::map_to_cta(a_ready0, 0) : a_ready0;
+  const uint32_t lead_t_empty0 = CG == 2 ? ptx::map_to_cta(t_empty0, 0) : t_empty0;
   const int KB = KB_T ? KB_T : p.kb;
   const int KB_IN = KB_T ? KB_T : p.kb_in;
   const int NT = p.n_tiles;
@@ -175,59 +218,86 @@ sim_fused_kernel(const __grid_constant__ LevelMaps amaps, const __grid_constant_
     // ================================ text (B) producer ======================================
     const uint32_t issue = ptx::elect_one();
     uint32_t g = 0;                                    // N tiles produced so far
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+    for (int pair = pair0; pair < total_pairs; pair += pair_stride) {
+      const int tile = pair * CG + (int)rank;
       const TileCoord tc = decode_tile(p, tile);
       const int tb = p.text_batched ? tc.b : 0;
       for (int nt = 0; nt < NT; ++nt, ++g) {
+        int n_size = p.classes - nt * F_BLOCK_N;
+        n_size = n_size >= F_BLOCK_N ? F_BLOCK_N : ((n_size + 15) & ~15);
+        const int n_half = n_size >> 1;
+        (void)n_half;
 #pragma unroll
-        for (int kb = 0; kb < KB; ++kb) {
-          const uint32_t it = g * (uint32_t)KB + (uint32_t)kb;       // k blocks produced so far
+        for (int sb = 0; sb < KB / KPS; ++sb) {
+          const uint32_t it = g * (uint32_t)(KB / KPS) + (uint32_t)sb;     // stages produced so far
           const uint32_t s = it % F_B_STAGES, ph = (it / F_B_STAGES) & 1u;
           ptx::mbar_wait(b_empty0 + 8u * s, ph ^ 1u);
-          ptx::mbar_arrive_expect_tx_if(issue, b_full0 + 8u * s, F_B_STAGE_BYTES);
-          ptx::tma_load_3d_if(issue, smem_b + s * F_B_STAGE_BYTES, &tmap_b, b_full0 + 8u * s,
-                              kb * F_BLOCK_K, nt * F_BLOCK_N, tb);
+          if constexpr (CG == 1) {
+            ptx::mbar_arrive_expect_tx_if(issue, b_full0 + 8u * s, F_B_STAGE_BYTES);
+            ptx::tma_load_3d_if(issue, smem_b + s * F_B_STAGE_BYTES, &tmap_b, b_full0 + 8u * s,
+                                sb * F_BLOCK_K, nt * F_BLOCK_N, tb);
+          } else {
+            // this CTA's half of the N tile (rows [rank * n/2, (rank + 1) * n/2) of it) lands in its
+            // own shared memory; both halves complete on the LEADER's barrier, which expects both
+            if (rank == 0) ptx::mbar_arrive_expect_tx_if(issue, b_full0 + 8u * s, 2 * F_B_STAGE_BYTES);
+#pragma unroll
+            for (int j = 0; j < KPS; ++j)
+              ptx::tma_load_3d_pair_if(issue, smem_b + s * F_B_STAGE_BYTES + j * F_B_SUB_BYTES, &tmap_b,
+                                       lead_b_full0 + 8u * s, (sb * KPS + j) * F_BLOCK_K,
+                                       nt * F_BLOCK_N + (int)rank * n_half, tb);
+          }
         }
       }
     }
-  } else if (warp == 1) {
-    // ================================ MMA issuer =============================================
+  } else if (warp == 1 && rank == 0) {
+    // ================================ MMA issuer (leader CTA) ================================
     // broadcast from lane 0 so that the compiler keeps every MMA operand in uniform registers
     const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem_base, 0);
+    const uint32_t smem_b_u = __shfl_sync(0xffffffffu, smem_b, 0);
     uint32_t g = 0, lt = 0;
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++lt) {
+    for (int pair = pair0; pair < total_pairs; pair += pair_stride, ++lt) {
       for (int nt = 0; nt < NT; ++nt, ++g) {
         int n_size = p.classes - nt * F_BLOCK_N;
         n_size = n_size >= F_BLOCK_N ? F_BLOCK_N : ((n_size + 15) & ~15);
-        const uint32_t idesc = ptx::umma_idesc_bf16_f32(F_BLOCK_M, (uint32_t)n_size);
+        const uint32_t idesc = ptx::umma_idesc_bf16_f32(F_BLOCK_M * CG, (uint32_t)n_size);
         const uint32_t as = g & 1u;
         const bool first_nt = nt == 0, last_nt = nt == NT - 1;
-        const uint32_t it0 = g * (uint32_t)KB;
+        const uint32_t it0 = g * (uint32_t)(KB / KPS);
         // peek at the first text stage while waiting for the accumulator to drain
         bool ready = ptx::mbar_try_wait(b_full0 + 8u * (it0 % F_B_STAGES), (it0 / F_B_STAGES) & 1u);
         ptx::mbar_wait(t_empty0 + 8u * as, ((g >> 1) & 1u) ^ 1u);
         const uint32_t d_tmem = tmem_u + (uint32_t)F_ACC_COL + as * (uint32_t)F_BLOCK_N;
 #pragma unroll
-        for (int kb = 0; kb < KB; ++kb) {
-          const uint32_t it = it0 + (uint32_t)kb;
+        for (int sb = 0; sb < KB / KPS; ++sb) {
+          const uint32_t it = it0 + (uint32_t)sb;
           const uint32_t s = it % F_B_STAGES, ph = (it / F_B_STAGES) & 1u;
-          if (first_nt) ptx::mbar_wait(a_ready0 + 8u * kb, lt & 1u);     // A block converted?
+          if (first_nt) {                                                // A blocks converted (both CTAs)?
+#pragma unroll
+            for (int j = 0; j < KPS; ++j) ptx::mbar_wait(a_ready0 + 8u * (sb * KPS + j), lt & 1u);
+          }
           ptx::mbar_wait_if_not(ready, b_full0 + 8u * s, ph);
           ptx::tc_fence_after();
-          if (kb + 1 < KB)                                               // hide the next wait's latency
+          if (sb + 1 < KB / KPS)                                         // hide the next wait's latency
             ready = ptx::mbar_try_wait(b_full0 + 8u * ((it + 1) % F_B_STAGES), ((it + 1) / F_B_STAGES) & 1u);
-          const uint64_t b_desc = ptx::umma_desc_k_sw128(smem_b + s * F_B_STAGE_BYTES);
-          const uint32_t a_tmem = tmem_u + (uint32_t)(F_A_COL + kb * 32);
           if (ptx::elect_one()) {
 #pragma unroll
-            for (int k = 0; k < F_BLOCK_K / 16; ++k)
-              ptx::umma_bf16_ts(d_tmem, a_tmem + 8u * k, b_desc + 2u * k, idesc, (kb | k) != 0);
-            ptx::umma_commit(b_empty0 + 8u * s);                  // text stage reusable
-            if (last_nt) ptx::umma_commit(a_free0 + 8u * kb);     // A block kb may be overwritten
+            for (int j = 0; j < KPS; ++j) {
+              const int kb = sb * KPS + j;
+              const uint64_t b_desc = ptx::umma_desc_k_sw128(smem_b_u + s * F_B_STAGE_BYTES + j * F_B_SUB_BYTES);
+              const uint32_t a_tmem = tmem_u + (uint32_t)(F_A_COL + kb * 32);
+#pragma unroll
+              for (int k = 0; k < F_BLOCK_K / 16; ++k)
+                ptx::umma_bf16_ts_cg<CG>(d_tmem, a_tmem + 8u * k, b_desc + 2u * k, idesc, (kb | k) != 0);
+            }
+            ptx::umma_commit_cg<CG>(b_empty0 + 8u * s);                  // text stage reusable (both CTAs)
+            if (last_nt) {                                               // these A blocks may be overwritten
+#pragma unroll
+              for (int j = 0; j < KPS; ++j) ptx::umma_commit_cg<CG>(a_free0 + 8u * (sb * KPS + j));
+            }
           }
           __syncwarp();
         }
-        if (ptx::elect_one()) ptx::umma_commit(t_full0 + 8u * as);
+        if (ptx::elect_one()) ptx::umma_commit_cg<CG>(t_full0 + 8u * as);
         __syncwarp();
       }
     }
@@ -235,7 +305,8 @@ sim_fused_kernel(const __grid_constant__ LevelMaps amaps, const __grid_constant_
     // ================================ activation (A) producer ================================
     const uint32_t issue = ptx::elect_one();
     uint32_t ia = 0;
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+    for (int pair = pair0; pair < total_pairs; pair += pair_stride) {
+      const int tile = pair * CG + (int)rank;
       const TileCoord tc = decode_tile(p, tile);
       const CUtensorMap* map = &amaps.m[tc.level];
 #pragma unroll
@@ -250,15 +321,22 @@ sim_fused_kernel(const __grid_constant__ LevelMaps amaps, const __grid_constant_
     }
   } else if (warp == 3) {
     // ================================ L2 prefetcher ==========================================
-    // Only A_STAGES + 1 blocks of the next anchor tile can be staged before the current tile
-    // releases its TMEM blocks, so the rest of the fp32 tile is fetched inside the last N tile.
-    // Pull the whole next tile into L2 one tile ahead so that those loads are L2 hits.
+    // Experiment kept behind OVDET_DBG=1: pull the next anchor tile into L2 one tile ahead.  With
+    // the 2-stage activation ring of the first version it hid the HBM latency of the loads issued
+    // at a tile boundary; with the 4-stage ring it only competes with the text stream for the
+    // SM's TMA path (measured 2.25 ms with it vs 2.14 ms without, single-CTA kernel), so it is off.
     const uint32_t issue = ptx::elect_one();
     uint32_t lt = 0;
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++lt) {
-      const int next = tile + gridDim.x;
-      if (next >= total_tiles || (p.dbg & 1)) break;
-      ptx::mbar_wait(a_ready0, lt & 1u);               // conversion of the current tile has begun
+    for (int pair = pair0; pair < total_pairs; pair += pair_stride, ++lt) {
+      const int tile = pair * CG + (int)rank;
+      const int next = tile + pair_stride * CG;
+      if (next >= total_tiles || !(p.dbg & 1)) break;       // off unless OVDET_DBG bit 0 is set
+      if (CG == 1 && (p.dbg & 4)) {
+        ptx::mbar_wait(a_ready0, lt & 1u);
+      } else {                                         // the current tile's first N tile is done
+        const uint32_t g0 = lt * (uint32_t)NT;
+        ptx::mbar_wait(t_full0 + 8u * (g0 & 1u), (g0 >> 1) & 1u);
+      }
       const TileCoord tc = decode_tile(p, next);
       const CUtensorMap* map = &amaps.m[tc.level];
 #pragma unroll
@@ -270,7 +348,8 @@ sim_fused_kernel(const __grid_constant__ LevelMaps amaps, const __grid_constant_
     const int lg = warp & 3;
     const int arow = lg * 32 + lane;                 // anchor row of the tile == TMEM lane
     uint32_t ia = 0, lt = 0;
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++lt) {
+    for (int pair = pair0; pair < total_pairs; pair += pair_stride, ++lt) {
+      const int tile = pair * CG + (int)rank;
       const TileCoord tc = decode_tile(p, tile);
       float ss0 = 0.f, ss1 = 0.f, ss2 = 0.f, ss3 = 0.f;
       // block `t` of the A region: wait until the previous tile's MMAs have read it, store, publish
@@ -281,7 +360,10 @@ sim_fused_kernel(const __grid_constant__ LevelMaps amaps, const __grid_constant_
         ptx::tmem_st_wait();
         ptx::tc_fence_before();
         __syncwarp();
-        if (lane == 0) ptx::mbar_arrive(a_ready0 + 8u * t);
+        if (lane == 0) {
+          if constexpr (CG == 2) ptx::mbar_arrive_cluster(lead_a_ready0 + 8u * t);
+          else ptx::mbar_arrive(a_ready0 + 8u * t);
+        }
       };
 #pragma unroll
       for (int kb = 0; kb < KB_IN; ++kb, ++ia) {
@@ -327,7 +409,8 @@ sim_fused_kernel(const __grid_constant__ LevelMaps amaps, const __grid_constant_
     float* stage = epi_stage + lg * 32 * F_PITCH;
     const bool want_max = p.row_max != nullptr;
     uint32_t acc_it = 0, lt = 0;
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++lt) {
+    for (int pair = pair0; pair < total_pairs; pair += pair_stride, ++lt) {
+      const int tile = pair * CG + (int)rank;
       const TileCoord tc = decode_tile(p, tile);
       const int r_in_tile = lg * 32 + lane;
       const bool row_ok = r_in_tile < tc.rows;
@@ -338,11 +421,14 @@ sim_fused_kernel(const __grid_constant__ LevelMaps amaps, const __grid_constant_
       const float beta = p.beta;
       float bv[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
       int bi[4] = {0, 0, 0, 0};
-      // Max without argmax or logits (the attention row): the row scale is >= 0, so
-      // max_c fma(scale, acc_c, beta) == fma(scale, max_c acc_c, beta) exactly (rounding is
-      // monotone) and the running maximum is taken over the raw accumulators, one FMNMX3 per
-      // two values instead of FFMA + compare + two selects per value.
-      const bool max_only = want_max && p.row_arg == nullptr && p.logits == nullptr && p.alpha >= 0.f;
+      // No logits to write and a row scale >= 0: max_c fma(scale, acc_c, beta) ==
+      // fma(scale, max_c acc_c, beta) exactly (rounding is monotone), so the running maximum is
+      // taken over the RAW accumulators and the affine map is applied once per row.  Scores only
+      // (the attention row): one FMNMX3 per two values.  With argmax: compare + select + index
+      // per value, no FFMA; the class returned is the argmax of the fp32 accumulators (lowest
+      // index among equal accumulators).
+      const bool raw_mode = want_max && p.logits == nullptr && p.alpha >= 0.f && !(p.dbg & 2);
+      const bool max_only = raw_mode && p.row_arg == nullptr;
       float raw_best = -INFINITY;
       for (int nt = 0; nt < NT; ++nt, ++acc_it) {
         const int n0 = nt * F_BLOCK_N;
@@ -372,8 +458,10 @@ sim_fused_kernel(const __grid_constant__ LevelMaps amaps, const __grid_constant_
             raw_best = fmaxf(m0, m1);
             return;
           }
+          if (!raw_mode) {
 #pragma unroll
-          for (int j = 0; j < 32; ++j) r[j] = __float_as_uint(fmaf(scale, __uint_as_float(r[j]), beta));
+            for (int j = 0; j < 32; ++j) r[j] = __float_as_uint(fmaf(scale, __uint_as_float(r[j]), beta));
+          }
           if (want_max) {
             const int col = n0 + c0;
             if (valid >= 32) {
@@ -425,7 +513,10 @@ sim_fused_kernel(const __grid_constant__ LevelMaps amaps, const __grid_constant_
         }
         ptx::tc_fence_before();
         __syncwarp();
-        if (lane == 0) ptx::mbar_arrive(t_empty0 + 8u * as);
+        if (lane == 0) {
+          if constexpr (CG == 2) ptx::mbar_arrive_cluster(lead_t_empty0 + 8u * as);
+          else ptx::mbar_arrive(t_empty0 + 8u * as);
+        }
       }
       if (max_only) {
         if (row_ok) p.row_max[grow] = fmaf(scale, raw_best, beta);
@@ -435,6 +526,7 @@ sim_fused_kernel(const __grid_constant__ LevelMaps amaps, const __grid_constant_
 #pragma unroll
         for (int q = 1; q < 4; ++q)
           if (bv[q] > best || (bv[q] == best && bi[q] < best_idx)) { best = bv[q]; best_idx = bi[q]; }
+        if (raw_mode) best = fmaf(scale, best, beta);
         p.row_max[grow] = best;
         if (p.row_arg != nullptr) p.row_arg[grow] = best_idx;
       }
@@ -442,10 +534,11 @@ sim_fused_kernel(const __grid_constant__ LevelMaps amaps, const __grid_constant_
   }
 
   ptx::tc_fence_before();
-  __syncthreads();
+  if constexpr (CG == 2) ptx::cluster_sync_all();      // the peer may still read this CTA's smem / TMEM
+  else __syncthreads();
   if (warp == 2) {
     ptx::tc_fence_after();
-    ptx::tmem_dealloc(tmem_base, F_TMEM_COLS);
+    ptx::tmem_dealloc_cg<CG>(tmem_base, F_TMEM_COLS);
   }
 }
 
@@ -485,6 +578,9 @@ int fused_launch(const float* const* obj_embeds, const int64_t* hw, const int64_
     return OVDET_ERR_INVALID_ARG;
   const int kb_in = (int)ceil_div<int64_t>(dim, F_BLOCK_K);
   const int kb = kb_in * (split3 ? 3 : 1);
+  // CTA pairs (cta_group::2) for the dim = 512 similarity; OVDET_FUSED_CG=1 forces single CTAs
+  static const int cg_env = []() { const char* e = getenv("OVDET_FUSED_CG"); return e ? atoi(e) : 2; }();
+  const int cg = (kb == 8 && !split3 && cg_env == 2) ? 2 : 1;
   if (num_levels > F_MAX_LEVELS || kb > F_MAX_KB || batch > 65535) return OVDET_ERR_UNSUPPORTED_SHAPE;
   if ((uintptr_t)text_op & 15) return OVDET_ERR_INVALID_ARG;
   EncodeTiledFn enc = nullptr;
@@ -498,6 +594,7 @@ int fused_launch(const float* const* obj_embeds, const int64_t* hw, const int64_
       return OVDET_ERR_UNSUPPORTED_SHAPE;
     p.hw[l] = (int)hw[l];
     p.mt[l] = (int)ceil_div<int64_t>(hw[l], F_BLOCK_M);
+    if (cg == 2 && text_batched) p.mt[l] = (p.mt[l] + 1) & ~1;     // a pair never straddles two images
     p.off[l] = (int)anchors;
     p.tile_start[l] = (int)tiles;
     anchors += hw[l];
@@ -526,7 +623,7 @@ int fused_launch(const float* const* obj_embeds, const int64_t* hw, const int64_
     const int64_t kop = (int64_t)kb * F_BLOCK_K;
     cuuint64_t dims[3] = {(cuuint64_t)kop, (cuuint64_t)classes, (cuuint64_t)tb};
     cuuint64_t strides[2] = {(cuuint64_t)kop * 2, (cuuint64_t)classes * (cuuint64_t)kop * 2};
-    cuuint32_t box[3] = {(cuuint32_t)F_BLOCK_K, (cuuint32_t)F_BLOCK_N, 1};
+    cuuint32_t box[3] = {(cuuint32_t)F_BLOCK_K, (cuuint32_t)(F_BLOCK_N / cg), 1};
     cuuint32_t estr[3] = {1, 1, 1};
     CUresult r = enc(&map_b, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(text_op), dims, strides,
                      box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
@@ -555,18 +652,36 @@ int fused_launch(const float* const* obj_embeds, const int64_t* hw, const int64_
 
   static bool attr_set = false;
   if (!attr_set) {
-    OVDET_CUDA_TRY(cudaFuncSetAttribute(sim_fused_kernel<8, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, F_SMEM_BYTES));
-    OVDET_CUDA_TRY(cudaFuncSetAttribute(sim_fused_kernel<0, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, F_SMEM_BYTES));
-    OVDET_CUDA_TRY(cudaFuncSetAttribute(sim_fused_kernel<0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, F_SMEM_BYTES));
+    OVDET_CUDA_TRY(cudaFuncSetAttribute(sim_fused_kernel<8, false, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, FSmem<1>::bytes));
+    OVDET_CUDA_TRY(cudaFuncSetAttribute(sim_fused_kernel<0, false, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, FSmem<1>::bytes));
+    OVDET_CUDA_TRY(cudaFuncSetAttribute(sim_fused_kernel<0, true, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, FSmem<1>::bytes));
+    OVDET_CUDA_TRY(cudaFuncSetAttribute(sim_fused_kernel<8, false, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, FSmem<2>::bytes));
     attr_set = true;
+  }
+  if (cg == 2) {
+    // one CTA per SM, launched as clusters of two (the pair shares a TPC)
+    const long long pairs = (tiles + 1) / 2;
+    const int max_pairs = sm_count() / 2;
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3((unsigned)(2 * (pairs < max_pairs ? pairs : max_pairs)));
+    cfg.blockDim = dim3(F_THREADS);
+    cfg.dynamicSmemBytes = FSmem<2>::bytes;
+    cfg.stream = as_stream(stream);
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    OVDET_CUDA_TRY(cudaLaunchKernelEx(&cfg, sim_fused_kernel<8, false, 2>, maps, map_b, p));
+    return OVDET_OK;
   }
   const int grid = (int)(tiles < sm_count() ? tiles : sm_count());
   if (split3)
-    sim_fused_kernel<0, true><<<grid, F_THREADS, F_SMEM_BYTES, as_stream(stream)>>>(maps, map_b, p);
+    sim_fused_kernel<0, true, 1><<<grid, F_THREADS, FSmem<1>::bytes, as_stream(stream)>>>(maps, map_b, p);
   else if (p.kb == 8)
-    sim_fused_kernel<8, false><<<grid, F_THREADS, F_SMEM_BYTES, as_stream(stream)>>>(maps, map_b, p);
+    sim_fused_kernel<8, false, 1><<<grid, F_THREADS, FSmem<1>::bytes, as_stream(stream)>>>(maps, map_b, p);
   else
-    sim_fused_kernel<0, false><<<grid, F_THREADS, F_SMEM_BYTES, as_stream(stream)>>>(maps, map_b, p);
+    sim_fused_kernel<0, false, 1><<<grid, F_THREADS, FSmem<1>::bytes, as_stream(stream)>>>(maps, map_b, p);
   OVDET_LAUNCH_CHECK();
   return OVDET_OK;
 }
