@@ -500,6 +500,47 @@ sim_fused_kernel(const __grid_constant__ LevelMaps amaps, const __grid_constant_
         };
 
         uint32_t ra[32], rb[32];
+        if (raw_mode && n_valid == F_BLOCK_N) {
+          // Hot path (full tile, no logits): straight-line, and the accumulator is handed back to
+          // the MMA warp as soon as its last 32 columns are in registers - the compare work on
+          // that chunk runs after the arrive, off the MMA -> epilogue -> MMA critical chain.
+          auto scan = [&](const uint32_t (&r)[32], int col) {
+            if (max_only) {
+              float m0 = raw_best, m1 = -INFINITY;
+#pragma unroll
+              for (int j = 0; j < 32; j += 4) {
+                m0 = fmaxf(m0, fmaxf(__uint_as_float(r[j]), __uint_as_float(r[j + 1])));
+                m1 = fmaxf(m1, fmaxf(__uint_as_float(r[j + 2]), __uint_as_float(r[j + 3])));
+              }
+              raw_best = fmaxf(m0, m1);
+            } else {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) {
+                const float v = __uint_as_float(r[j]);
+                if (v > bv[j & 3]) { bv[j & 3] = v; bi[j & 3] = col + j; }
+              }
+            }
+          };
+          ptx::tmem_ld_32x32(t_row, ra);
+          ptx::tmem_ld_wait();
+          ptx::tmem_ld_32x32(t_row + 32u, rb);
+          scan(ra, n0);
+          ptx::tmem_ld_wait();
+          ptx::tmem_ld_32x32(t_row + 64u, ra);
+          scan(rb, n0 + 32);
+          ptx::tmem_ld_wait();
+          ptx::tmem_ld_32x32(t_row + 96u, rb);
+          scan(ra, n0 + 64);
+          ptx::tmem_ld_wait();
+          ptx::tc_fence_before();
+          __syncwarp();
+          if (lane == 0) {
+            if constexpr (CG == 2) ptx::mbar_arrive_cluster(lead_t_empty0 + 8u * as);
+            else ptx::mbar_arrive(t_empty0 + 8u * as);
+          }
+          scan(rb, n0 + 96);
+          continue;
+        }
         ptx::tmem_ld_32x32(t_row, ra);
         for (int c = 0; c < nchunks; c += 2) {
           ptx::tmem_ld_wait();
