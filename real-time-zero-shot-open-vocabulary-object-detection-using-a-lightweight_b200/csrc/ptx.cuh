@@ -47,6 +47,19 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   }
 }
 
+// Wait of a warp that is NOT on the MMA critical chain (producers waiting for a free stage,
+// converters waiting for the previous tile's MMAs): back off between polls so that the spinning
+// warp does not take issue slots from the epilogue warp on the same SM sub-partition, nor power
+// from the tensor pipe (the kernel runs at the 1 kW cap).
+__device__ __forceinline__ void mbar_wait_lazy(uint32_t bar, uint32_t parity, unsigned ns = 64) {
+  if (mbar_try_wait(bar, parity)) return;
+  const long long t0 = clock64();
+  while (!mbar_try_wait(bar, parity)) {
+    if (ns) __nanosleep(ns);
+    if (clock64() - t0 > OVDET_MBAR_TIMEOUT_CYCLES) __trap();
+  }
+}
+
 // ---- TMA -----------------------------------------------------------------------------------
 __device__ __forceinline__ void prefetch_tmap(const CUtensorMap* m) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(m)) : "memory");

@@ -202,6 +202,7 @@ sim_fused_kernel(const __grid_constant__ LevelMaps amaps, const __grid_constant_
   ptx::tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_smem;
 
+  const unsigned lazy_ns = (p.dbg & 16) ? 0u : ((p.dbg & 32) ? 256u : 64u);   // back-off of the non-critical waits
   const int total_tiles = p.tile_start[p.levels];
   const int total_pairs = (total_tiles + CG - 1) / CG;
   // barriers of the leader CTA that both CTAs arrive on (shared::cluster addresses)
@@ -231,7 +232,7 @@ sim_fused_kernel(const __grid_constant__ LevelMaps amaps, const __grid_constant_
         for (int sb = 0; sb < KB / KPS; ++sb) {
           const uint32_t it = g * (uint32_t)(KB / KPS) + (uint32_t)sb;     // stages produced so far
           const uint32_t s = it % F_B_STAGES, ph = (it / F_B_STAGES) & 1u;
-          ptx::mbar_wait(b_empty0 + 8u * s, ph ^ 1u);
+          ptx::mbar_wait_lazy(b_empty0 + 8u * s, ph ^ 1u, lazy_ns);
           if constexpr (CG == 1) {
             ptx::mbar_arrive_expect_tx_if(issue, b_full0 + 8u * s, F_B_STAGE_BYTES);
             ptx::tma_load_3d_if(issue, smem_b + s * F_B_STAGE_BYTES, &tmap_b, b_full0 + 8u * s,
@@ -313,7 +314,7 @@ sim_fused_kernel(const __grid_constant__ LevelMaps amaps, const __grid_constant_
       for (int kb = 0; kb < KB_IN; ++kb, ++ia) {
         const uint32_t s = ia % F_A_STAGES;
         const uint32_t ph = (ia / F_A_STAGES) & 1u;
-        ptx::mbar_wait(as_empty0 + 8u * s, ph ^ 1u);
+        ptx::mbar_wait_lazy(as_empty0 + 8u * s, ph ^ 1u, lazy_ns);
         ptx::mbar_arrive_expect_tx_if(issue, as_full0 + 8u * s, F_A_STAGE_BYTES);
         ptx::tma_load_3d_if(issue, smem_a + s * F_A_STAGE_BYTES, map, as_full0 + 8u * s, tc.m0,
                             kb * F_BLOCK_K, tc.b);
@@ -354,7 +355,7 @@ sim_fused_kernel(const __grid_constant__ LevelMaps amaps, const __grid_constant_
       float ss0 = 0.f, ss1 = 0.f, ss2 = 0.f, ss3 = 0.f;
       // block `t` of the A region: wait until the previous tile's MMAs have read it, store, publish
       auto publish = [&](int t, const uint32_t (&regs)[32]) {
-        ptx::mbar_wait(a_free0 + 8u * t, (lt & 1u) ^ 1u);
+        ptx::mbar_wait_lazy(a_free0 + 8u * t, (lt & 1u) ^ 1u, lazy_ns >> 1);
         ptx::tc_fence_after();
         ptx::tmem_st_32x32(tmem_base + ((uint32_t)(lg * 32) << 16) + (uint32_t)(F_A_COL + t * 32), regs);
         ptx::tmem_st_wait();
@@ -368,7 +369,7 @@ sim_fused_kernel(const __grid_constant__ LevelMaps amaps, const __grid_constant_
 #pragma unroll
       for (int kb = 0; kb < KB_IN; ++kb, ++ia) {
         const uint32_t s = ia % F_A_STAGES;
-        ptx::mbar_wait(as_full0 + 8u * s, (ia / F_A_STAGES) & 1u);
+        ptx::mbar_wait_lazy(as_full0 + 8u * s, (ia / F_A_STAGES) & 1u, lazy_ns >> 1);
         const float* col = a_stage_ptr + s * (F_A_STAGE_BYTES / 4) + arow;
         uint32_t packed[32];
         uint32_t packed_lo[32];                            // dead (eliminated) unless SPLIT3
