@@ -111,7 +111,7 @@ def ncu_traffic(kernel_substr: str, batch: int):
     """DRAM bytes per launch (dram__bytes_read.sum + dram__bytes_write.sum) of the dominant kernel
     from the committed `ncu --set full` capture of this same workload (profiles/, batch 256);
     None when the run's shape differs from the captured one."""
-    path = os.path.join(ROOT, "profiles", "r1_ncu_full_pipeline_b256_v3.json")
+    path = os.path.join(ROOT, "profiles", "r1_ncu_full_pipeline_b256_v4.json")
     if batch != 256 or (IMAGE_SIZE, NUM_CLASSES) != (640, 1203) or not os.path.exists(path):
         return None
     scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
@@ -350,7 +350,7 @@ def run_ours(args):
             "roofline": {"bound": "tensor", "kernel": kernel, "achieved": achieved,
                          "peak": peaks["tflops"], "unit": "TFLOP/s", "frac": achieved / peaks["tflops"],
                          "traffic": ncu_traffic("sim_fused" if fused else "sim_gemm", batch),
-                         "traffic_source": "profiles/r1_ncu_full_pipeline_b256_v3.json (ncu --set full, bytes per launch)",
+                         "traffic_source": "profiles/r1_ncu_full_pipeline_b256_v4.json (ncu --set full, bytes per launch)",
                          "algorithmic_bytes": batch * anchors * (EMBED_DIM * 4 + 12) + NUM_CLASSES * EMBED_DIM * 2,
                          "peak_source": peaks["source"] + " (bf16_tflops_sustained)",
                          "ms_per_launch": stages["similarity"]},
