@@ -585,3 +585,37 @@ def test_tcsp_layer_golden(ov, cuda_device, golden_dir):
         a = layer(x, shared)
         bb = layer(x, shared.contiguous())
     torch.testing.assert_close(a, bb, rtol=1e-5, atol=1e-6)
+
+
+def test_graph_replay_equals_eager(ov, cuda_device):
+    """HeadPipeline.capture / replay: same detections as the eager launches, and a replay reads
+    the CURRENT contents of the captured input tensors."""
+    from ovdet import synth
+    from ovdet.pipeline import HeadConfig, HeadPipeline
+    shapes = [(20, 20), (10, 10), (5, 5)]
+    a = synth.make_inputs(batch=2, image_size=160, num_classes=90, seed=31, device=cuda_device)
+    b = synth.make_inputs(batch=2, image_size=160, num_classes=90, seed=32, device=cuda_device)
+    pipe = HeadPipeline(2, shapes, 90, HeadConfig(precision="bf16", max_det=64), device=cuda_device)
+    pipe.set_vocabulary(a.text)
+
+    def snapshot(res):
+        torch.cuda.synchronize()
+        return [t.clone() for t in (res.count, res.boxes, res.scores, res.classes, res.anchor, res.keep)]
+
+    want_a = snapshot(pipe.run(a.obj_embeds, a.box_preds))
+    want_b = snapshot(pipe.run(b.obj_embeds, b.box_preds))
+    assert int(want_a[0].sum()) > 0 and not torch.equal(want_a[4], want_b[4])
+    bufs_e = [t.clone() for t in a.obj_embeds]
+    bufs_p = [t.clone() for t in a.box_preds]
+    pipe.capture(bufs_e, bufs_p)
+    def same(got, want):                      # rows past count[b] are not written by a step
+        assert torch.equal(got[0], want[0])
+        for i in range(2):
+            k = int(want[0][i])
+            for g, w in zip(got[1:], want[1:]):
+                assert torch.equal(g[i, :k], w[i, :k])
+
+    same(snapshot(pipe.replay()), want_a)
+    for dst, src in zip(bufs_e + bufs_p, b.obj_embeds + b.box_preds):
+        dst.copy_(src)
+    same(snapshot(pipe.replay()), want_b)
