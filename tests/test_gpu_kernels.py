@@ -441,6 +441,27 @@ def test_similarity_fused_vs_oracle(ov, cuda_device, classes, batched, dim):
     assert a1 is None and torch.equal(m1, rmax)
 
 
+@pytest.mark.parametrize("batch,shapes", [(1, [(20, 20), (10, 12)]), (5, [(12, 12)]), (1, [(4, 4)])])
+def test_similarity_fused_odd_tile_counts(ov, cuda_device, batch, shapes):
+    """CTA pairs take tiles 2i / 2i+1: an odd number of 128-anchor tiles (5, 5 x 2 - 1 ... and a
+    single tile) leaves the second CTA of the last pair with a tile past the end."""
+    from ovdet import ops
+    torch.manual_seed(batch)
+    embs = [torch.randn(batch, 512, h, w) for h, w in shapes]
+    text = torch.randn(77, 512)
+    ref = torch.cat([ref_port.compute_similarity(e, text.unsqueeze(0).expand(batch, -1, -1)).flatten(2).transpose(1, 2)
+                     for e in embs], dim=1)
+    top = ops.l2norm_text(text.to(cuda_device))
+    logits, rmax, rarg = ops.similarity_fused([e.to(cuda_device) for e in embs], top,
+                                              logits_dtype=torch.float32, want_max=True)
+    torch.cuda.synchronize()
+    assert_logits_close(logits, ref, "bf16", 1.0)
+    m, a = logits.max(dim=-1)
+    assert torch.equal(rmax, m) and torch.equal(rarg.long(), a)
+    _, m0, a0 = ops.similarity_fused([e.to(cuda_device) for e in embs], top, logits_dtype=None, want_max=True)
+    assert torch.equal(m0, rmax) and torch.equal(a0, rarg)
+
+
 def test_fused_unsupported_shape_is_an_error(ov, cuda_device):
     from ovdet import ops
     embs = [torch.randn(1, 64, 5, 5, device=cuda_device)]      # hw = 25: row stride not 16-byte aligned
