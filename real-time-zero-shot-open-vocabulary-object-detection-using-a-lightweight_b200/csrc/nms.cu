@@ -13,6 +13,11 @@
 //               order (score desc, anchor index desc) == np.argsort(kind='stable')[::-1]
 //   3. select   optional top-k truncation; bitmask of the selected anchors + prefix popcounts so
 //               that every survivor knows its index in the thresholded array (what `_nms` returns)
+//   (resident path, the common case: no top-k, <= 4096 candidates, <= 65536 anchors: the keys are
+//   placed in anchor order straight into the shared-memory sort block from an in-block prefix
+//   scan of the mask popcounts - which is also every survivor's index in the thresholded array -
+//   sorted there, and never touch the workspace; phases 1-3 then cost three dependent global
+//   reads instead of ten.  At batch 1 the kernel went from 37.6 to ~20 us.)
 //   4. nms      chunks of 512 sorted candidates: boxes gathered / rescaled / clipped into shared
 //               memory, a 512 x 512 suppression bitmask built with one warp ballot per 32 IoUs
 //               (only tiles on or above the diagonal), one warp resolves the chunk 32 candidates
@@ -29,7 +34,8 @@ constexpr int NMS_WARPS = NMS_THREADS / 32;
 constexpr int SORT_CAP = 4096;                 // keys per shared-memory sort block (32 KiB)
 constexpr int CHUNK = 512;                     // candidates per NMS chunk
 constexpr int CHUNK_WORDS = CHUNK / 32;        // 16
-constexpr int NMS_SMEM_BYTES = SORT_CAP * 8 + CHUNK * 16 + 4 * CHUNK * 4 + NMS_THREADS * 4;
+constexpr int FAST_WORDS = 2048;               // resident path: pass-mask words per image (anchors <= 65536)
+constexpr int NMS_SMEM_BYTES = SORT_CAP * 8 + CHUNK * 16 + 4 * CHUNK * 4 + NMS_THREADS * 4 + FAST_WORDS * 4;
 static_assert(CHUNK * CHUNK_WORDS * 4 <= SORT_CAP * 8, "mask must fit in the sort block");
 static_assert(CHUNK == NMS_THREADS, "one thread per chunk candidate");
 
@@ -155,6 +161,7 @@ nms_batched_kernel(const NmsParams p) {
   int* s_anchor = s_cls + CHUNK;
   int* s_kept_pos = s_anchor + CHUNK;           // positions (inside the chunk) kept by this chunk
   int* s_scan = s_kept_pos + CHUNK;             // NMS_THREADS entries
+  int* s_prefix = s_scan + NMS_THREADS;         // FAST_WORDS entries (resident path)
   __shared__ uint32_t s_removed[CHUNK_WORDS];
   __shared__ int s_count, s_kept_total, s_kept_chunk, s_carry;
 
@@ -177,11 +184,101 @@ nms_batched_kernel(const NmsParams p) {
   if (tid == 0) { s_count = 0; s_kept_total = 0; s_carry = 0; }
   __syncthreads();
 
-  // ---- 1. gather ---------------------------------------------------------------------------
   const uint32_t tail_bits = (A & 31) ? ((1u << (A & 31)) - 1u) : 0xffffffffu;
-  for (int w = tid; w < W; w += NMS_THREADS) {
+  auto mask_word = [&](int w) -> uint32_t {
     uint32_t bits = pm ? pm[w] : 0xffffffffu;
     if (w == W - 1) bits &= tail_bits;
+    return bits;
+  };
+  int N, M;
+  bool resident = false;
+  const unsigned long long* sorted_keys = keys;     // where phase 4 reads the sorted keys from
+
+  if (W <= FAST_WORDS) {
+    // ---- 0. exclusive prefix of the mask popcounts (contiguous words per thread) -------------
+    const int per = (W + NMS_THREADS - 1) / NMS_THREADS;           // <= 4
+    const int w_lo = tid * per;
+    int local = 0;
+    for (int i = 0; i < per; ++i)
+      if (w_lo + i < W) local += __popc(mask_word(w_lo + i));
+    int incl = local;                                              // inclusive scan over the block
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int v = __shfl_up_sync(0xffffffffu, incl, o);
+      if (lane >= o) incl += v;
+    }
+    if (lane == 31) s_scan[warp] = incl;
+    __syncthreads();
+    if (warp == 0) {
+      int v = (lane < NMS_WARPS) ? s_scan[lane] : 0;
+#pragma unroll
+      for (int o = 1; o < NMS_WARPS; o <<= 1) {
+        const int u = __shfl_up_sync(0xffffffffu, v, o);
+        if (lane >= o) v += u;
+      }
+      if (lane < NMS_WARPS) s_scan[lane] = v;                      // inclusive warp totals
+    }
+    __syncthreads();
+    N = s_scan[NMS_WARPS - 1];
+    int run = incl - local + (warp ? s_scan[warp - 1] : 0);
+    for (int i = 0; i < per; ++i)
+      if (w_lo + i < W) { s_prefix[w_lo + i] = run; run += __popc(mask_word(w_lo + i)); }
+    resident = N <= SORT_CAP && (p.topk == 0 || p.topk >= N);
+    __syncthreads();
+  } else {
+    N = -1;
+  }
+
+  if (resident) {
+    if (p.out_candidates && tid == 0) p.out_candidates[b] = N;
+    if (N == 0) {
+      if (tid == 0) p.out_count[b] = 0;
+      return;
+    }
+    // ---- 1r. keys in anchor order, straight into the sort block ------------------------------
+    for (int w = tid; w < W; w += NMS_THREADS) {
+      uint32_t bits = mask_word(w);
+      int slot = s_prefix[w];
+      while (bits) {
+        const int l = __ffs(bits) - 1;
+        bits &= bits - 1;
+        const int a = (w << 5) + l;
+        s_big[slot++] = ((unsigned long long)float_to_ordered(scores[a]) << 32) | (unsigned)a;
+      }
+    }
+    __syncthreads();
+    // ---- 2r. sort in shared memory -------------------------------------------------------------
+    if (N <= CHUNK) {
+      // rank sort: thread i counts the keys larger than its own (keys are pairwise distinct, so
+      // the ranks are a permutation): one pass of broadcast reads and one barrier instead of
+      // the 36 barrier-separated steps a 256-key bitonic network takes.
+      unsigned long long mine = 0ull;
+      int rank = 0;
+      if (tid < N) {
+        mine = s_big[tid];
+        for (int j = 0; j < N; ++j) rank += s_big[j] > mine;
+      }
+      __syncthreads();
+      if (tid < N) s_big[rank] = mine;
+      __syncthreads();
+    } else {
+      int P = 32;
+      while (P < N) P <<= 1;
+      for (int i = N + tid; i < P; i += NMS_THREADS) s_big[i] = 0ull;
+      __syncthreads();
+      for (int k = 2; k <= P; k <<= 1) smem_bitonic_steps(s_big, P, 0, k, k >> 1);
+    }
+    M = N;
+    if (M > CHUNK) {            // several NMS chunks: the mask will overwrite the sort block
+      for (int i = tid; i < M; i += NMS_THREADS) keys[i] = s_big[i];
+      __syncthreads();
+    } else {
+      sorted_keys = s_big;      // single chunk: read into registers before the mask is built
+    }
+  } else {
+  // ---- 1. gather ---------------------------------------------------------------------------
+  for (int w = tid; w < W; w += NMS_THREADS) {
+    uint32_t bits = mask_word(w);
     const int c = __popc(bits);
     if (c) {
       int slot = atomicAdd(&s_count, c);
@@ -194,7 +291,7 @@ nms_batched_kernel(const NmsParams p) {
     }
   }
   __syncthreads();
-  const int N = s_count;
+  N = s_count;
   if (p.out_candidates && tid == 0) p.out_candidates[b] = N;
   if (N == 0) {
     if (tid == 0) p.out_count[b] = 0;
@@ -209,7 +306,7 @@ nms_batched_kernel(const NmsParams p) {
   sort_keys_desc(keys, P, s_big);
 
   // ---- 3. select (top-k) + rank of every selected anchor in the thresholded array ------------
-  const int M = (p.topk > 0 && p.topk < N) ? p.topk : N;
+  M = (p.topk > 0 && p.topk < N) ? p.topk : N;
   for (int w = tid; w < W; w += NMS_THREADS) sel[w] = 0u;
   __syncthreads();
   for (int i = tid; i < M; i += NMS_THREADS) {
@@ -234,6 +331,7 @@ nms_batched_kernel(const NmsParams p) {
     if (tid == NMS_THREADS - 1) s_carry = carry + s_scan[tid];
     __syncthreads();
   }
+  }
 
   // ---- 4. greedy NMS over the sorted candidates ----------------------------------------------
   const float scale = p.scale ? p.scale[b] : 1.0f;
@@ -254,7 +352,7 @@ nms_batched_kernel(const NmsParams p) {
     float my_area = 0.f;
     int my_cls = -1;
     if (tid < n) {
-      const unsigned a = (unsigned)(keys[c0 + tid] & 0xffffffffull);
+      const unsigned a = (unsigned)(sorted_keys[c0 + tid] & 0xffffffffull);
       float4 v = boxes[a];
       if (do_scale) {
         v.x = __fdiv_rn(v.x, scale); v.y = __fdiv_rn(v.y, scale);
@@ -309,27 +407,27 @@ nms_batched_kernel(const NmsParams p) {
       mask[((rb << 5) + lane) * CHUNK_WORDS + cb] = my_word;
     }
     __syncthreads();
-    // 4d. resolve: warp 0, 32 candidates per step
+    // 4d. resolve: warp 0, one 32-candidate block per step.  The 32 diagonal words are loaded up
+    // front (broadcast reads, independent of the greedy chain), so the chain itself is 32
+    // register-only steps; the rows of the kept candidates are then OR-ed into the later blocks
+    // with predicated, independent loads (lane = mask word).
     if (warp == 0) {
       uint32_t removed = (lane < CHUNK_WORDS) ? s_removed[lane] : 0xffffffffu;
       int kept_chunk = 0;
       for (int wb = 0; wb < nblk; ++wb) {
         const uint32_t cur = __shfl_sync(0xffffffffu, removed, wb);
         uint32_t alive = ~cur;
-        const uint32_t diag = mask[((wb << 5) + lane) * CHUNK_WORDS + wb];
+        const uint32_t* rows = mask + (wb << 5) * CHUNK_WORDS;
+        uint32_t d[32];
 #pragma unroll
-        for (int r = 0; r < 32; ++r) {
-          const uint32_t d = __shfl_sync(0xffffffffu, diag, r);
-          if ((alive >> r) & 1u) alive &= ~d;
-        }
-        // rows of the kept candidates suppress later blocks
+        for (int r = 0; r < 32; ++r) d[r] = rows[r * CHUNK_WORDS + wb];
+#pragma unroll
+        for (int r = 0; r < 32; ++r)
+          if ((alive >> r) & 1u) alive &= ~d[r];
         if (lane < CHUNK_WORDS && lane > wb) {
-          uint32_t bits = alive;
-          while (bits) {
-            const int r = __ffs(bits) - 1;
-            bits &= bits - 1;
-            removed |= mask[((wb << 5) + r) * CHUNK_WORDS + lane];
-          }
+#pragma unroll
+          for (int r = 0; r < 32; ++r)
+            if ((alive >> r) & 1u) removed |= rows[r * CHUNK_WORDS + lane];
         }
         if ((alive >> lane) & 1u)
           s_kept_pos[kept_chunk + __popc(alive & ((1u << lane) - 1u))] = (wb << 5) + lane;
@@ -353,7 +451,9 @@ nms_batched_kernel(const NmsParams p) {
         if (p.out_scores) p.out_scores[o] = scores[a];
         if (p.out_classes) p.out_classes[o] = classes ? s_cls[pos] : 0;
         if (p.out_anchor) p.out_anchor[o] = a;
-        if (p.out_keep) p.out_keep[o] = prefix[a >> 5] + __popc(sel[a >> 5] & ((1u << (a & 31)) - 1u));
+        if (p.out_keep)
+          p.out_keep[o] = resident ? s_prefix[a >> 5] + __popc(mask_word(a >> 5) & ((1u << (a & 31)) - 1u))
+                                   : prefix[a >> 5] + __popc(sel[a >> 5] & ((1u << (a & 31)) - 1u));
       }
     }
     __syncthreads();
