@@ -82,10 +82,37 @@ __device__ __forceinline__ void dfl_expectation(const float* __restrict__ p, lon
   }
 }
 
+// Latency variant for small launches (batch 1): one anchor per thread, all 4 x BINS loads issued
+// before any arithmetic, so the kernel pays one memory round trip instead of four.
+template <int BINS>
+__device__ __forceinline__ void dfl_expectation4_hoisted(const float* __restrict__ p, long long cstride,
+                                                         float (&e)[4]) {
+  float v[4][BINS];
+#pragma unroll
+  for (int c = 0; c < 4; ++c)
+#pragma unroll
+    for (int k = 0; k < BINS; ++k) v[c][k] = ld_stream_f32(p + (long long)(c * BINS + k) * cstride);
+#pragma unroll
+  for (int c = 0; c < 4; ++c) {
+    float m = v[c][0];
+#pragma unroll
+    for (int k = 1; k < BINS; ++k) m = fmaxf(m, v[c][k]);
+    const float nm = -m * kLog2e;
+    float s = 0.f, n = 0.f;
+#pragma unroll
+    for (int k = 0; k < BINS; ++k) {
+      const float t = exp_rel(v[c][k], nm);
+      s += t;
+      n = fmaf((float)k, t, n);
+    }
+    e[c] = __fdiv_rn(n, s);
+  }
+}
+
 // V = 4: a thread decodes 4 consecutive cells of one level with 16-byte loads (every level's
 // H*W and batch stride must be a multiple of 4 and the pointers 16-byte aligned); V = 1 is the
 // general path.  blockIdx.y = image.
-template <int BINS, int V>
+template <int BINS, int V, bool HOIST = false>
 __global__ void __launch_bounds__(256)
 decode_filter_kernel(const DecodeParams p, int anchors, const float* __restrict__ scores,
                      float conf, int activation, float* __restrict__ boxes,
@@ -104,10 +131,16 @@ decode_filter_kernel(const DecodeParams p, int anchors, const float* __restrict_
     const float* base = p.pred[l] + b * p.bstride[l] + cell;
     const int bins = p.bins;
     float e0[V], e1[V], e2[V], e3[V];
-    dfl_expectation<BINS, V>(base, cstride, bins, e0);
-    dfl_expectation<BINS, V>(base + 1ll * bins * cstride, cstride, bins, e1);
-    dfl_expectation<BINS, V>(base + 2ll * bins * cstride, cstride, bins, e2);
-    dfl_expectation<BINS, V>(base + 3ll * bins * cstride, cstride, bins, e3);
+    if constexpr (HOIST && V == 1 && BINS > 0) {
+      float e[4];
+      dfl_expectation4_hoisted<BINS>(base, cstride, e);
+      e0[0] = e[0]; e1[0] = e[1]; e2[0] = e[2]; e3[0] = e[3];
+    } else {
+      dfl_expectation<BINS, V>(base, cstride, bins, e0);
+      dfl_expectation<BINS, V>(base + 1ll * bins * cstride, cstride, bins, e1);
+      dfl_expectation<BINS, V>(base + 2ll * bins * cstride, cstride, bins, e2);
+      dfl_expectation<BINS, V>(base + 3ll * bins * cstride, cstride, bins, e3);
+    }
     const float st = (float)p.stride[l];
     const long long ga = (long long)b * anchors + a;
     float sc[V];
@@ -204,7 +237,12 @@ extern "C" int ovdet_decode_filter(const float* const* box_preds, const int32_t*
   for (int l = 0; l < num_levels && vec4; ++l)
     vec4 = ((long long)heights[l] * widths[l]) % 4 == 0 && batch_strides[l] % 4 == 0 &&
            !((uintptr_t)box_preds[l] & 15);
-  if (vec4) {
+  if (bins == 17 && (long long)anchors * batch <= 65536) {
+    // small launch: latency matters, not bandwidth
+    dim3 grid((unsigned)ceil_div(anchors, 256), (unsigned)batch);
+    decode_filter_kernel<17, 1, true><<<grid, 256, 0, s>>>(p, anchors, scores, conf, activation, boxes,
+                                                           scores_act, pass_mask, words);
+  } else if (vec4) {
     dim3 grid((unsigned)ceil_div(anchors, 1024), (unsigned)batch);
     decode_filter_kernel<17, 4><<<grid, 256, 0, s>>>(p, anchors, scores, conf, activation, boxes,
                                                      scores_act, pass_mask, words);
