@@ -201,7 +201,7 @@ def run_ours(args):
     shapes = [(IMAGE_SIZE // s, IMAGE_SIZE // s) for s in STRIDES]
     anchors = sum(h * w for h, w in shapes)
 
-    cfg = HeadConfig(precision="bf16", max_det=MAX_DET, fused=not args.no_fused)
+    cfg = HeadConfig(precision=args.precision, max_det=MAX_DET, fused=not args.no_fused)
     inp = synth.make_inputs(batch=batch, image_size=IMAGE_SIZE, num_classes=NUM_CLASSES,
                             embed_dim=EMBED_DIM, device=dev, seed=1234 + rank)
     pipe = HeadPipeline(batch, shapes, NUM_CLASSES, cfg, device=dev)
@@ -335,21 +335,42 @@ def run_ours(args):
 
     if rank == 0:
         peaks = measured_peaks()
-        flops = 2.0 * batch * anchors * NUM_CLASSES * EMBED_DIM
+        flops = 2.0 * batch * anchors * NUM_CLASSES * EMBED_DIM * (3 if args.precision == "fp32" else 1)
         achieved = flops / (stages["similarity"] * 1e-3) / 1e12
         fused = pipe.last_path == "fused"
         launches = (3 if fused else len(shapes) + 3)
         kernel = ("sim_fused_kernel (K1+K2: fp32 NCHW in, L2 norm, tcgen05 GEMM, class max/argmax)" if fused
                   else "sim_gemm_kernel (K2)")
+        # dominant kernel's algorithmic bytes: the fused kernel reads the fp32 activations once; the
+        # two-kernel path's GEMM reads the bf16 operand (hi|lo halves for the fp32 recipe)
+        kop_bytes = EMBED_DIM * 2 * (2 if args.precision == "fp32" else 1)
+        alg_bytes = (batch * anchors * (EMBED_DIM * 4 + 12) if fused else batch * anchors * (kop_bytes + 12)) \
+            + NUM_CLASSES * kop_bytes
+        t_tensor = flops / (peaks["tflops"] * 1e12)
+        t_hbm = alg_bytes / (peaks["hbm_gbs"] * 1e9)
+        if t_tensor >= t_hbm:
+            roofline = {"bound": "tensor", "kernel": kernel, "achieved": achieved, "peak": peaks["tflops"],
+                        "unit": "TFLOP/s", "frac": achieved / peaks["tflops"],
+                        "peak_source": peaks["source"] + " (bf16_tflops_sustained)"}
+        else:       # few classes: the contraction is HBM-bound (C = 80 is 35 FLOP/B)
+            gbs = alg_bytes / (stages["similarity"] * 1e-3) / 1e9
+            roofline = {"bound": "hbm", "kernel": kernel, "achieved": gbs, "peak": peaks["hbm_gbs"],
+                        "unit": "GB/s", "frac": gbs / peaks["hbm_gbs"], "peak_source": peaks["source"] + " (hbm_gbs)"}
+        roofline.update({"traffic": ncu_traffic("sim_fused" if fused else "sim_gemm", batch),
+                         "traffic_source": "profiles/r1_ncu_full_pipeline_b256_v4.json (ncu --set full, bytes per launch)",
+                         "algorithmic_bytes": alg_bytes, "algorithmic_flops": flops,
+                         "ms_per_launch": stages["similarity"]})
         k1_bytes = batch * anchors * (EMBED_DIM * 4 + EMBED_DIM * 2 + 4)
         k3_bytes = batch * anchors * (68 * 4 + 4 + 16) + batch * ((anchors + 31) // 32) * 4
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": n_gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": elapsed_ms / args.steps, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+            "scaling": "weak", "vs_baseline": None,
+            "dtype": "bf16" if args.precision == "bf16" else "bf16x3 (fp32-accurate hi/lo split)", "data": "synthetic",
             "config": {"workload": workload_name(batch), "global_batch": batch * n_gpus,
                        "anchors": anchors, "classes": NUM_CLASSES, "embed_dim": EMBED_DIM,
-                       "precision": "bf16 operands, fp32 accumulate, fused class max/argmax",
+                       "precision": ("bf16 operands, fp32 accumulate, fused class max/argmax" if args.precision == "bf16"
+                                     else "three bf16 passes over hi/lo operand halves (|dlogit| ~ 1e-5), fp32 accumulate"),
                        "path": pipe.last_path,
                        "conf": cfg.conf_threshold, "iou": cfg.iou_threshold, "max_det": MAX_DET,
                        "parallelism": f"batch-sharded x{n_gpus}, vocabulary replicated, no collective",
@@ -360,13 +381,7 @@ def run_ours(args):
                     "d2h_bytes_per_step": d2h_bytes, "steps": e2e_steps, "chunk_images": chunk,
                     "api": "ovdet.detector.Detector.predict_host (pinned host buffers in, detections out)"},
             "gpu_launches": launches * args.steps,
-            "roofline": {"bound": "tensor", "kernel": kernel, "achieved": achieved,
-                         "peak": peaks["tflops"], "unit": "TFLOP/s", "frac": achieved / peaks["tflops"],
-                         "traffic": ncu_traffic("sim_fused" if fused else "sim_gemm", batch),
-                         "traffic_source": "profiles/r1_ncu_full_pipeline_b256_v4.json (ncu --set full, bytes per launch)",
-                         "algorithmic_bytes": batch * anchors * (EMBED_DIM * 4 + 12) + NUM_CLASSES * EMBED_DIM * 2,
-                         "peak_source": peaks["source"] + " (bf16_tflops_sustained)",
-                         "ms_per_launch": stages["similarity"]},
+            "roofline": roofline,
             "stages_ms": stages,
             "stage_rooflines": {
                 "l2norm_hbm_frac": (None if fused else
@@ -399,6 +414,8 @@ def main():
     ap.add_argument("--no-fused", action="store_true", help="two-kernel K1 -> K2 path instead of the fused kernel")
     ap.add_argument("--profile", action="store_true",
                     help="device-resident loop only (for ncu): no e2e, latency or CPU legs")
+    ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"],
+                    help="bf16 = the metric's configuration; fp32 = three-pass hi/lo recipe (BASELINE configs[1])")
     ap.add_argument("--image-size", type=int, default=IMAGE_SIZE,
                     help="default 640 (the metric's configuration); 1280 = BASELINE configs[3]")
     ap.add_argument("--classes", type=int, default=NUM_CLASSES,

@@ -28,6 +28,10 @@ inline int cuda_fail(cudaError_t e) {
 // Returns OVDET_OK when the current device is compute capability 10.x; cached per device.
 int check_device();
 int sm_count();
+// True the first time it is called for (current device, slot): kernel attributes such as the
+// dynamic shared-memory limit are per device, so they are set once per device, not once per
+// process.  Slots: 0 sim_gemm, 1 sim_fused, 2 nms.  Thread-safe.
+bool first_use_on_device(int slot);
 
 // sim_fused_sm100.cu: the fused normalise + GEMM + row max kernel behind ovdet_similarity_fused
 // and ovdet_max_sigmoid_attention.

@@ -512,10 +512,8 @@ extern "C" int ovdet_nms_batched(const float* boxes, const float* scores, const 
   p.ws = static_cast<unsigned char*>(workspace);
   p.pow2_cap = next_pow2_cap(anchors);
   p.ws_per_image = WsLayout(p.anchors, p.words, p.pow2_cap).total;
-  static bool attr_set = false;
-  if (!attr_set) {
+  if (first_use_on_device(2)) {
     OVDET_CUDA_TRY(cudaFuncSetAttribute(nms_batched_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, NMS_SMEM_BYTES));
-    attr_set = true;
   }
   nms_batched_kernel<<<(unsigned)batch, NMS_THREADS, NMS_SMEM_BYTES, as_stream(stream)>>>(p);
   OVDET_LAUNCH_CHECK();

@@ -1,5 +1,6 @@
 // Library runtime: version, error strings, device checks.
 #include "common.cuh"
+#include <atomic>
 
 namespace ovdet {
 
@@ -30,6 +31,14 @@ int check_device() {
   DeviceInfo* d = current_info();
   if (!d) { return OVDET_ERR_CUDA; }
   return d->status;
+}
+
+bool first_use_on_device(int slot) {
+  static std::atomic<unsigned> seen[64];
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return true;
+  const unsigned bit = 1u << slot;
+  return (seen[dev].fetch_or(bit) & bit) == 0;
 }
 
 int sm_count() {

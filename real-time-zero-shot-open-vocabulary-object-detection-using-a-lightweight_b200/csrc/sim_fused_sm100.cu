@@ -690,15 +690,16 @@ int fused_launch(const float* const* obj_embeds, const int64_t* hw, const int64_
   p.row_max = row_max;
   p.row_arg = row_arg;
   p.inv_norm = inv_norm;
-  { const char* e = getenv("OVDET_DBG"); p.dbg = e ? atoi(e) : 0; }
+  // experiment switches: 1 L2 prefetch warp on, 2 no raw-accumulator
+  // epilogue, 16 / 32 back-off of the non-critical waits off / 256 ns
+  static const int dbg_env = []() { const char* e = getenv("OVDET_DBG"); return e ? atoi(e) : 0; }();
+  p.dbg = dbg_env;
 
-  static bool attr_set = false;
-  if (!attr_set) {
+  if (first_use_on_device(1)) {
     OVDET_CUDA_TRY(cudaFuncSetAttribute(sim_fused_kernel<8, false, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, FSmem<1>::bytes));
     OVDET_CUDA_TRY(cudaFuncSetAttribute(sim_fused_kernel<0, false, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, FSmem<1>::bytes));
     OVDET_CUDA_TRY(cudaFuncSetAttribute(sim_fused_kernel<0, true, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, FSmem<1>::bytes));
     OVDET_CUDA_TRY(cudaFuncSetAttribute(sim_fused_kernel<8, false, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, FSmem<2>::bytes));
-    attr_set = true;
   }
   if (cg == 2) {
     // one CTA per SM, launched as clusters of two (the pair shares a TPC)

@@ -368,10 +368,8 @@ extern "C" int ovdet_similarity(const void* regions_op, const void* text_op, con
   if (int rc = make_operand_map(&map_a, regions_op, g_batch, g_rows, kop, BLOCK_M)) return rc;
   if (int rc = make_operand_map(&map_b, text_op, text_batched ? batch : 1, classes, kop, p.box_n)) return rc;
 
-  static bool attr_set = false;
-  if (!attr_set) {
+  if (first_use_on_device(0)) {
     OVDET_CUDA_TRY(cudaFuncSetAttribute(sim_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
-    attr_set = true;
   }
   const int64_t total_tiles = (int64_t)p.batch * p.m_tiles;
   const int grid = (int)(total_tiles < sm_count() ? total_tiles : sm_count());

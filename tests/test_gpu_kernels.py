@@ -642,3 +642,47 @@ def test_graph_replay_equals_eager(ov, cuda_device):
     for dst, src in zip(bufs_e + bufs_p, b.obj_embeds + b.box_preds):
         dst.copy_(src)
     same(snapshot(pipe.replay()), want_b)
+
+
+# ------------------------------------------------------------------------------------------
+# K4 properties (hypothesis): random box sets, duplicates, degenerate boxes, ties in IoU
+# ------------------------------------------------------------------------------------------
+def test_nms_properties_hypothesis(ov, cuda_device):
+    from hypothesis import given, settings, strategies as st, HealthCheck
+    from ovdet import ops
+
+    coord = st.integers(0, 40)
+
+    @st.composite
+    def box_sets(draw):
+        n = draw(st.integers(1, 80))
+        boxes = []
+        for _ in range(n):
+            x1, y1 = draw(coord), draw(coord)
+            w, h = draw(st.integers(0, 25)), draw(st.integers(0, 25))     # zero-area boxes included
+            boxes.append([x1, y1, x1 + w, y1 + h])
+        scores = draw(st.lists(st.integers(0, 10_000), min_size=n, max_size=n, unique=True))
+        thr = draw(st.sampled_from([0.0, 0.3, 0.45, 0.5, 1.0]))
+        return np.asarray(boxes, np.float32), np.asarray(scores, np.float32) / 10_000, thr
+
+    @settings(max_examples=60, deadline=None, suppress_health_check=list(HealthCheck))
+    @given(box_sets())
+    def check(case):
+        boxes, scores, thr = case
+        want = ref_port.nms(boxes, scores, thr, stable_ties=True)
+        b = torch.from_numpy(boxes).to(cuda_device).reshape(1, -1, 4)
+        s = torch.from_numpy(scores).to(cuda_device).reshape(1, -1)
+        res = ops.nms_batched(b, s, iou_thr=thr)
+        k = int(res.count[0])
+        got = res.anchor[0, :k].tolist()
+        assert got == [int(i) for i in want]                                 # bit-exact keep list, in order
+        kept = boxes[got]
+        for i in range(len(got)):                                            # no kept pair above the threshold
+            if i:
+                assert (ref_port.compute_iou(kept[i], kept[:i]) <= thr).all()
+        # idempotence: NMS of the kept set keeps everything
+        again = ops.nms_batched(torch.from_numpy(kept).to(cuda_device).reshape(1, -1, 4),
+                                torch.from_numpy(scores[got]).to(cuda_device).reshape(1, -1), iou_thr=thr)
+        assert int(again.count[0]) == len(got)
+
+    check()
