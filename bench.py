@@ -40,6 +40,9 @@ METRIC = "images/sec (640x640, 1203 prompts), head + post-process"
 UNIT = "images/s"
 
 
+PROJECTED_NOTE = " + the head's 1x1 projection (step starts at the hidden features, SURVEY 8f-2)"
+
+
 def workload_name(batch):
     which = {(640, 80): "configs[1] shapes", (640, 1203): "configs[2]", (1280, 1203): "configs[3] shapes",
              (640, 4800): "configs[4] shapes"}.get((IMAGE_SIZE, NUM_CLASSES), "custom")
@@ -126,17 +129,30 @@ def ncu_traffic(kernel_substr: str, batch: int):
 # ----------------------------------------------------------------------------------------------
 # reference CPU arm / cpu_baseline leg (the only places that execute oracle/)
 # ----------------------------------------------------------------------------------------------
-def cpu_reference_sample(sample_images: int, seed: int = 1234):
+def cpu_reference_sample(sample_images: int, seed: int = 1234, projected: bool = False):
     """Build a bounded sample of the workload on the host and return a callable running the
-    reference algorithm (oracle port of yolo_clip.py:173-214 + detector.py:163-223) over it."""
+    reference algorithm (oracle port of yolo_clip.py:173-214 + detector.py:163-223) over it;
+    ``projected``: the step starts one layer earlier, at the input of the head's 1x1 projection
+    (text_contrastive.py:67,112), which the reference computes as a convolution."""
     import torch
     from oracle import ref_port
     from ovdet import synth
+    sizes = [(IMAGE_SIZE, IMAGE_SIZE)] * sample_images
+    scales = [1.0] * sample_images
+    if projected:
+        pin = synth.make_projected_inputs(batch=sample_images, image_size=IMAGE_SIZE, num_classes=NUM_CLASSES,
+                                          embed_dim=EMBED_DIM, device="cpu", seed=seed)
+        ptext = pin.text_batched()
+
+        def pstep():
+            with torch.no_grad():
+                embeds = [torch.nn.functional.conv2d(h, w, b) for h, w, b in zip(pin.hidden, pin.weights, pin.biases)]
+                tail = ref_port.head_tail(embeds, ptext, pin.box_preds, STRIDES)
+                return ref_port.postprocess_batch(tail, sizes, scales)
+        return pstep
     inp = synth.make_inputs(batch=sample_images, image_size=IMAGE_SIZE, num_classes=NUM_CLASSES,
                             embed_dim=EMBED_DIM, device="cpu", seed=seed)
     text = inp.text_batched()
-    sizes = [(IMAGE_SIZE, IMAGE_SIZE)] * sample_images
-    scales = [1.0] * sample_images
 
     def step():
         with torch.no_grad():
@@ -153,7 +169,7 @@ def run_reference(args):
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
     sample = 4
-    step = cpu_reference_sample(sample)
+    step = cpu_reference_sample(sample, projected=args.projected)
     for _ in range(max(1, min(args.warmup, 2))):
         step()
     t0 = time.perf_counter()
@@ -168,7 +184,8 @@ def run_reference(args):
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
         "data": "synthetic",
-        "config": {"workload": workload_name(BATCH_PER_GPU), "sample_images_per_step": sample},
+        "config": {"workload": workload_name(BATCH_PER_GPU) + (PROJECTED_NOTE if args.projected else ""),
+                   "sample_images_per_step": sample},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
                          "sample": sample_desc},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -202,9 +219,19 @@ def run_ours(args):
     anchors = sum(h * w for h, w in shapes)
 
     cfg = HeadConfig(precision=args.precision, max_det=MAX_DET, fused=not args.no_fused)
-    inp = synth.make_inputs(batch=batch, image_size=IMAGE_SIZE, num_classes=NUM_CLASSES,
-                            embed_dim=EMBED_DIM, device=dev, seed=1234 + rank)
-    pipe = HeadPipeline(batch, shapes, NUM_CLASSES, cfg, device=dev)
+    projections = None
+    if args.projected:
+        pin = synth.make_projected_inputs(batch=batch, image_size=IMAGE_SIZE, num_classes=NUM_CLASSES,
+                                          embed_dim=EMBED_DIM, device=dev, seed=1234 + rank)
+        projections = pin.projections()
+
+        class _In:                      # same field names as HeadInputs; obj_embeds = hidden features
+            obj_embeds, box_preds, text = pin.hidden, pin.box_preds, pin.text
+        inp = _In
+    else:
+        inp = synth.make_inputs(batch=batch, image_size=IMAGE_SIZE, num_classes=NUM_CLASSES,
+                                embed_dim=EMBED_DIM, device=dev, seed=1234 + rank)
+    pipe = HeadPipeline(batch, shapes, NUM_CLASSES, cfg, device=dev, projections=projections)
     # the vocabulary is replicated: rank 0's copy goes to every GPU once, outside the timed region
     vocab = shard.broadcast_vocabulary(inp.text if rank == 0 else None, NUM_CLASSES, EMBED_DIM, dev)
     pipe.set_vocabulary(vocab)
@@ -265,7 +292,7 @@ def run_ours(args):
 
     def e2e_step():
         nonlocal out_host
-        out_host = det.predict_host(host_obj, host_box, chunk=chunk)
+        out_host = det.predict_host(host_obj, host_box, chunk=chunk, projections=projections)
 
     for _ in range(max(1, min(args.warmup, 3))):
         e2e_step()
@@ -286,9 +313,16 @@ def run_ours(args):
     # ---- batch-1 latency (the second half of BASELINE.json's metric) -------------------------
     p50 = p50_graph = None
     if rank == 0:
-        one = synth.make_inputs(batch=1, image_size=IMAGE_SIZE, num_classes=NUM_CLASSES,
-                                embed_dim=EMBED_DIM, device=dev, seed=77)
-        pipe1 = HeadPipeline(1, shapes, NUM_CLASSES, cfg, device=dev)
+        if args.projected:
+            pone = synth.make_projected_inputs(batch=1, image_size=IMAGE_SIZE, num_classes=NUM_CLASSES,
+                                               embed_dim=EMBED_DIM, device=dev, seed=1234 + rank)
+
+            class one:
+                obj_embeds, box_preds = pone.hidden, pone.box_preds
+        else:
+            one = synth.make_inputs(batch=1, image_size=IMAGE_SIZE, num_classes=NUM_CLASSES,
+                                    embed_dim=EMBED_DIM, device=dev, seed=77)
+        pipe1 = HeadPipeline(1, shapes, NUM_CLASSES, cfg, device=dev, projections=projections)
         pipe1.set_vocabulary(inp.text)
         lat = []
         for i in range(60):
@@ -321,7 +355,7 @@ def run_ours(args):
         cores = os.cpu_count() or 1
         _t.set_num_threads(cores)
         sample = 4
-        step = cpu_reference_sample(sample)
+        step = cpu_reference_sample(sample, projected=args.projected)
         step()
         t0 = time.perf_counter()
         reps = 0
@@ -337,15 +371,24 @@ def run_ours(args):
         peaks = measured_peaks()
         flops = 2.0 * batch * anchors * NUM_CLASSES * EMBED_DIM * (3 if args.precision == "fp32" else 1)
         achieved = flops / (stages["similarity"] * 1e-3) / 1e12
+        proj = pipe.last_path == "projected"
         fused = pipe.last_path == "fused"
-        launches = (3 if fused else len(shapes) + 3)
-        kernel = ("sim_fused_kernel (K1+K2: fp32 NCHW in, L2 norm, tcgen05 GEMM, class max/argmax)" if fused
+        launches = (3 if (fused or proj) else len(shapes) + 3)
+        kernel = ("sim_fused_kernel, projected mode (1x1 projection folded: hidden fp32 NCHW in, quadratic-form "
+                  "norm, tcgen05 GEMM K = 272, class max/argmax)" if proj else
+                  "sim_fused_kernel (K1+K2: fp32 NCHW in, L2 norm, tcgen05 GEMM, class max/argmax)" if fused
                   else "sim_gemm_kernel (K2)")
+        if proj:
+            # MMA work the kernel issues per launch: [A x 272] x [272 x (classes padded to 128 + 272 rows of G')]
+            flops = 2.0 * batch * anchors * ((NUM_CLASSES + 127) // 128 * 128 + 272) * 272
+            achieved = flops / (stages["similarity"] * 1e-3) / 1e12
         # dominant kernel's algorithmic bytes: the fused kernel reads the fp32 activations once; the
         # two-kernel path's GEMM reads the bf16 operand (hi|lo halves for the fp32 recipe)
         kop_bytes = EMBED_DIM * 2 * (2 if args.precision == "fp32" else 1)
         alg_bytes = (batch * anchors * (EMBED_DIM * 4 + 12) if fused else batch * anchors * (kop_bytes + 12)) \
             + NUM_CLASSES * kop_bytes
+        if proj:
+            alg_bytes = batch * anchors * (256 * 4 + 12) + 3 * (NUM_CLASSES + 272) * 272 * 2
         t_tensor = flops / (peaks["tflops"] * 1e12)
         t_hbm = alg_bytes / (peaks["hbm_gbs"] * 1e9)
         if t_tensor >= t_hbm:
@@ -356,7 +399,7 @@ def run_ours(args):
             gbs = alg_bytes / (stages["similarity"] * 1e-3) / 1e9
             roofline = {"bound": "hbm", "kernel": kernel, "achieved": gbs, "peak": peaks["hbm_gbs"],
                         "unit": "GB/s", "frac": gbs / peaks["hbm_gbs"], "peak_source": peaks["source"] + " (hbm_gbs)"}
-        roofline.update({"traffic": ncu_traffic("sim_fused" if fused else "sim_gemm", batch),
+        roofline.update({"traffic": None if proj else ncu_traffic("sim_fused" if fused else "sim_gemm", batch),
                          "traffic_source": "profiles/r1_ncu_full_pipeline_b256_v4.json (ncu --set full, bytes per launch)",
                          "algorithmic_bytes": alg_bytes, "algorithmic_flops": flops,
                          "ms_per_launch": stages["similarity"]})
@@ -367,7 +410,8 @@ def run_ours(args):
             "warmup": args.warmup, "ms_per_step": elapsed_ms / args.steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None,
             "dtype": "bf16" if args.precision == "bf16" else "bf16x3 (fp32-accurate hi/lo split)", "data": "synthetic",
-            "config": {"workload": workload_name(batch), "global_batch": batch * n_gpus,
+            "config": {"workload": workload_name(batch) + (PROJECTED_NOTE if args.projected else ""),
+                       "global_batch": batch * n_gpus,
                        "anchors": anchors, "classes": NUM_CLASSES, "embed_dim": EMBED_DIM,
                        "precision": ("bf16 operands, fp32 accumulate, fused class max/argmax" if args.precision == "bf16"
                                      else "three bf16 passes over hi/lo operand halves (|dlogit| ~ 1e-5), fp32 accumulate"),
@@ -384,7 +428,7 @@ def run_ours(args):
             "roofline": roofline,
             "stages_ms": stages,
             "stage_rooflines": {
-                "l2norm_hbm_frac": (None if fused else
+                "l2norm_hbm_frac": (None if (fused or proj) else
                                     k1_bytes / (stages["l2norm"] * 1e-3) / 1e9 / peaks["hbm_gbs"]),
                 "similarity_hbm_frac_fp32_input": batch * anchors * EMBED_DIM * 4 / (stages["similarity"] * 1e-3)
                                                   / 1e9 / peaks["hbm_gbs"],
@@ -414,6 +458,9 @@ def main():
     ap.add_argument("--no-fused", action="store_true", help="two-kernel K1 -> K2 path instead of the fused kernel")
     ap.add_argument("--profile", action="store_true",
                     help="device-resident loop only (for ncu): no e2e, latency or CPU legs")
+    ap.add_argument("--projected", action="store_true",
+                    help="SURVEY 8f-2: start the step at the hidden features and fold the head's 1x1 projection "
+                         "into the similarity (both arms)")
     ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"],
                     help="bf16 = the metric's configuration; fp32 = three-pass hi/lo recipe (BASELINE configs[1])")
     ap.add_argument("--image-size", type=int, default=IMAGE_SIZE,

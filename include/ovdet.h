@@ -135,6 +135,30 @@ OVDET_API int ovdet_similarity_fused(const float* const* obj_embeds, const int64
                                      int64_t ldc, float* row_max, int32_t* row_arg,
                                      float* inv_norm, void* stream);
 
+/* K1+K2 projected ("next" row f-2)  the head's last layer - nn.Conv2d(hidden_dim, embed_dim, 1),
+ * model/heads/text_contrastive.py:67 applied at :112 - folded into the similarity: the kernel
+ * reads the HIDDEN features and never forms the embed_dim-wide embedding.
+ * Replaces: text_contrastive.py:112 (1x1 conv) + :134-147 + model/yolo_clip.py:198-206, all levels.
+ *
+ *   hidden      HOST array of num_levels device pointers, fp32 [batch, hidden_dim, hw[l]] (same
+ *               addressing / alignment rules as ovdet_similarity_fused); hidden_dim <= 448
+ *   level_ops   HOST array of num_levels device pointers: level l's bf16 operand
+ *               [text_batch, Cpad + kop, kop], kop = ceil(hidden_dim / 64) * 64 + 16,
+ *               Cpad = classes rounded up to 128: rows [0, classes) = [W^T t_c | <b, t_c>] (t_c the
+ *               unit-norm text row, W / b the level's 1x1 conv), rows [Cpad, Cpad + kop) =
+ *               G' = [[W^T W, W^T b], [b^T W, b^T b]] (the constant of x' = [x, 1] sits at column
+ *               ceil(hidden_dim / 64) * 64); built by the host layer (ops.project_vocabulary)
+ *   row_max     fp32 [batch, anchors]: alpha * max_c cos(W x + b, t_c) + beta   (alpha >= 0)
+ *   row_arg     optional int32 [batch, anchors]; inv_norm optional fp32: 1 / max(||W x + b||, 1e-12)
+ * One bf16 tensor-core pass (|dscore| <~ 8e-3); no logits in this mode.
+ */
+OVDET_API int ovdet_similarity_projected(const float* const* hidden, const int64_t* hw,
+                                         const int64_t* stride_b, const int64_t* stride_d,
+                                         int num_levels, int64_t batch, int64_t hidden_dim,
+                                         const void* const* level_ops, int64_t classes, int text_batched,
+                                         float alpha, float beta, float* row_max, int32_t* row_arg,
+                                         float* inv_norm, void* stream);
+
 /* K2b  max/argmax over classes of materialised logits (any producer).
  * Replaces: model/yolo_clip.py:198-202 (similarity.max(dim=1)); ties -> lowest class index.
  *   logits [rows, ldc] fp32 or bf16, columns [0,classes) are read. */

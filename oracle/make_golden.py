@@ -246,6 +246,28 @@ def tcsp_case():
     save("tcsp_layer", **arrays)
 
 
+def head_projection_case():
+    """Live reference TextContrastiveHead: the hidden features entering the last (1x1) layer of
+    obj_embed_conv, that layer's weight / bias, forward()'s obj_embed, compute_similarity() and
+    the class max of yolo_clip.py:198-202 - the reference for the folded projection (row f-2).
+    Small hidden / embed dims keep the fixture small."""
+    torch.manual_seed(18)
+    head = TextContrastiveHead(in_channels=12, embed_dim=128, hidden_dim=64, cls_alpha=1.2, cls_beta=0.05).eval()
+    head.obj_embed_conv[2].bias.data.normal_(0, 0.1)
+    x = torch.randn(2, 12, 8, 6)
+    text = torch.randn(2, 7, 128)
+    captured = {}
+    hook = head.obj_embed_conv[1].register_forward_hook(lambda m, i, o: captured.__setitem__("h", o.detach().clone()))
+    with torch.no_grad():
+        obj_embed, _ = head(x)
+        sim = head.compute_similarity(obj_embed, text)
+        scores, ids = sim.max(dim=1)
+    hook.remove()
+    save("head_projection", hidden=captured["h"].numpy(), weight=head.obj_embed_conv[2].weight.detach().numpy(),
+         bias=head.obj_embed_conv[2].bias.detach().numpy(), text=text.numpy(), obj_embed=obj_embed.numpy(),
+         scores=scores.flatten(1).numpy(), class_ids=ids.flatten(1).numpy(), alpha_beta=np.array([1.2, 0.05]))
+
+
 def vocabulary_case():
     """Reference VocabBuilder.build_offline_vocabulary -> JSON file (stub CLIP encoder), and the
     matrix YOLOCLIP.load_offline_vocabulary stacks from it."""
@@ -276,3 +298,4 @@ if __name__ == "__main__":
     preprocess_cases()
     vocabulary_case()
     tcsp_case()
+    head_projection_case()

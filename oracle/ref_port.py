@@ -327,3 +327,18 @@ def max_sigmoid_attention(y: torch.Tensor, projected_text: torch.Tensor) -> Tupl
     weights = torch.sigmoid(max_scores)                                        # :89
     attended = y_r * weights                                                   # :92
     return attended.reshape(b, h, w, c).permute(0, 3, 1, 2), max_scores.squeeze(-1)   # :95
+
+
+def project_similarity_max(hidden: Sequence[torch.Tensor], weights: Sequence[torch.Tensor],
+                           biases: Sequence[torch.Tensor], text_embed: torch.Tensor,
+                           alpha: float = 1.0, beta: float = 0.0):
+    """"Next" row f-2: the last layer of ``obj_embed_conv`` (``nn.Conv2d(hidden_dim, embed_dim, 1)``,
+    model/heads/text_contrastive.py:67 applied at :112) followed by ``compute_similarity`` (:119-153)
+    and the class max / level concat of model/yolo_clip.py:198-206, per level.  ``hidden[l]`` is
+    ``[B, hidden_dim, H, W]`` (the output of the second ConvBlock), ``weights[l] [embed, hidden, 1, 1]``
+    and ``biases[l] [embed]`` the level's 1x1 convolution.  Returns (scores [B, A], class_ids [B, A],
+    obj_embeds list)."""
+    embeds = [F.conv2d(h, w, b) for h, w, b in zip(hidden, weights, biases)]
+    sims = [compute_similarity(e, text_embed, alpha, beta) for e in embeds]
+    scores, ids = class_max_concat(sims)
+    return scores, ids, embeds

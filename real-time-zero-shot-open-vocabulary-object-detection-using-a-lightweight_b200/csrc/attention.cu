@@ -55,7 +55,7 @@ extern "C" int ovdet_max_sigmoid_attention(const float* y, int64_t batch, int64_
     return OVDET_ERR_UNSUPPORTED_SHAPE;
   const float* levels[1] = {y};
   const int64_t hws[1] = {hw}, sb[1] = {stride_b}, sc[1] = {stride_c};
-  int rc = fused_launch(levels, hws, sb, sc, 1, batch, channels, text_op, classes, text_batched,
+  int rc = fused_launch(levels, hws, sb, sc, 1, batch, channels, text_op, nullptr, classes, text_batched,
                         /*normalize=*/0, precise ? 1 : 0, 1.0f, 0.0f, nullptr, OVDET_F32, classes,
                         row_max, nullptr, nullptr, stream);
   if (rc != OVDET_OK || batch == 0) return rc;

@@ -87,7 +87,7 @@ struct FSmem {
 };
 static_assert(FSmem<1>::bytes <= 227 * 1024 && FSmem<2>::bytes <= 227 * 1024, "shared memory budget");
 
-struct LevelMaps { CUtensorMap m[F_MAX_LEVELS]; };
+struct LevelMaps { CUtensorMap m[F_MAX_LEVELS]; };   // activations; (projected) one text operand per level
 
 struct FusedParams {
   int levels;
@@ -101,7 +101,11 @@ struct FusedParams {
   int kb;                          // k blocks of 64 the MMA walks (3 * kb_in with split3)
   int kb_in;                       // fp32 input blocks per anchor tile: ceil(dim / 64)
   int normalize;                   // 1: scale rows by 1 / max(||x||, 1e-12) (cosine); 0: raw dot product
-  int n_tiles;
+  int n_tiles;                     // N tiles per anchor tile (projected: ng_tiles of G' first, then classes)
+  int proj;                        // 1: projected similarity (hidden features in, quadratic-form norm)
+  int ng_tiles;                    // projected: N tiles holding G' (kop rows)
+  int cpad;                        // projected: first G' row of the operand (classes padded to 128)
+  int kop;                         // projected: operand row length = kb_in * 64 + 16
   int text_batched;
   float alpha, beta;
   void* logits;
@@ -142,16 +146,26 @@ __device__ __forceinline__ TileCoord decode_tile(const FusedParams& p, int tile)
 // hi = bf16(x), lo = bf16(x - hi); the activation blocks are written to tensor memory as
 // [hi | hi | lo] and the text operand is laid out [hi | lo | hi] (ovdet_cast_text), so the plain
 // block loop accumulates hi*hi + hi*lo + lo*hi (the lo*lo term is < 2^-16 relative).
-template <int KB_T, bool SPLIT3, int CG>
+//
+// PROJ ("next" row f-2): the head's 1x1 projection folded into the vocabulary (ops.py
+// project_vocabulary).  The activations are the HIDDEN features x (K = hidden + 1 with the
+// constant 1 in an extra 16-wide k block that is written to tensor memory once); the operand of
+// level l holds the projected classes [W^T t_c | <b, t_c>] and then the rows of
+// G' = [[W^T W, W^T b], [b^T W, b^T b]].  The first ng N tiles of every anchor tile multiply
+// against G': their epilogue accumulates q = sum_j (x' G')_j x'_j = ||W x + b||^2 with x' read
+// back from the A region of tensor memory; the class tiles keep the raw running max/argmax and
+// the row is scaled by alpha / sqrt(q) once at the end.  No logits in this mode.
+template <int KB_T, bool SPLIT3, int CG, bool PROJ>
 __global__ void __launch_bounds__(F_THREADS, 1)
-sim_fused_kernel(const __grid_constant__ LevelMaps amaps, const __grid_constant__ CUtensorMap tmap_b,
+sim_fused_kernel(const __grid_constant__ LevelMaps amaps, const __grid_constant__ LevelMaps bmaps,
                  const FusedParams p) {
   using FSmem = ovdet::FSmem<CG>;
   constexpr int F_B_STAGES = FSmem::b_stages;
   constexpr int F_B_STAGE_BYTES = FSmem::b_stage_bytes;
   constexpr int KPS = FSmem::kps;
   constexpr int F_B_SUB_BYTES = FSmem::b_sub_bytes;
-  static_assert(CG == 1 || KB_T % KPS == 0, "CTA pairs need a compile-time, even k-block count");
+  static_assert(CG == 1 || KB_T > 0, "CTA pairs need a compile-time k-block count");
+  static_assert(!(PROJ && SPLIT3), "the projected mode is a single bf16 pass");
   // cluster rank: 0 = leader (issues the MMAs, owns the barriers the pair synchronises on)
   const uint32_t rank = CG == 2 ? ptx::cluster_ctarank() : 0u;
   const int pair0 = blockIdx.x / CG, pair_stride = gridDim.x / CG;
@@ -182,12 +196,13 @@ sim_fused_kernel(const __grid_constant__ LevelMaps amaps, const __grid_constant_
   const int lane = threadIdx.x & 31;
 
   if (warp == 0 && lane == 0) {
-    ptx::prefetch_tmap(&tmap_b);
-    for (int l = 0; l < p.levels; ++l) ptx::prefetch_tmap(&amaps.m[l]);
+    for (int l = 0; l < p.levels; ++l) { ptx::prefetch_tmap(&amaps.m[l]); ptx::prefetch_tmap(&bmaps.m[PROJ ? l : 0]); }
     for (int s = 0; s < F_B_STAGES; ++s) { ptx::mbar_init(b_full0 + 8u * s, 1); ptx::mbar_init(b_empty0 + 8u * s, 1); }
     for (int s = 0; s < F_A_STAGES; ++s) { ptx::mbar_init(as_full0 + 8u * s, 1); ptx::mbar_init(as_empty0 + 8u * s, 4); }
     // a_ready / t_empty collect the converter / epilogue warps of BOTH CTAs on the leader
-    for (int k = 0; k < F_MAX_KB; ++k) { ptx::mbar_init(a_ready0 + 8u * k, 4 * CG); ptx::mbar_init(a_free0 + 8u * k, 1); }
+    for (int k = 0; k < F_MAX_KB; ++k) { ptx::mbar_init(a_ready0 + 8u * k, 4 * CG);
+      // projected: the epilogue warps read x' back from the A region, so they release it too
+      ptx::mbar_init(a_free0 + 8u * k, PROJ ? 5 : 1); }
     for (int s = 0; s < 2; ++s) { ptx::mbar_init(t_full0 + 8u * s, 1); ptx::mbar_init(t_empty0 + 8u * s, 4 * CG); }
     for (int s = 0; s < 3; ++s) ptx::mbar_init(n_ready0 + 8u * s, 4);
     ptx::fence_mbar_init();
@@ -209,9 +224,19 @@ sim_fused_kernel(const __grid_constant__ LevelMaps amaps, const __grid_constant_
   const uint32_t lead_b_full0 = CG == 2 ? ptx::map_to_cta(b_full0, 0) : b_full0;
   const uint32_t lead_a_ready0 = CG == 2 ? ptx::map_to_cta(a_ready0, 0) : a_ready0;
   const uint32_t lead_t_empty0 = CG == 2 ? ptx::map_to_cta(t_empty0, 0) : t_empty0;
-  const int KB = KB_T ? KB_T : p.kb;
-  const int KB_IN = KB_T ? KB_T : p.kb_in;
+  const int KB_IN = KB_T ? KB_T : p.kb_in;                       // fp32 input blocks per anchor tile
+  const int KB = PROJ ? KB_IN + 1 : (KB_T ? KB_T : p.kb);        // k blocks the MMA walks
+  const int KB_A = PROJ ? KB_IN : KB;                            // A blocks rewritten per anchor tile
+  const int NSTAGE = (KB + KPS - 1) / KPS;                       // text stages per N tile
   const int NT = p.n_tiles;
+  const int NG = PROJ ? p.ng_tiles : 0;
+  // N tile nt of an anchor tile: first operand row, MMA N (multiple of 16), valid columns
+  auto ntile_row0 = [&](int nt) { return nt < NG ? p.cpad + nt * F_BLOCK_N : (nt - NG) * F_BLOCK_N; };
+  auto ntile_valid = [&](int nt) {
+    const int n = nt < NG ? p.kop - nt * F_BLOCK_N : p.classes - (nt - NG) * F_BLOCK_N;
+    return n >= F_BLOCK_N ? F_BLOCK_N : n;
+  };
+  auto ntile_nsize = [&](int nt) { return (ntile_valid(nt) + 15) & ~15; };
 
   // Producer / issuer warps run warp-uniform control flow; `issue` is 1 in one elected lane and
   // predicates the single-thread instructions (see ptx::elect_one).
@@ -223,29 +248,31 @@ sim_fused_kernel(const __grid_constant__ LevelMaps amaps, const __grid_constant_
       const int tile = pair * CG + (int)rank;
       const TileCoord tc = decode_tile(p, tile);
       const int tb = p.text_batched ? tc.b : 0;
+      const CUtensorMap* bmap = &bmaps.m[PROJ ? tc.level : 0];
       for (int nt = 0; nt < NT; ++nt, ++g) {
-        int n_size = p.classes - nt * F_BLOCK_N;
-        n_size = n_size >= F_BLOCK_N ? F_BLOCK_N : ((n_size + 15) & ~15);
-        const int n_half = n_size >> 1;
+        const int row0 = ntile_row0(nt);
+        const int n_half = ntile_nsize(nt) >> 1;
         (void)n_half;
 #pragma unroll
-        for (int sb = 0; sb < KB / KPS; ++sb) {
-          const uint32_t it = g * (uint32_t)(KB / KPS) + (uint32_t)sb;     // stages produced so far
+        for (int sb = 0; sb < NSTAGE; ++sb) {
+          const uint32_t it = g * (uint32_t)NSTAGE + (uint32_t)sb;         // stages produced so far
           const uint32_t s = it % F_B_STAGES, ph = (it / F_B_STAGES) & 1u;
+          const int subs = min(KPS, KB - sb * KPS);                         // k blocks in this stage
           ptx::mbar_wait_lazy(b_empty0 + 8u * s, ph ^ 1u, lazy_ns);
           if constexpr (CG == 1) {
             ptx::mbar_arrive_expect_tx_if(issue, b_full0 + 8u * s, F_B_STAGE_BYTES);
-            ptx::tma_load_3d_if(issue, smem_b + s * F_B_STAGE_BYTES, &tmap_b, b_full0 + 8u * s,
-                                sb * F_BLOCK_K, nt * F_BLOCK_N, tb);
+            ptx::tma_load_3d_if(issue, smem_b + s * F_B_STAGE_BYTES, bmap, b_full0 + 8u * s,
+                                sb * F_BLOCK_K, row0, tb);
           } else {
             // this CTA's half of the N tile (rows [rank * n/2, (rank + 1) * n/2) of it) lands in its
             // own shared memory; both halves complete on the LEADER's barrier, which expects both
-            if (rank == 0) ptx::mbar_arrive_expect_tx_if(issue, b_full0 + 8u * s, 2 * F_B_STAGE_BYTES);
+            if (rank == 0) ptx::mbar_arrive_expect_tx_if(issue, b_full0 + 8u * s, 2 * subs * F_B_SUB_BYTES);
 #pragma unroll
             for (int j = 0; j < KPS; ++j)
-              ptx::tma_load_3d_pair_if(issue, smem_b + s * F_B_STAGE_BYTES + j * F_B_SUB_BYTES, &tmap_b,
-                                       lead_b_full0 + 8u * s, (sb * KPS + j) * F_BLOCK_K,
-                                       nt * F_BLOCK_N + (int)rank * n_half, tb);
+              if (j < subs)
+                ptx::tma_load_3d_pair_if(issue, smem_b + s * F_B_STAGE_BYTES + j * F_B_SUB_BYTES, bmap,
+                                         lead_b_full0 + 8u * s, (sb * KPS + j) * F_BLOCK_K,
+                                         row0 + (int)rank * n_half, tb);
           }
         }
       }
@@ -258,42 +285,48 @@ sim_fused_kernel(const __grid_constant__ LevelMaps amaps, const __grid_constant_
     uint32_t g = 0, lt = 0;
     for (int pair = pair0; pair < total_pairs; pair += pair_stride, ++lt) {
       for (int nt = 0; nt < NT; ++nt, ++g) {
-        int n_size = p.classes - nt * F_BLOCK_N;
-        n_size = n_size >= F_BLOCK_N ? F_BLOCK_N : ((n_size + 15) & ~15);
+        const int n_size = ntile_nsize(nt);
         const uint32_t idesc = ptx::umma_idesc_bf16_f32(F_BLOCK_M * CG, (uint32_t)n_size);
         const uint32_t as = g & 1u;
         const bool first_nt = nt == 0, last_nt = nt == NT - 1;
-        const uint32_t it0 = g * (uint32_t)(KB / KPS);
+        const uint32_t it0 = g * (uint32_t)NSTAGE;
         // peek at the first text stage while waiting for the accumulator to drain
         bool ready = ptx::mbar_try_wait(b_full0 + 8u * (it0 % F_B_STAGES), (it0 / F_B_STAGES) & 1u);
         ptx::mbar_wait(t_empty0 + 8u * as, ((g >> 1) & 1u) ^ 1u);
         const uint32_t d_tmem = tmem_u + (uint32_t)F_ACC_COL + as * (uint32_t)F_BLOCK_N;
 #pragma unroll
-        for (int sb = 0; sb < KB / KPS; ++sb) {
+        for (int sb = 0; sb < NSTAGE; ++sb) {
           const uint32_t it = it0 + (uint32_t)sb;
           const uint32_t s = it % F_B_STAGES, ph = (it / F_B_STAGES) & 1u;
           if (first_nt) {                                                // A blocks converted (both CTAs)?
 #pragma unroll
-            for (int j = 0; j < KPS; ++j) ptx::mbar_wait(a_ready0 + 8u * (sb * KPS + j), lt & 1u);
+            for (int j = 0; j < KPS; ++j)
+              if (sb * KPS + j < KB_A) ptx::mbar_wait(a_ready0 + 8u * (sb * KPS + j), lt & 1u);
           }
           ptx::mbar_wait_if_not(ready, b_full0 + 8u * s, ph);
           ptx::tc_fence_after();
-          if (sb + 1 < KB / KPS)                                         // hide the next wait's latency
+          if (sb + 1 < NSTAGE)                                           // hide the next wait's latency
             ready = ptx::mbar_try_wait(b_full0 + 8u * ((it + 1) % F_B_STAGES), ((it + 1) / F_B_STAGES) & 1u);
           if (ptx::elect_one()) {
 #pragma unroll
             for (int j = 0; j < KPS; ++j) {
               const int kb = sb * KPS + j;
-              const uint64_t b_desc = ptx::umma_desc_k_sw128(smem_b_u + s * F_B_STAGE_BYTES + j * F_B_SUB_BYTES);
-              const uint32_t a_tmem = tmem_u + (uint32_t)(F_A_COL + kb * 32);
+              if (kb < KB) {
+                const uint64_t b_desc = ptx::umma_desc_k_sw128(smem_b_u + s * F_B_STAGE_BYTES + j * F_B_SUB_BYTES);
+                const uint32_t a_tmem = tmem_u + (uint32_t)(F_A_COL + kb * 32);
+                // projected: the last block is the 16-wide constant block of x' = [x, 1]
+                const int ksteps = (PROJ && kb == KB - 1) ? 1 : F_BLOCK_K / 16;
 #pragma unroll
-              for (int k = 0; k < F_BLOCK_K / 16; ++k)
-                ptx::umma_bf16_ts_cg<CG>(d_tmem, a_tmem + 8u * k, b_desc + 2u * k, idesc, (kb | k) != 0);
+                for (int k = 0; k < F_BLOCK_K / 16; ++k)
+                  if (k < ksteps)
+                    ptx::umma_bf16_ts_cg<CG>(d_tmem, a_tmem + 8u * k, b_desc + 2u * k, idesc, (kb | k) != 0);
+              }
             }
             ptx::umma_commit_cg<CG>(b_empty0 + 8u * s);                  // text stage reusable (both CTAs)
             if (last_nt) {                                               // these A blocks may be overwritten
 #pragma unroll
-              for (int j = 0; j < KPS; ++j) ptx::umma_commit_cg<CG>(a_free0 + 8u * (sb * KPS + j));
+              for (int j = 0; j < KPS; ++j)
+                if (sb * KPS + j < KB_A) ptx::umma_commit_cg<CG>(a_free0 + 8u * (sb * KPS + j));
             }
           }
           __syncwarp();
@@ -348,6 +381,16 @@ sim_fused_kernel(const __grid_constant__ LevelMaps amaps, const __grid_constant_
     // ================================ converters =============================================
     const int lg = warp & 3;
     const int arow = lg * 32 + lane;                 // anchor row of the tile == TMEM lane
+    if constexpr (PROJ) {
+      // x' = [x, 1]: the constant block (k = KB_IN * 64: 1, then zeros) never changes
+      uint32_t one[32];
+#pragma unroll
+      for (int i = 0; i < 32; ++i) one[i] = 0u;
+      one[0] = 0x00003F80u;                           // bf16 pair (1.0, 0.0)
+      ptx::tmem_st_32x32(tmem_base + ((uint32_t)(lg * 32) << 16) + (uint32_t)(F_A_COL + KB_IN * 32), one);
+      ptx::tmem_st_wait();
+      ptx::tc_fence_before();
+    }
     uint32_t ia = 0, lt = 0;
     for (int pair = pair0; pair < total_pairs; pair += pair_stride, ++lt) {
       const int tile = pair * CG + (int)rank;
@@ -400,7 +443,7 @@ sim_fused_kernel(const __grid_constant__ LevelMaps amaps, const __grid_constant_
       const float inv = 1.0f / fmaxf(sqrtf((ss0 + ss1) + (ss2 + ss3)), 1e-12f);
       const int slot = lt % 3;
       norm_s[slot * F_BLOCK_M + arow] = inv;
-      if (p.inv_norm != nullptr && arow < tc.rows) p.inv_norm[tc.out_row0 + arow] = inv;
+      if (!PROJ && p.inv_norm != nullptr && arow < tc.rows) p.inv_norm[tc.out_row0 + arow] = inv;
       __syncwarp();
       if (lane == 0) ptx::mbar_arrive(n_ready0 + 8u * slot);
     }
@@ -417,8 +460,9 @@ sim_fused_kernel(const __grid_constant__ LevelMaps amaps, const __grid_constant_
       const bool row_ok = r_in_tile < tc.rows;
       const long long grow = tc.out_row0 + r_in_tile;
       const int slot = lt % 3;
-      ptx::mbar_wait(n_ready0 + 8u * slot, (lt / 3) & 1u);
-      const float scale = p.normalize ? p.alpha * norm_s[slot * F_BLOCK_M + r_in_tile] : p.alpha;
+      if constexpr (!PROJ) ptx::mbar_wait(n_ready0 + 8u * slot, (lt / 3) & 1u);
+      const float scale = PROJ ? 1.0f : (p.normalize ? p.alpha * norm_s[slot * F_BLOCK_M + r_in_tile] : p.alpha);
+      float q = 0.f;                                   // projected: ||W x + b||^2
       const float beta = p.beta;
       float bv[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
       int bi[4] = {0, 0, 0, 0};
@@ -428,17 +472,46 @@ sim_fused_kernel(const __grid_constant__ LevelMaps amaps, const __grid_constant_
       // (the attention row): one FMNMX3 per two values.  With argmax: compare + select + index
       // per value, no FFMA; the class returned is the argmax of the fp32 accumulators (lowest
       // index among equal accumulators).
-      const bool raw_mode = want_max && p.logits == nullptr && p.alpha >= 0.f && !(p.dbg & 2);
+      const bool raw_mode = PROJ || (want_max && p.logits == nullptr && p.alpha >= 0.f && !(p.dbg & 2));
       const bool max_only = raw_mode && p.row_arg == nullptr;
       float raw_best = -INFINITY;
       for (int nt = 0; nt < NT; ++nt, ++acc_it) {
-        const int n0 = nt * F_BLOCK_N;
-        const int n_valid = min(F_BLOCK_N, p.classes - n0);
+        const int n0 = (nt - NG) * F_BLOCK_N;          // first class of a class tile
+        const int n_valid = ntile_valid(nt);
         const int nchunks = (n_valid + 31) >> 5;
         const int as = acc_it & 1;
         ptx::mbar_wait(t_full0 + 8u * as, (acc_it >> 1) & 1u);
         ptx::tc_fence_after();
         const uint32_t t_row = tmem_base + ((uint32_t)(lg * 32) << 16) + (uint32_t)(F_ACC_COL + as * F_BLOCK_N);
+        if (PROJ && nt < NG) {
+          // G' tile: q += sum_j acc_j * x'_j, x' (bf16 pairs) read back from the A region
+          const uint32_t a_row = tmem_base + ((uint32_t)(lg * 32) << 16) + (uint32_t)F_A_COL;
+          uint32_t acc[32], xa[16];
+          for (int c = 0; c < nchunks; ++c) {
+            const int j0 = nt * F_BLOCK_N + (c << 5);                  // k index of the chunk's first column
+            ptx::tmem_ld_32x32(t_row + (uint32_t)(c << 5), acc);
+            ptx::tmem_ld_32x32_x16(a_row + (uint32_t)(j0 >> 1), xa);
+            ptx::tmem_ld_wait();
+            const int valid = n_valid - (c << 5);                      // 32, or 16 in the last tile
+            float q0 = 0.f, q1 = 0.f;
+#pragma unroll
+            for (int i = 0; i < 16; ++i)
+              if (2 * i < valid) {
+                q0 = fmaf(__uint_as_float(acc[2 * i]), __uint_as_float(xa[i] << 16), q0);
+                q1 = fmaf(__uint_as_float(acc[2 * i + 1]), __uint_as_float(xa[i] & 0xffff0000u), q1);
+              }
+            q += q0 + q1;
+          }
+          ptx::tc_fence_before();
+          __syncwarp();
+          if (lane == 0) {
+            if constexpr (CG == 2) ptx::mbar_arrive_cluster(lead_t_empty0 + 8u * as);
+            else ptx::mbar_arrive(t_empty0 + 8u * as);
+            if (nt == NG - 1)                                          // done reading x': the A region may be rewritten
+              for (int kb = 0; kb < KB_IN; ++kb) ptx::mbar_arrive(a_free0 + 8u * kb);
+          }
+          continue;
+        }
 
         auto consume = [&](uint32_t (&r)[32], int c) {
           const int c0 = c << 5;
@@ -560,7 +633,20 @@ sim_fused_kernel(const __grid_constant__ LevelMaps amaps, const __grid_constant_
           else ptx::mbar_arrive(t_empty0 + 8u * as);
         }
       }
-      if (max_only) {
+      if (PROJ) {
+        float best = bv[0];
+        int best_idx = bi[0];
+#pragma unroll
+        for (int qd = 1; qd < 4; ++qd)
+          if (bv[qd] > best || (bv[qd] == best && bi[qd] < best_idx)) { best = bv[qd]; best_idx = bi[qd]; }
+        if (max_only) best = raw_best;
+        const float inv = 1.0f / fmaxf(sqrtf(fmaxf(q, 0.f)), 1e-12f);  // F.normalize's eps
+        if (row_ok) {
+          p.row_max[grow] = fmaf(p.alpha * inv, best, beta);
+          if (p.row_arg != nullptr) p.row_arg[grow] = best_idx;
+          if (p.inv_norm != nullptr) p.inv_norm[grow] = inv;
+        }
+      } else if (max_only) {
         if (row_ok) p.row_max[grow] = fmaf(scale, raw_best, beta);
       } else if (want_max && row_ok) {
         float best = bv[0];
@@ -603,40 +689,48 @@ EncodeTiledFn fused_encode_fn() {
 
 }  // namespace
 
-// Shared launcher.  `dim` is the real embedding length; it is padded to a multiple of 64 by the
-// TMA zero fill on the activation side and by zero columns in the text operand, whose row length
-// is kop = (split3 ? 3 : 1) * ceil(dim / 64) * 64.
+// Shared launcher.  `dim` is the real length of an activation vector; it is padded to a multiple
+// of 64 by the TMA zero fill on the activation side and by zero columns in the text operand.
+// Cosine / raw modes: one operand `text_op` with rows of kop = (split3 ? 3 : 1) * ceil(dim / 64) * 64.
+// Projected mode (`level_ops` != NULL): one operand per level, [Cpad + kop, kop] with
+// kop = ceil(dim / 64) * 64 + 16 (ops.py project_vocabulary), scores / argmax only.
 int fused_launch(const float* const* obj_embeds, const int64_t* hw, const int64_t* stride_b,
                  const int64_t* stride_d, int num_levels, int64_t batch, int64_t dim,
-                 const void* text_op, int64_t classes, int text_batched, int normalize, int split3,
-                 float alpha, float beta, void* logits, int logits_dtype, int64_t ldc,
-                 float* row_max, int32_t* row_arg, float* inv_norm, void* stream) {
-  if (!obj_embeds || !hw || !stride_b || !stride_d || !text_op || batch < 0 || classes <= 0 || dim <= 0)
+                 const void* text_op, const void* const* level_ops, int64_t classes, int text_batched,
+                 int normalize, int split3, float alpha, float beta, void* logits, int logits_dtype,
+                 int64_t ldc, float* row_max, int32_t* row_arg, float* inv_norm, void* stream) {
+  const int proj = level_ops != nullptr;
+  if (!obj_embeds || !hw || !stride_b || !stride_d || (!text_op && !proj) || batch < 0 || classes <= 0 || dim <= 0)
     return OVDET_ERR_INVALID_ARG;
   if (num_levels <= 0) return OVDET_ERR_INVALID_ARG;
   if (!logits && !row_max) return OVDET_ERR_INVALID_ARG;
   if (row_arg && !row_max) return OVDET_ERR_INVALID_ARG;
   if (logits && (ldc < classes || (logits_dtype != OVDET_F32 && logits_dtype != OVDET_BF16)))
     return OVDET_ERR_INVALID_ARG;
+  if (proj && (logits || split3 || alpha < 0.f || !row_max)) return OVDET_ERR_INVALID_ARG;
   const int kb_in = (int)ceil_div<int64_t>(dim, F_BLOCK_K);
-  const int kb = kb_in * (split3 ? 3 : 1);
-  // CTA pairs (cta_group::2) for the dim = 512 similarity; OVDET_FUSED_CG=1 forces single CTAs
-  static const int cg_env = []() { const char* e = getenv("OVDET_FUSED_CG"); return e ? atoi(e) : 2; }();
-  const int cg = (kb == 8 && !split3 && cg_env == 2) ? 2 : 1;
+  const int kb = proj ? kb_in + 1 : kb_in * (split3 ? 3 : 1);
   if (num_levels > F_MAX_LEVELS || kb > F_MAX_KB || batch > 65535) return OVDET_ERR_UNSUPPORTED_SHAPE;
-  if ((uintptr_t)text_op & 15) return OVDET_ERR_INVALID_ARG;
+  if (!proj && ((uintptr_t)text_op & 15)) return OVDET_ERR_INVALID_ARG;
+  // CTA pairs (cta_group::2) for the dim = 512 similarity and the hidden = 256 projected one;
+  // OVDET_FUSED_CG=1 forces single CTAs
+  static const int cg_env = []() { const char* e = getenv("OVDET_FUSED_CG"); return e ? atoi(e) : 2; }();
+  const int cg = (cg_env == 2 && !split3 && ((!proj && kb == 8) || (proj && kb_in == 4))) ? 2 : 1;
   EncodeTiledFn enc = nullptr;
   FusedParams p{};
-  LevelMaps maps;
+  LevelMaps maps, bmaps;
   long long anchors = 0, tiles = 0;
   for (int l = 0; l < num_levels; ++l) {
     if (!obj_embeds[l] || hw[l] <= 0) return OVDET_ERR_INVALID_ARG;
+    if (proj && (!level_ops[l] || ((uintptr_t)level_ops[l] & 15))) return OVDET_ERR_INVALID_ARG;
     // TMA needs 16-byte aligned base and strides
     if (((uintptr_t)obj_embeds[l] & 15) || (stride_d[l] & 3) || (stride_b[l] & 3) || stride_d[l] < hw[l])
       return OVDET_ERR_UNSUPPORTED_SHAPE;
     p.hw[l] = (int)hw[l];
     p.mt[l] = (int)ceil_div<int64_t>(hw[l], F_BLOCK_M);
-    if (cg == 2 && text_batched) p.mt[l] = (p.mt[l] + 1) & ~1;     // a pair never straddles two images
+    // a pair multiplies against ONE text tile: it never straddles two images (per-image text) or
+    // two levels (per-level operands)
+    if (cg == 2 && (text_batched || proj)) p.mt[l] = (p.mt[l] + 1) & ~1;
     p.off[l] = (int)anchors;
     p.tile_start[l] = (int)tiles;
     anchors += hw[l];
@@ -659,19 +753,22 @@ int fused_launch(const float* const* obj_embeds, const int64_t* hw, const int64_
     if (r != CUDA_SUCCESS) return OVDET_ERR_DRIVER;
   }
   for (int l = num_levels; l < F_MAX_LEVELS; ++l) maps.m[l] = maps.m[0];
-  CUtensorMap map_b;
-  {
+  const int64_t kop = proj ? (int64_t)kb_in * F_BLOCK_K + 16 : (int64_t)kb * F_BLOCK_K;
+  const int64_t cpad = ceil_div<int64_t>(classes, F_BLOCK_N) * F_BLOCK_N;
+  const int64_t op_rows = proj ? cpad + kop : classes;
+  for (int l = 0; l < (proj ? num_levels : 1); ++l) {
     const int64_t tb = text_batched ? batch : 1;
-    const int64_t kop = (int64_t)kb * F_BLOCK_K;
-    cuuint64_t dims[3] = {(cuuint64_t)kop, (cuuint64_t)classes, (cuuint64_t)tb};
-    cuuint64_t strides[2] = {(cuuint64_t)kop * 2, (cuuint64_t)classes * (cuuint64_t)kop * 2};
+    cuuint64_t dims[3] = {(cuuint64_t)kop, (cuuint64_t)op_rows, (cuuint64_t)tb};
+    cuuint64_t strides[2] = {(cuuint64_t)kop * 2, (cuuint64_t)op_rows * (cuuint64_t)kop * 2};
     cuuint32_t box[3] = {(cuuint32_t)F_BLOCK_K, (cuuint32_t)(F_BLOCK_N / cg), 1};
     cuuint32_t estr[3] = {1, 1, 1};
-    CUresult r = enc(&map_b, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(text_op), dims, strides,
+    const void* op = proj ? level_ops[l] : text_op;
+    CUresult r = enc(&bmaps.m[l], CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(op), dims, strides,
                      box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
                      CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) return OVDET_ERR_DRIVER;
   }
+  for (int l = (proj ? num_levels : 1); l < F_MAX_LEVELS; ++l) bmaps.m[l] = bmaps.m[0];
   p.levels = num_levels;
   p.batch = (int)batch;
   p.tile_start[num_levels] = (int)tiles;
@@ -680,7 +777,11 @@ int fused_launch(const float* const* obj_embeds, const int64_t* hw, const int64_
   p.kb = kb;
   p.kb_in = kb_in;
   p.normalize = normalize ? 1 : 0;
-  p.n_tiles = (int)ceil_div<int64_t>(classes, F_BLOCK_N);
+  p.proj = proj;
+  p.ng_tiles = proj ? (int)ceil_div<int64_t>(kop, F_BLOCK_N) : 0;
+  p.cpad = (int)cpad;
+  p.kop = (int)kop;
+  p.n_tiles = (int)ceil_div<int64_t>(classes, F_BLOCK_N) + p.ng_tiles;
   p.text_batched = text_batched ? 1 : 0;
   p.alpha = alpha;
   p.beta = beta;
@@ -696,10 +797,12 @@ int fused_launch(const float* const* obj_embeds, const int64_t* hw, const int64_
   p.dbg = dbg_env;
 
   if (first_use_on_device(1)) {
-    OVDET_CUDA_TRY(cudaFuncSetAttribute(sim_fused_kernel<8, false, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, FSmem<1>::bytes));
-    OVDET_CUDA_TRY(cudaFuncSetAttribute(sim_fused_kernel<0, false, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, FSmem<1>::bytes));
-    OVDET_CUDA_TRY(cudaFuncSetAttribute(sim_fused_kernel<0, true, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, FSmem<1>::bytes));
-    OVDET_CUDA_TRY(cudaFuncSetAttribute(sim_fused_kernel<8, false, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, FSmem<2>::bytes));
+    OVDET_CUDA_TRY(cudaFuncSetAttribute(sim_fused_kernel<8, false, 1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, FSmem<1>::bytes));
+    OVDET_CUDA_TRY(cudaFuncSetAttribute(sim_fused_kernel<0, false, 1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, FSmem<1>::bytes));
+    OVDET_CUDA_TRY(cudaFuncSetAttribute(sim_fused_kernel<0, true, 1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, FSmem<1>::bytes));
+    OVDET_CUDA_TRY(cudaFuncSetAttribute(sim_fused_kernel<8, false, 2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, FSmem<2>::bytes));
+    OVDET_CUDA_TRY(cudaFuncSetAttribute(sim_fused_kernel<0, false, 1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, FSmem<1>::bytes));
+    OVDET_CUDA_TRY(cudaFuncSetAttribute(sim_fused_kernel<4, false, 2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, FSmem<2>::bytes));
   }
   if (cg == 2) {
     // one CTA per SM, launched as clusters of two (the pair shares a TPC)
@@ -715,16 +818,19 @@ int fused_launch(const float* const* obj_embeds, const int64_t* hw, const int64_
     attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    OVDET_CUDA_TRY(cudaLaunchKernelEx(&cfg, sim_fused_kernel<8, false, 2>, maps, map_b, p));
+    if (proj) OVDET_CUDA_TRY(cudaLaunchKernelEx(&cfg, sim_fused_kernel<4, false, 2, true>, maps, bmaps, p));
+    else OVDET_CUDA_TRY(cudaLaunchKernelEx(&cfg, sim_fused_kernel<8, false, 2, false>, maps, bmaps, p));
     return OVDET_OK;
   }
   const int grid = (int)(tiles < sm_count() ? tiles : sm_count());
-  if (split3)
-    sim_fused_kernel<0, true, 1><<<grid, F_THREADS, FSmem<1>::bytes, as_stream(stream)>>>(maps, map_b, p);
+  if (proj)
+    sim_fused_kernel<0, false, 1, true><<<grid, F_THREADS, FSmem<1>::bytes, as_stream(stream)>>>(maps, bmaps, p);
+  else if (split3)
+    sim_fused_kernel<0, true, 1, false><<<grid, F_THREADS, FSmem<1>::bytes, as_stream(stream)>>>(maps, bmaps, p);
   else if (p.kb == 8)
-    sim_fused_kernel<8, false, 1><<<grid, F_THREADS, FSmem<1>::bytes, as_stream(stream)>>>(maps, map_b, p);
+    sim_fused_kernel<8, false, 1, false><<<grid, F_THREADS, FSmem<1>::bytes, as_stream(stream)>>>(maps, bmaps, p);
   else
-    sim_fused_kernel<0, false, 1><<<grid, F_THREADS, FSmem<1>::bytes, as_stream(stream)>>>(maps, map_b, p);
+    sim_fused_kernel<0, false, 1, false><<<grid, F_THREADS, FSmem<1>::bytes, as_stream(stream)>>>(maps, bmaps, p);
   OVDET_LAUNCH_CHECK();
   return OVDET_OK;
 }
@@ -739,7 +845,19 @@ extern "C" int ovdet_similarity_fused(const float* const* obj_embeds, const int6
                                       int64_t ldc, float* row_max, int32_t* row_arg,
                                       float* inv_norm, void* stream) {
   if (dim % 64 != 0) return OVDET_ERR_UNSUPPORTED_SHAPE;   // the text operand has exactly `dim` columns
-  return ovdet::fused_launch(obj_embeds, hw, stride_b, stride_d, num_levels, batch, dim, text_op, classes,
-                             text_batched, /*normalize=*/1, /*split3=*/0, alpha, beta, logits, logits_dtype,
-                             ldc, row_max, row_arg, inv_norm, stream);
+  return ovdet::fused_launch(obj_embeds, hw, stride_b, stride_d, num_levels, batch, dim, text_op, nullptr,
+                             classes, text_batched, /*normalize=*/1, /*split3=*/0, alpha, beta, logits,
+                             logits_dtype, ldc, row_max, row_arg, inv_norm, stream);
+}
+
+extern "C" int ovdet_similarity_projected(const float* const* hidden, const int64_t* hw,
+                                          const int64_t* stride_b, const int64_t* stride_d,
+                                          int num_levels, int64_t batch, int64_t hidden_dim,
+                                          const void* const* level_ops, int64_t classes, int text_batched,
+                                          float alpha, float beta, float* row_max, int32_t* row_arg,
+                                          float* inv_norm, void* stream) {
+  if (!level_ops) return OVDET_ERR_INVALID_ARG;
+  return ovdet::fused_launch(hidden, hw, stride_b, stride_d, num_levels, batch, hidden_dim, nullptr, level_ops,
+                             classes, text_batched, /*normalize=*/1, /*split3=*/0, alpha, beta, nullptr,
+                             OVDET_F32, classes, row_max, row_arg, inv_norm, stream);
 }

@@ -150,13 +150,14 @@ class Detector:
 
     # ---- predict: conv outputs -> detections (detect.py:121-125 -> detector.py:310-319) -----
     def pipeline_for(self, obj_embeds: Sequence[torch.Tensor], num_classes: int,
-                     per_image_text: bool) -> HeadPipeline:
+                     per_image_text: bool, projections=None) -> HeadPipeline:
         shapes = tuple((e.shape[2], e.shape[3]) for e in obj_embeds)
-        key = (obj_embeds[0].shape[0], shapes, num_classes, per_image_text, obj_embeds[0].device)
+        proj_key = None if projections is None else tuple(w.data_ptr() for w, _ in projections)
+        key = (obj_embeds[0].shape[0], shapes, num_classes, per_image_text, obj_embeds[0].device, proj_key)
         if key not in self._pipelines:
             self._pipelines[key] = HeadPipeline(key[0], shapes, num_classes, self.config,
                                                 device=obj_embeds[0].device,
-                                                per_image_text=per_image_text)
+                                                per_image_text=per_image_text, projections=projections)
         return self._pipelines[key]
 
     def set_vocabulary(self, text: torch.Tensor) -> None:
@@ -168,24 +169,29 @@ class Detector:
                 pipe.set_vocabulary(self._vocabulary)
 
     def predict_host(self, obj_embeds: Sequence[torch.Tensor], box_preds: Sequence[torch.Tensor],
-                     chunk: int = 32) -> Dict[str, torch.Tensor]:
+                     chunk: int = 32, projections=None) -> Dict[str, torch.Tensor]:
         """``predict`` for HOST buffers (pinned CPU tensors, as a serving front-end holds them):
         the batch is cut into chunks; chunk i+1 is copied host->device on a copy stream while
         chunk i runs K1..K4 on the compute stream, and each chunk's detections are copied back
         as soon as its NMS has finished.  Returns pinned host tensors ``boxes [B,max_det,4]``,
-        ``scores``, ``classes`` [B,max_det] and ``count`` [B]; needs ``set_vocabulary`` first."""
+        ``scores``, ``classes`` [B,max_det] and ``count`` [B]; needs ``set_vocabulary`` first.
+        With ``projections`` (per level ``(weight, bias)`` of the head's last 1x1 convolution) the
+        host buffers are the HIDDEN features and the projection is folded into the similarity:
+        half the bytes cross PCIe."""
         if self._vocabulary is None:
             raise RuntimeError("ovdet: predict_host needs set_vocabulary() first")
         batch = obj_embeds[0].shape[0]
         chunk = min(chunk, batch)
         if batch % chunk:
             raise ValueError("ovdet: batch must be a multiple of the chunk size")
-        key = (batch, chunk, tuple(tuple(e.shape[1:]) for e in obj_embeds))
+        key = (batch, chunk, tuple(tuple(e.shape[1:]) for e in obj_embeds),
+               None if projections is None else tuple(w.data_ptr() for w, _ in projections))
         st = self._host_state
         if st is None or st["key"] != key:
             dev = self.device
             shapes = tuple((e.shape[2], e.shape[3]) for e in obj_embeds)
-            pipe = HeadPipeline(chunk, shapes, self._vocabulary.shape[0], self.config, device=dev)
+            pipe = HeadPipeline(chunk, shapes, self._vocabulary.shape[0], self.config, device=dev,
+                                projections=projections)
             pipe.set_vocabulary(self._vocabulary)
             md = pipe.max_det
             st = {
@@ -232,12 +238,14 @@ class Detector:
 
     def predict(self, obj_embeds: Sequence[torch.Tensor], box_preds: Sequence[torch.Tensor],
                 text_embeddings: torch.Tensor, orig_sizes: Optional[Sequence[Tuple[int, int]]] = None,
-                scale_factors: Optional[Sequence[float]] = None) -> ops.NmsResult:
+                scale_factors: Optional[Sequence[float]] = None, projections=None) -> ops.NmsResult:
         """Per-level ``obj_embed [B,D,H,W]`` / ``box_preds [B,4R,H,W]`` (what the head
         convolutions emit) and text embeddings ``[C,D]`` or ``[B,C,D]`` -> per-image kept
-        boxes / scores / classes, every image of the batch."""
+        boxes / scores / classes, every image of the batch.  With ``projections`` (per level
+        ``(weight, bias)`` of the head's last 1x1 convolution) ``obj_embeds`` are the HIDDEN features
+        entering that convolution and it is folded into the similarity ("next" row f-2)."""
         per_image = not ops.shared_text(text_embeddings)
-        pipe = self.pipeline_for(obj_embeds, text_embeddings.shape[-2], per_image)
+        pipe = self.pipeline_for(obj_embeds, text_embeddings.shape[-2], per_image, projections)
         if orig_sizes is not None:
             pipe.set_geometry(orig_sizes, scale_factors if scale_factors is not None
                               else [1.0] * len(orig_sizes))

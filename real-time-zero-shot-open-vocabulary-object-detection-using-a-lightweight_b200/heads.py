@@ -80,6 +80,17 @@ class TextContrastiveHead(nn.Module):
         """text_contrastive.py:101-117: ``(obj_embed [B,D,H,W], box_preds [B,4R,H,W])``."""
         return self.obj_embed_conv(x), self.box_conv(x)
 
+    def forward_hidden(self, x: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
+        """``(hidden [B,hidden_dim,H,W], box_preds)``: ``forward`` without the last layer of
+        ``obj_embed_conv`` - the 1x1 projection that ``ops.similarity_projected`` folds into the
+        similarity (``projection()`` hands out its weight and bias)."""
+        return self.obj_embed_conv[1](self.obj_embed_conv[0](x)), self.box_conv(x)
+
+    def projection(self) -> Tuple[torch.Tensor, Optional[torch.Tensor]]:
+        """Weight ``[embed_dim, hidden_dim, 1, 1]`` and bias of text_contrastive.py:67."""
+        conv = self.obj_embed_conv[2]
+        return conv.weight, conv.bias
+
     def compute_similarity(self, obj_embed: torch.Tensor, text_embed: torch.Tensor) -> torch.Tensor:
         """text_contrastive.py:119-153: L2-normalise both sides, contract over D, apply
         ``cls_alpha * s + cls_beta``.  Returns logical ``[B,C,H,W]`` whose memory is ``[B,HW,C]``
@@ -160,3 +171,19 @@ def head_tail(obj_embeds: Sequence[torch.Tensor], text_embeddings: torch.Tensor,
     if return_logits:
         out["logits"] = logits
     return out
+
+
+def head_tail_projected(hidden: Sequence[torch.Tensor], projections: Sequence[Tuple[torch.Tensor, Optional[torch.Tensor]]],
+                        text_embeddings: torch.Tensor, box_preds: Sequence[torch.Tensor],
+                        strides: Sequence[int] = (8, 16, 32), cls_alpha: float = 1.0,
+                        cls_beta: float = 0.0) -> Dict[str, torch.Tensor]:
+    """``head_tail`` from the HIDDEN features of every level's ``obj_embed_conv`` (the input of its
+    last, 1x1 layer) with that layer folded into the similarity ("next" row f-2): one launch for
+    projection + normalise + similarity + class max of all levels, one decode launch.  The
+    512-wide ``obj_embeddings`` are never formed, so the dict carries only ``boxes`` / ``scores`` /
+    ``class_ids`` - what ``YOLOCLIPDetector.postprocess_detections`` consumes."""
+    classes = text_embeddings.shape[-2]
+    level_ops = [ops.project_vocabulary(text_embeddings, w, b) for w, b in projections]
+    scores, class_ids = ops.similarity_projected(hidden, level_ops, classes, cls_alpha, cls_beta)
+    boxes, _, _ = ops.decode_filter(box_preds, strides)
+    return {"boxes": boxes, "scores": scores, "class_ids": class_ids.long()}

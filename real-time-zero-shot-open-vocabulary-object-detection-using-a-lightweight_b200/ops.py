@@ -448,3 +448,97 @@ def max_sigmoid_attention(y: torch.Tensor, projected_text: torch.Tensor, precise
                                                 out.data_ptr(), out.stride(0), out.stride(1), _stream(y)),
               "ovdet_max_sigmoid_attention")
     return (out, row_max) if return_scores else out
+
+
+# --------------------------------------------------------------------------------------------
+# f-2: the head's 1x1 projection folded into the similarity ("next" row)
+# --------------------------------------------------------------------------------------------
+def project_vocabulary(text: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tensor]) -> torch.Tensor:
+    """Fold ``nn.Conv2d(hidden, embed, 1)`` (text_contrastive.py:67) into the vocabulary.
+
+    With ``E = W x + b`` (the conv) and unit-norm text rows ``t``: ``<E, t> = <x, W^T t> + <b, t>``
+    and ``||E||^2 = x'^T G' x'`` for the augmented ``x' = [x, 1]`` and
+    ``G' = [[W^T W, W^T b], [b^T W, b^T b]]``.  So the kernel multiplies the HIDDEN features
+    (K = hidden + 1 instead of embed) against one operand holding the projected classes
+    ``[W^T t_c | <b, t_c>]`` followed by the rows of ``G'``; the 512-wide embedding is never formed.
+
+    text ``[C, D]`` (or ``[B, C, D]`` per image) fp32, weight ``[D, K]`` or ``[D, K, 1, 1]``, bias
+    ``[D]`` or None.  Returns the bf16 operand ``[Bt, Cpad + kop, kop]`` with
+    ``kop = ceil(K / 64) * 64 + 16`` (class rows padded to a multiple of 128, then ``kop`` rows of
+    ``G'``; the constant 1 of ``x'`` sits at column ``ceil(K / 64) * 64``).  Built once per
+    (vocabulary, weights) with plain fp32 torch GEMMs (a one-off ``[C, D] x [D, K]`` product)."""
+    _require_cuda(text, "text", torch.float32)
+    w = weight.reshape(weight.shape[0], -1).to(torch.float32)
+    d, k = w.shape
+    b = bias.to(torch.float32) if bias is not None else torch.zeros(d, device=w.device)
+    if text.dim() == 2:
+        text = text.unsqueeze(0)
+    elif shared_text(text):
+        text = text[:1]
+    bt, classes, dt = text.shape
+    assert dt == d
+    kpad = (k + 63) // 64 * 64
+    kop = kpad + 16
+    cpad = (classes + 127) // 128 * 128
+    that = torch.nn.functional.normalize(text, p=2, dim=-1)              # text_contrastive.py:138
+    v = torch.zeros(bt, cpad + kop, kop, device=text.device, dtype=torch.float32)
+    v[:, :classes, :k] = that @ w                                         # W^T t_c
+    v[:, :classes, kpad] = that @ b                                       # <b, t_c>
+    g = v[:, cpad:, :]
+    g[:, :k, :k] = w.t() @ w
+    g[:, :k, kpad] = w.t() @ b
+    g[:, kpad, :k] = w.t() @ b
+    g[:, kpad, kpad] = b @ b
+    return v.to(torch.bfloat16).contiguous()
+
+
+def similarity_projected(hidden: Sequence[torch.Tensor], level_ops: Sequence[torch.Tensor], classes: int,
+                         alpha: float = 1.0, beta: float = 0.0, row_max: Optional[torch.Tensor] = None,
+                         row_arg: Optional[torch.Tensor] = None, inv_norm: Optional[torch.Tensor] = None,
+                         want_arg: bool = True):
+    """text_contrastive.py:112 (the 1x1 projection) + :134-147 + yolo_clip.py:198-206 for all levels in
+    one launch, from the HIDDEN features ``hidden[l] [B, K, H, W]`` and the per-level operands of
+    ``project_vocabulary``.  Returns ``(row_max [B, A], row_arg [B, A] int32 or None)``."""
+    first = hidden[0]
+    _require_cuda(first, "hidden", torch.float32)
+    if not fused_supported_strides(hidden):
+        raise ValueError("ovdet: hidden feature strides not addressable by TMA (H*W and strides must be multiples of 4)")
+    batch, k = first.shape[0], first.shape[1]
+    n = len(hidden)
+    assert len(level_ops) == n
+    anchors = sum(h.shape[2] * h.shape[3] for h in hidden)
+    kop = (k + 63) // 64 * 64 + 16
+    cpad = (classes + 127) // 128 * 128
+    bt = level_ops[0].shape[0]
+    for op in level_ops:
+        _require_cuda(op, "level_op", torch.bfloat16)
+        assert op.shape == (bt, cpad + kop, kop) and op.is_contiguous()
+    dev = first.device
+    if row_max is None:
+        row_max = torch.empty(batch, anchors, device=dev, dtype=torch.float32)
+    if want_arg and row_arg is None:
+        row_arg = torch.empty(batch, anchors, device=dev, dtype=torch.int32)
+    ptrs = (ctypes.c_void_p * n)(*[h.data_ptr() for h in hidden])
+    hw = (ctypes.c_int64 * n)(*[h.shape[2] * h.shape[3] for h in hidden])
+    sb = (ctypes.c_int64 * n)(*[h.stride(0) for h in hidden])
+    sd = (ctypes.c_int64 * n)(*[h.stride(1) for h in hidden])
+    ops_ptr = (ctypes.c_void_p * n)(*[op.data_ptr() for op in level_ops])
+    with torch.cuda.device(dev):
+        check(lib().ovdet_similarity_projected(ptrs, hw, sb, sd, n, batch, k, ops_ptr, classes,
+                                               int(bt == batch and batch > 1), float(alpha), float(beta),
+                                               _ptr(row_max), _ptr(row_arg), _ptr(inv_norm), _stream(first)),
+              "ovdet_similarity_projected")
+    return row_max, row_arg
+
+
+def fused_supported_strides(levels: Sequence[torch.Tensor]) -> bool:
+    """TMA addressability of per-level fp32 ``[B, K, H, W]`` tensors (any K)."""
+    if len(levels) > 4:
+        return False
+    for e in levels:
+        b, d, h, w = e.shape
+        if e.dtype != torch.float32 or e.stride(3) != 1 or e.stride(2) != w:
+            return False
+        if e.stride(1) % 4 or e.stride(0) % 4 or e.data_ptr() % 16 or e.stride(1) < h * w:
+            return False
+    return True

@@ -42,7 +42,12 @@ class HeadConfig:
 
 class HeadPipeline:
     def __init__(self, batch: int, level_shapes: Sequence[Tuple[int, int]], num_classes: int,
-                 config: HeadConfig = HeadConfig(), device="cuda", per_image_text: bool = False):
+                 config: HeadConfig = HeadConfig(), device="cuda", per_image_text: bool = False,
+                 projections: Optional[Sequence[Tuple[torch.Tensor, Optional[torch.Tensor]]]] = None):
+        """``projections``: per level ``(weight, bias)`` of the head's last 1x1 convolution
+        (text_contrastive.py:67).  When given, ``run`` takes the HIDDEN features of
+        ``obj_embed_conv`` instead of its output and the projection is folded into the similarity
+        (``ops.similarity_projected``, bf16 precision only)."""
         self.cfg = config
         self.batch = batch
         self.level_shapes = [tuple(s) for s in level_shapes]
@@ -51,6 +56,15 @@ class HeadPipeline:
         self.device = torch.device(device)
         self.per_image_text = per_image_text
         self.split = config.precision == "fp32"
+        self.projections = None
+        if projections is not None:
+            if self.split:
+                raise ValueError("ovdet: the projected similarity is a bf16 path")
+            self.projections = [(w.detach().to(device, torch.float32),
+                                 None if b is None else b.detach().to(device, torch.float32))
+                                for w, b in projections]
+            assert len(self.projections) == len(self.level_shapes)
+        self.level_ops = None
         d, a, dev = config.embed_dim, self.anchors, self.device
         kop = d * (2 if self.split else 1)
         self.want_fused = config.fused and not self.split and d % 64 == 0 and d <= 512
@@ -94,7 +108,10 @@ class HeadPipeline:
         """Normalise a shared ``[C, D]`` vocabulary once (the reference re-normalises it three
         times per forward, text_contrastive.py:138)."""
         assert not self.per_image_text
-        ops.l2norm_text(text, split=self.split, operand=self.text_op)
+        if self.projections is not None:
+            self.level_ops = [ops.project_vocabulary(text, w, b) for w, b in self.projections]
+        else:
+            ops.l2norm_text(text, split=self.split, operand=self.text_op)
         self._vocab_ready = True
 
     def set_geometry(self, orig_sizes: Sequence[Tuple[int, int]], scale_factors: Sequence[float]) -> None:
@@ -123,6 +140,8 @@ class HeadPipeline:
                 else:
                     events[name][1] = ev
 
+        if self.projections is not None:
+            return self._run_projected(obj_embeds, box_preds, text, mark)
         fused = self.want_fused and ops.fused_supported(obj_embeds)
         self.last_path = "fused" if fused else "split"
         mark("l2norm", True)
@@ -148,6 +167,27 @@ class HeadPipeline:
                            cfg.cls_beta, split=self.split, logits_dtype=None, logits=self.logits,
                            want_max=True, row_max=self.scores, row_arg=self.class_ids)
         mark("similarity", False)
+        return self._decode_and_nms(box_preds, mark)
+
+    def _run_projected(self, hidden, box_preds, text, mark) -> ops.NmsResult:
+        cfg = self.cfg
+        self.last_path = "projected"
+        mark("l2norm", True)
+        if self.per_image_text:
+            self.level_ops = [ops.project_vocabulary(text, w, b) for w, b in self.projections]
+        elif text is not None:
+            self.set_vocabulary(text)
+        elif not self._vocab_ready:
+            raise RuntimeError("ovdet: no vocabulary set (call set_vocabulary or pass text)")
+        mark("l2norm", False)
+        mark("similarity", True)
+        ops.similarity_projected(hidden, self.level_ops, self.num_classes, cfg.cls_alpha, cfg.cls_beta,
+                                 row_max=self.scores, row_arg=self.class_ids, inv_norm=self.inv_norm)
+        mark("similarity", False)
+        return self._decode_and_nms(box_preds, mark)
+
+    def _decode_and_nms(self, box_preds, mark) -> ops.NmsResult:
+        cfg = self.cfg
         mark("decode", True)
         ops.decode_filter(box_preds, cfg.strides, scores=self.scores, conf=cfg.conf_threshold,
                           activation=cfg.activation, boxes=self.boxes, scores_act=self.scores_act,

@@ -89,3 +89,48 @@ def make_inputs(batch: int, image_size: int = 640, num_classes: int = 1203, embe
         pred.scatter_add_(2, kstar, torch.full_like(kstar, box_boost, dtype=torch.float32))
         box_preds.append(pred.reshape(batch, 4 * bins, h, w))
     return HeadInputs(obj_embeds, box_preds, text, tuple(strides), image_size)
+
+
+@dataclass
+class ProjectedInputs:
+    hidden: List[torch.Tensor]          # per level [B, K, H, W] fp32: input of the head's last 1x1 conv
+    weights: List[torch.Tensor]         # per level [D, K, 1, 1]
+    biases: List[torch.Tensor]          # per level [D]
+    box_preds: List[torch.Tensor]
+    text: torch.Tensor
+    strides: Sequence[int]
+    image_size: int
+
+    @property
+    def batch(self) -> int:
+        return self.hidden[0].shape[0]
+
+    def text_batched(self) -> torch.Tensor:
+        return self.text.unsqueeze(0).expand(self.batch, -1, -1)
+
+    def projections(self):
+        return list(zip(self.weights, self.biases))
+
+
+def make_projected_inputs(batch: int, hidden_dim: int = 256, bias_scale: float = 0.05, **kw) -> ProjectedInputs:
+    """Inputs for the projected path ("next" row f-2): per-level 1x1 convolutions ``(W, b)`` with the
+    reference's initialisation scale (text_contrastive.py:90-99, kaiming fan_out) and HIDDEN
+    features ``x = W^+ (e - b)`` for the embeddings ``e`` of ``make_inputs``, so that ``W x + b`` is
+    the orthogonal projection of ``e`` onto the range of ``W``: the planted anchors keep cosine
+    ~0.6 to their class (> conf), the background stays ~0, and the candidate statistics match
+    the un-projected workload."""
+    base = make_inputs(batch=batch, **kw)
+    dev = base.text.device
+    d = base.text.shape[1]
+    g = torch.Generator(device=dev).manual_seed(kw.get("seed", 1234) + 99)
+    hidden, weights, biases = [], [], []
+    for e in base.obj_embeds:
+        w = torch.randn(d, hidden_dim, generator=g, device=dev) * (2.0 / d) ** 0.5
+        b = torch.randn(d, generator=g, device=dev) * bias_scale
+        pinv = torch.linalg.pinv(w)                                           # [K, D]
+        bsz, _, h, wd = e.shape
+        x = torch.matmul(pinv, e.reshape(bsz, d, h * wd) - b.view(1, d, 1))   # [B, K, HW]
+        hidden.append(x.reshape(bsz, hidden_dim, h, wd).contiguous())
+        weights.append(w.reshape(d, hidden_dim, 1, 1))
+        biases.append(b)
+    return ProjectedInputs(hidden, weights, biases, base.box_preds, base.text, base.strides, base.image_size)

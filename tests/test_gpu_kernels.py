@@ -686,3 +686,73 @@ def test_nms_properties_hypothesis(ov, cuda_device):
         assert int(again.count[0]) == len(got)
 
     check()
+
+
+# ------------------------------------------------------------------------------------------
+# f-2 ("next" row): the head's 1x1 projection folded into the similarity
+# ------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("hidden_dim,classes,batched,batch", [(256, 300, False, 2), (256, 80, True, 3),
+                                                             (64, 17, False, 1), (96, 1203, False, 2)])
+def test_similarity_projected_vs_oracle(ov, cuda_device, hidden_dim, classes, batched, batch):
+    from ovdet import ops
+    torch.manual_seed(hidden_dim + classes)
+    embed = 512 if hidden_dim == 256 else 128
+    shapes = [(20, 20), (10, 12), (4, 5)]                       # 400 | 120 | 20 anchors
+    hidden = [torch.nn.functional.silu(torch.randn(batch, hidden_dim, h, w)) for h, w in shapes]
+    hidden[1][0, :, 0, 0] = 0.0
+    ws = [torch.randn(embed, hidden_dim, 1, 1) * (2.0 / embed) ** 0.5 for _ in shapes]
+    bs = [torch.randn(embed) * 0.1 for _ in shapes]
+    text = torch.randn(batch, classes, embed) if batched else torch.randn(classes, embed)
+    tb = text if batched else text.unsqueeze(0).expand(batch, -1, -1)
+    alpha, beta = 1.3, -0.1
+    want, want_ids, embeds = ref_port.project_similarity_max(hidden, ws, bs, tb, alpha, beta)
+    dev_hidden = [h.to(cuda_device) for h in hidden]
+    level_ops = [ops.project_vocabulary(text.to(cuda_device), w.to(cuda_device), b.to(cuda_device))
+                 for w, b in zip(ws, bs)]
+    inv = torch.empty(batch, want.shape[1], device=cuda_device)
+    rmax, rarg = ops.similarity_projected(dev_hidden, level_ops, classes, alpha, beta, inv_norm=inv)
+    torch.cuda.synchronize()
+    # one bf16 pass, stated separately from the fp32 bar: |dscore| <= 8e-3 * alpha
+    assert (rmax.cpu() - want).abs().max().item() <= 8e-3 * alpha
+    flat = torch.cat([e.flatten(2).transpose(1, 2) for e in embeds], dim=1)
+    torch.testing.assert_close(inv.cpu(), 1.0 / flat.norm(dim=-1).clamp_min(1e-12), rtol=5e-3, atol=0)
+    # argmax: equal, or a near-tie within the bf16 tolerance
+    ids = rarg.cpu().long()
+    sims = torch.cat([ref_port.compute_similarity(e, tb, alpha, beta).flatten(2).transpose(1, 2) for e in embeds], dim=1)
+    picked = sims.gather(-1, ids.unsqueeze(-1)).squeeze(-1)
+    assert (want - picked).max().item() <= 1.6e-2 * alpha
+    assert (ids == want_ids).float().mean().item() >= 0.97
+    # scores only
+    m1, a1 = ops.similarity_projected(dev_hidden, level_ops, classes, alpha, beta, want_arg=False)
+    assert a1 is None and torch.equal(m1, rmax)
+
+
+def test_projected_pipeline_vs_oracle(ov, cuda_device):
+    """Detector.predict with the 1x1 projection folded in: detections equal the oracle's
+    post-processing of the pipeline's own scores, and the scores match conv + similarity + max."""
+    from ovdet import synth
+    from ovdet.detector import Detector
+    from ovdet.pipeline import HeadConfig
+    pin = synth.make_projected_inputs(batch=2, image_size=256, num_classes=90, seed=12)
+    det = Detector(device=str(cuda_device), config=HeadConfig(precision="bf16"))
+    proj = [(w.to(cuda_device), b.to(cuda_device)) for w, b in pin.projections()]
+    sizes, scales = [(256, 256), (200, 240)], [1.0, 0.8]
+    res = det.predict([h.to(cuda_device) for h in pin.hidden], [p.to(cuda_device) for p in pin.box_preds],
+                      pin.text.to(cuda_device), sizes, scales, projections=proj)
+    torch.cuda.synchronize()
+    pipe = next(iter(det._pipelines.values()))
+    assert pipe.last_path == "projected"
+    want, want_ids, _ = ref_port.project_similarity_max(pin.hidden, pin.weights, pin.biases, pin.text_batched())
+    assert (pipe.scores.cpu() - want).abs().max().item() <= 8e-3
+    strong = want > 0.25 + 1.6e-2
+    assert torch.equal(pipe.class_ids.cpu().long()[strong], want_ids[strong])
+    fed = {"boxes": pipe.boxes.cpu(), "scores": pipe.scores.cpu(), "class_ids": pipe.class_ids.cpu().long()}
+    ref = ref_port.postprocess_batch(fed, sizes, scales)
+    kept = 0
+    for i in range(2):
+        k = int(res.count[i])
+        kept += k
+        np.testing.assert_array_equal(res.keep[i, :k].cpu().numpy(), ref[i]["keep"])
+        np.testing.assert_array_equal(res.boxes[i, :k].cpu().numpy(), ref[i]["boxes"])
+        np.testing.assert_array_equal(res.classes[i, :k].cpu().numpy(), ref[i]["class_ids"])
+    assert kept > 0

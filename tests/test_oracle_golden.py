@@ -139,3 +139,16 @@ def test_tcsp_attention_restatement(golden_dir):
         y1, _ = ref_port.max_sigmoid_attention(torch.from_numpy(g["y_temp"]), torch.from_numpy(g["proj"]))
         out = layer.cv3(torch.cat((y1, layer.cv2(x)), dim=1))
     torch.testing.assert_close(out, torch.from_numpy(g["out"]), rtol=1e-5, atol=1e-5)
+
+
+def test_head_projection_restatement(golden_dir):
+    """oracle.project_similarity_max == live reference head: 1x1 conv on the hidden features,
+    compute_similarity, class max (text_contrastive.py:67,112,119-153; yolo_clip.py:198-202)."""
+    g = _load(golden_dir, "head_projection")
+    alpha, beta = (float(v) for v in g["alpha_beta"])
+    scores, ids, embeds = ref_port.project_similarity_max(
+        [torch.from_numpy(g["hidden"])], [torch.from_numpy(g["weight"])], [torch.from_numpy(g["bias"])],
+        torch.from_numpy(g["text"]), alpha, beta)
+    torch.testing.assert_close(embeds[0], torch.from_numpy(g["obj_embed"]), rtol=1e-5, atol=1e-6)
+    torch.testing.assert_close(scores, torch.from_numpy(g["scores"]), rtol=1e-5, atol=2e-6)
+    assert torch.equal(ids, torch.from_numpy(g["class_ids"]))

@@ -12,6 +12,7 @@ ap.add_argument("--iters", type=int, default=30)
 ap.add_argument("--logits", default="none")
 ap.add_argument("--split", action="store_true")
 ap.add_argument("--fused", action="store_true")
+ap.add_argument("--projected", action="store_true", help="f-2: hidden features (K = 256) in, 1x1 projection folded")
 a = ap.parse_args()
 dev = torch.device("cuda:0")
 D = 512
@@ -28,7 +29,15 @@ if a.fused:
     assert a.anchors == 8400
     embs = [torch.randn(a.batch, D, s, s, device=dev) for s in (80, 40, 20)]
     top1 = top[:, :, :D].contiguous()
+if a.projected:
+    hid = [torch.randn(a.batch, 256, s, s, device=dev) for s in (80, 40, 20)]
+    text = torch.randn(a.classes, D, device=dev)
+    lops = [ops.project_vocabulary(text, torch.randn(D, 256, device=dev) * 0.06, torch.randn(D, device=dev) * 0.1)
+            for _ in hid]
 def run():
+    if a.projected:
+        ops.similarity_projected(hid, lops, a.classes, row_max=rmax, row_arg=rarg)
+        return
     if a.fused:
         ops.similarity_fused(embs, top1, logits_dtype=None, logits=logits, want_max=True, row_max=rmax, row_arg=rarg)
         return
@@ -41,4 +50,7 @@ for _ in range(a.iters): run()
 e.record(); torch.cuda.synchronize()
 ms = s.elapsed_time(e) / a.iters
 fl = 2.0 * a.batch * a.anchors * a.classes * D * (3 if a.split else 1)
+if a.projected:
+    mma = 2.0 * a.batch * a.anchors * ((a.classes + 127) // 128 * 128 + 272) * 272
+    print(f"projected: {ms:.3f} ms; equivalent D=512 similarity rate {fl/ms/1e9:.1f} TFLOP/s; MMA work issued {mma/ms/1e9:.1f} TFLOP/s")
 print(f"gemm B={a.batch} A={a.anchors} C={a.classes} logits={a.logits} split={a.split} fused={a.fused}: {ms:.3f} ms  {fl/ms/1e9:.1f} TFLOP/s (bf16 MMA flops)")
