@@ -579,6 +579,10 @@ sim_fused_kernel(const __grid_constant__ LevelMaps amaps, const __grid_constant_
           // the MMA warp as soon as its last 32 columns are in registers - the compare work on
           // that chunk runs after the arrive, off the MMA -> epilogue -> MMA critical chain.
           auto scan = [&](const uint32_t (&r)[32], int col) {
+            if (p.dbg & 64) {                       // experiment: drain only (results are wrong)
+              raw_best = fmaxf(raw_best, __uint_as_float(r[0]));
+              return;
+            }
             if (max_only) {
               float m0 = raw_best, m1 = -INFINITY;
 #pragma unroll
