@@ -423,6 +423,9 @@ def run_ours(args):
                        "images_at_max_det": overflow},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": input_bytes,
                     "d2h_bytes_per_step": d2h_bytes, "steps": e2e_steps, "chunk_images": chunk,
+                    "h2d_GBps_achieved_per_gpu": e2e_value / n_gpus * (input_bytes / batch) / 1e9,
+                    "h2d_note": "PCIe-bound: pinned host->device copies of this box peak at 55.6 GB/s "
+                                "(Gen5 x16, tools/pcie_probe.py); copies and kernels overlap on two streams",
                     "api": "ovdet.detector.Detector.predict_host (pinned host buffers in, detections out)"},
             "gpu_launches": launches * args.steps,
             "roofline": roofline,
