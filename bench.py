@@ -218,7 +218,8 @@ def run_ours(args):
     shapes = [(IMAGE_SIZE // s, IMAGE_SIZE // s) for s in STRIDES]
     anchors = sum(h * w for h, w in shapes)
 
-    cfg = HeadConfig(precision=args.precision, max_det=MAX_DET, fused=not args.no_fused)
+    cfg = HeadConfig(precision=args.precision, max_det=MAX_DET, fused=not args.no_fused,
+                     logits_dtype=None if args.logits == "none" else args.logits)
     projections = None
     if args.projected:
         pin = synth.make_projected_inputs(batch=batch, image_size=IMAGE_SIZE, num_classes=NUM_CLASSES,
@@ -415,7 +416,7 @@ def run_ours(args):
                        "anchors": anchors, "classes": NUM_CLASSES, "embed_dim": EMBED_DIM,
                        "precision": ("bf16 operands, fp32 accumulate, fused class max/argmax" if args.precision == "bf16"
                                      else "three bf16 passes over hi/lo operand halves (|dlogit| ~ 1e-5), fp32 accumulate"),
-                       "path": pipe.last_path,
+                       "path": pipe.last_path, "materialised_logits": args.logits,
                        "conf": cfg.conf_threshold, "iou": cfg.iou_threshold, "max_det": MAX_DET,
                        "parallelism": f"batch-sharded x{n_gpus}, vocabulary replicated, no collective",
                        "l2": f"inputs are {input_bytes / 1e9:.2f} GB per step per GPU (> 126 MB L2), no flush needed",
@@ -464,6 +465,9 @@ def main():
     ap.add_argument("--projected", action="store_true",
                     help="SURVEY 8f-2: start the step at the hidden features and fold the head's 1x1 projection "
                          "into the similarity (both arms)")
+    ap.add_argument("--logits", default="none", choices=["none", "bf16", "fp32"],
+                    help="also materialise the [B, A, C] logits (the reference's compute_similarity output); "
+                         "default: class max/argmax fused in the GEMM epilogue only")
     ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"],
                     help="bf16 = the metric's configuration; fp32 = three-pass hi/lo recipe (BASELINE configs[1])")
     ap.add_argument("--image-size", type=int, default=IMAGE_SIZE,

@@ -472,6 +472,9 @@ sim_fused_kernel(const __grid_constant__ LevelMaps amaps, const __grid_constant_
       // (the attention row): one FMNMX3 per two values.  With argmax: compare + select + index
       // per value, no FFMA; the class returned is the argmax of the fp32 accumulators (lowest
       // index among equal accumulators).
+      // logits rows start 16-byte aligned when the leading dimension is padded to 16 bytes
+      const bool vec_logits = p.logits != nullptr && ((uintptr_t)p.logits & 15) == 0 &&
+                              (p.ldc * (p.logits_bf16 ? 2 : 4)) % 16 == 0;
       const bool raw_mode = PROJ || (want_max && p.logits == nullptr && p.alpha >= 0.f && !(p.dbg & 2));
       const bool max_only = raw_mode && p.row_arg == nullptr;
       float raw_best = -INFINITY;
@@ -552,7 +555,29 @@ sim_fused_kernel(const __grid_constant__ LevelMaps amaps, const __grid_constant_
               }
             }
           }
-          if (p.logits != nullptr) {
+          if (p.logits != nullptr && vec_logits) {
+            // 16-byte aligned rows (padded leading dimension): every thread writes its own row's 32
+            // columns straight from registers with 16-byte stores - no staging, 4 (bf16) or 8 (fp32)
+            // store instructions per chunk instead of 32.  Columns in [classes, ldc) are padding.
+            if (row_ok) {
+              const int col0 = n0 + c0;
+              if (p.logits_bf16) {
+                uint4* dst = reinterpret_cast<uint4*>(static_cast<__nv_bfloat16*>(p.logits) + grow * p.ldc + col0);
+#pragma unroll
+                for (int v = 0; v < 4; ++v)
+                  if (col0 + 8 * v < (int)p.ldc)
+                    dst[v] = make_uint4(pack_bf16x2(__uint_as_float(r[8 * v + 0]), __uint_as_float(r[8 * v + 1])),
+                                        pack_bf16x2(__uint_as_float(r[8 * v + 2]), __uint_as_float(r[8 * v + 3])),
+                                        pack_bf16x2(__uint_as_float(r[8 * v + 4]), __uint_as_float(r[8 * v + 5])),
+                                        pack_bf16x2(__uint_as_float(r[8 * v + 6]), __uint_as_float(r[8 * v + 7])));
+              } else {
+                uint4* dst = reinterpret_cast<uint4*>(static_cast<float*>(p.logits) + grow * p.ldc + col0);
+#pragma unroll
+                for (int v = 0; v < 8; ++v)
+                  if (col0 + 4 * v < (int)p.ldc) dst[v] = make_uint4(r[4 * v], r[4 * v + 1], r[4 * v + 2], r[4 * v + 3]);
+              }
+            }
+          } else if (p.logits != nullptr) {
 #pragma unroll
             for (int j = 0; j < 32; ++j) stage[lane * F_PITCH + j] = __uint_as_float(r[j]);
             __syncwarp();
@@ -560,14 +585,19 @@ sim_fused_kernel(const __grid_constant__ LevelMaps amaps, const __grid_constant_
             const bool col_ok = lane < valid;
             const int rows_here = min(32, tc.rows - lg * 32);
             const long long out_row0 = tc.out_row0 + lg * 32;
+            // rows are written one per instruction (32 lanes = 32 consecutive classes); fully
+            // unrolled with warp-uniform predicates so that the 32 shared-memory reads and stores
+            // are independent and pipeline (the rolled loop left the epilogue issue-bound: 5.4 ms)
             if (p.logits_bf16) {
-              __nv_bfloat16* out = static_cast<__nv_bfloat16*>(p.logits);
-              for (int i = 0; i < rows_here; ++i)
-                if (col_ok) out[(out_row0 + i) * p.ldc + col] = __float2bfloat16_rn(stage[i * F_PITCH + lane]);
+              __nv_bfloat16* out = static_cast<__nv_bfloat16*>(p.logits) + out_row0 * p.ldc + col;
+#pragma unroll
+              for (int i = 0; i < 32; ++i)
+                if (i < rows_here && col_ok) out[(long long)i * p.ldc] = __float2bfloat16_rn(stage[i * F_PITCH + lane]);
             } else {
-              float* out = static_cast<float*>(p.logits);
-              for (int i = 0; i < rows_here; ++i)
-                if (col_ok) out[(out_row0 + i) * p.ldc + col] = stage[i * F_PITCH + lane];
+              float* out = static_cast<float*>(p.logits) + out_row0 * p.ldc + col;
+#pragma unroll
+              for (int i = 0; i < 32; ++i)
+                if (i < rows_here && col_ok) out[(long long)i * p.ldc] = stage[i * F_PITCH + lane];
             }
             __syncwarp();
           }

@@ -78,7 +78,11 @@ class HeadPipeline:
         self.logits = None
         if config.logits_dtype is not None:
             dt = {"bf16": torch.bfloat16, "fp32": torch.float32}[config.logits_dtype]
-            self.logits = torch.empty(batch, a, num_classes, device=dev, dtype=dt)
+            # rows padded to 16 bytes so that the kernel can use 16-byte stores; `logits` is the
+            # [B, A, C] view of the padded buffer (same shape as the reference's, wider row pitch)
+            per16 = 16 // torch.empty(0, dtype=dt).element_size()
+            ldc = (num_classes + per16 - 1) // per16 * per16
+            self.logits = torch.empty(batch, a, ldc, device=dev, dtype=dt)[..., :num_classes]
         self.boxes = torch.empty(batch, a, 4, device=dev, dtype=torch.float32)
         self.scores_act = (torch.empty(batch, a, device=dev, dtype=torch.float32)
                            if config.activation == "sigmoid" else None)

@@ -94,3 +94,33 @@ def test_module_state_dict_keys_match_reference_layout():
     grid = box._create_grid(2, 3, 4, 8, torch.device("cpu"))
     assert grid.shape == (2, 3, 4, 3) and grid.dtype == torch.int64
     assert grid[0, 1, 2].tolist() == [2, 1, 8]
+
+
+def test_new_entries_validate_arguments(handle):
+    """Argument checks of the later entry points run before the device check (CPU-testable)."""
+    assert handle.ovdet_letterbox_u8(None, None, None, None, None, None, 1, 640, 640, None, None) == -1
+    assert handle.ovdet_pack_boxes_i32(None, None, 1, 1, None, None) == -1
+    assert handle.ovdet_cast_text(None, 1, 1, 64, 1, 1, None, 64, 0, None) == -1
+    assert handle.ovdet_max_sigmoid_attention(None, 1, 64, 16, 1, 1, None, 1, 0, 0, None, None, 1, 1, None) == -1
+    assert handle.ovdet_similarity_projected(None, None, None, None, 1, 1, 256, None, 80, 0, 1.0, 0.0,
+                                             None, None, None, None) == -1
+    assert handle.ovdet_similarity_fused(None, None, None, None, 1, 1, 512, None, 80, 0, 1.0, 0.0, None, 0,
+                                         80, None, None, None, None) == -1
+
+
+def test_bench_reference_arm_contract():
+    """`bench.py --impl reference` (the CPU arm the driver runs) prints one JSON line with the
+    contract's keys; it is the one place outside tests/ that may execute oracle/."""
+    import json
+    import subprocess
+    import sys
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1",
+                          "--warmup", "1"], capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0, out.stderr[-2000:]
+    line = json.loads(out.stdout.strip().splitlines()[-1])
+    for key in ("impl", "metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better",
+                "scaling", "vs_baseline", "dtype", "data", "config", "cpu_baseline", "e2e", "gpu_launches"):
+        assert key in line, key
+    assert line["impl"] == "reference" and line["value"] > 0 and line["gpu_launches"] == 0
+    assert line["e2e"]["h2d_bytes_per_step"] == 0 and line["cpu_baseline"]["kind"] == "port"
+    assert "workload" in line["config"]

@@ -436,6 +436,14 @@ def test_similarity_fused_vs_oracle(ov, cuda_device, classes, batched, dim):
     # max-only launch gives the same answer
     _, m0, a0 = ops.similarity_fused(dev_embs, top, alpha, beta, logits_dtype=None, want_max=True)
     assert torch.equal(m0, rmax) and torch.equal(a0, rarg)
+    # padded leading dimension (16-byte rows): the 16-byte-store epilogue writes the same values
+    for dt, per16 in ((torch.float32, 4), (torch.bfloat16, 8)):
+        ldc = (classes + per16 - 1) // per16 * per16
+        buf = torch.full((b, ref.shape[1], ldc), float("nan"), device=cuda_device, dtype=dt)
+        lp, mp, ap = ops.similarity_fused(dev_embs, top, alpha, beta, logits=buf[..., :classes], want_max=True)
+        torch.cuda.synchronize()
+        assert lp.data_ptr() == buf.data_ptr() and torch.equal(mp, rmax) and torch.equal(ap, rarg)
+        assert torch.equal(lp.float(), logits.to(dt).float())
     # scores only (no argmax): the raw-accumulator fast path gives bit-identical maxima
     _, m1, a1 = ops.similarity_fused(dev_embs, top, alpha, beta, logits_dtype=None, want_max=True, want_arg=False)
     assert a1 is None and torch.equal(m1, rmax)
