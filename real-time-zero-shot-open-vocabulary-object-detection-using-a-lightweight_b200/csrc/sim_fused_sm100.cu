@@ -56,7 +56,8 @@ constexpr int F_THREADS = 384;
 constexpr int F_TMEM_COLS = 512;
 constexpr int F_ACC_COL = 0;
 constexpr int F_A_COL = 256;
-constexpr int F_PITCH = 33;
+constexpr int F_PITCH = 33;                       // staging pitch (floats) of the scalar logit stores
+constexpr int F_VPITCH = 36;                      // staging pitch of the 16-byte logit stores (144-byte rows)
 constexpr int F_MAX_LEVELS = 4;
 
 // CG = CTAs per MMA (tcgen05 cta_group): 1 = one CTA per 128-anchor tile; 2 = a CTA PAIR on one
@@ -75,7 +76,7 @@ struct FSmem {
   static constexpr int b_off = 0;
   static constexpr int a_off = b_off + b_stages * b_stage_bytes;                     // 64 KiB
   static constexpr int epi_off = a_off + F_A_STAGES * F_A_STAGE_BYTES;               // +128 KiB
-  static constexpr int epi_bytes = 4 * 32 * F_PITCH * 4;
+  static constexpr int epi_bytes = 4 * 32 * F_VPITCH * 4;
   static constexpr int norm_off = epi_off + epi_bytes;
   static constexpr int norm_bytes = 3 * F_BLOCK_M * 4;
   static constexpr int bar_off = norm_off + norm_bytes;
@@ -450,7 +451,7 @@ sim_fused_kernel(const __grid_constant__ LevelMaps amaps, const __grid_constant_
   } else if (warp >= 8) {
     // ================================ epilogue ===============================================
     const int lg = warp & 3;
-    float* stage = epi_stage + lg * 32 * F_PITCH;
+    float* stage = epi_stage + lg * 32 * F_VPITCH;
     const bool want_max = p.row_max != nullptr;
     uint32_t acc_it = 0, lt = 0;
     for (int pair = pair0; pair < total_pairs; pair += pair_stride, ++lt) {
@@ -555,28 +556,47 @@ sim_fused_kernel(const __grid_constant__ LevelMaps amaps, const __grid_constant_
               }
             }
           }
-          if (p.logits != nullptr && vec_logits) {
-            // 16-byte aligned rows (padded leading dimension): every thread writes its own row's 32
-            // columns straight from registers with 16-byte stores - no staging, 4 (bf16) or 8 (fp32)
-            // store instructions per chunk instead of 32.  Columns in [classes, ldc) are padding.
+          if (p.logits != nullptr && vec_logits && p.logits_bf16) {
+            // 16-byte aligned rows (padded leading dimension), bf16: every thread writes its own
+            // row's 32 classes (64 bytes) straight from registers with four 16-byte stores; measured
+            // faster than turning the block through shared memory (3.15 vs 3.48 ms at batch 256).
             if (row_ok) {
               const int col0 = n0 + c0;
-              if (p.logits_bf16) {
-                uint4* dst = reinterpret_cast<uint4*>(static_cast<__nv_bfloat16*>(p.logits) + grow * p.ldc + col0);
+              uint4* dst = reinterpret_cast<uint4*>(static_cast<__nv_bfloat16*>(p.logits) + grow * p.ldc + col0);
 #pragma unroll
-                for (int v = 0; v < 4; ++v)
-                  if (col0 + 8 * v < (int)p.ldc)
-                    dst[v] = make_uint4(pack_bf16x2(__uint_as_float(r[8 * v + 0]), __uint_as_float(r[8 * v + 1])),
-                                        pack_bf16x2(__uint_as_float(r[8 * v + 2]), __uint_as_float(r[8 * v + 3])),
-                                        pack_bf16x2(__uint_as_float(r[8 * v + 4]), __uint_as_float(r[8 * v + 5])),
-                                        pack_bf16x2(__uint_as_float(r[8 * v + 6]), __uint_as_float(r[8 * v + 7])));
-              } else {
-                uint4* dst = reinterpret_cast<uint4*>(static_cast<float*>(p.logits) + grow * p.ldc + col0);
+              for (int v = 0; v < 4; ++v)
+                if (col0 + 8 * v < (int)p.ldc)
+                  dst[v] = make_uint4(pack_bf16x2(__uint_as_float(r[8 * v + 0]), __uint_as_float(r[8 * v + 1])),
+                                      pack_bf16x2(__uint_as_float(r[8 * v + 2]), __uint_as_float(r[8 * v + 3])),
+                                      pack_bf16x2(__uint_as_float(r[8 * v + 4]), __uint_as_float(r[8 * v + 5])),
+                                      pack_bf16x2(__uint_as_float(r[8 * v + 6]), __uint_as_float(r[8 * v + 7])));
+            }
+          } else if (p.logits != nullptr && vec_logits) {
+            // fp32: the warp's 32 x 32 block is turned through shared memory (144-byte pitch: the
+            // 128-bit writes by row and the 128-bit reads by quarter-row are both bank-conflict free)
+            // so that one store instruction writes 4 rows x 128 contiguous bytes instead of 32 rows
+            // x 4 bytes (2.72 -> 1.96 ms at batch 128).  Columns in [classes, ldc) are padding.
+            float4* srow = reinterpret_cast<float4*>(stage + lane * F_VPITCH);
 #pragma unroll
-                for (int v = 0; v < 8; ++v)
-                  if (col0 + 4 * v < (int)p.ldc) dst[v] = make_uint4(r[4 * v], r[4 * v + 1], r[4 * v + 2], r[4 * v + 3]);
+            for (int q4 = 0; q4 < 8; ++q4)
+              srow[q4] = make_float4(__uint_as_float(r[4 * q4]), __uint_as_float(r[4 * q4 + 1]),
+                                     __uint_as_float(r[4 * q4 + 2]), __uint_as_float(r[4 * q4 + 3]));
+            __syncwarp();
+            const int col0 = n0 + c0;
+            const int rows_here = min(32, tc.rows - lg * 32);
+            const long long out_row0 = tc.out_row0 + lg * 32;
+            {
+              float* out = static_cast<float*>(p.logits);
+              const int c4 = (lane & 7) * 4;                             // 8 lanes x 4 classes per row
+#pragma unroll
+              for (int i = 0; i < 8; ++i) {
+                const int row = 4 * i + (lane >> 3);
+                const float4 a = *reinterpret_cast<const float4*>(stage + row * F_VPITCH + c4);
+                if (row < rows_here && col0 + c4 < (int)p.ldc)
+                  *reinterpret_cast<float4*>(out + (out_row0 + row) * p.ldc + col0 + c4) = a;
               }
             }
+            __syncwarp();
           } else if (p.logits != nullptr) {
 #pragma unroll
             for (int j = 0; j < 32; ++j) stage[lane * F_PITCH + j] = __uint_as_float(r[j]);
@@ -585,19 +605,17 @@ sim_fused_kernel(const __grid_constant__ LevelMaps amaps, const __grid_constant_
             const bool col_ok = lane < valid;
             const int rows_here = min(32, tc.rows - lg * 32);
             const long long out_row0 = tc.out_row0 + lg * 32;
-            // rows are written one per instruction (32 lanes = 32 consecutive classes); fully
-            // unrolled with warp-uniform predicates so that the 32 shared-memory reads and stores
-            // are independent and pipeline (the rolled loop left the epilogue issue-bound: 5.4 ms)
+            // unaligned rows (odd class count, exact reference strides): one row per instruction, 32
+            // lanes = 32 consecutive classes, 2- or 4-byte stores.  Slow (5.4 ms at batch 256, bf16):
+            // callers that can pad the leading dimension to 16 bytes get the paths above.
             if (p.logits_bf16) {
-              __nv_bfloat16* out = static_cast<__nv_bfloat16*>(p.logits) + out_row0 * p.ldc + col;
-#pragma unroll
-              for (int i = 0; i < 32; ++i)
-                if (i < rows_here && col_ok) out[(long long)i * p.ldc] = __float2bfloat16_rn(stage[i * F_PITCH + lane]);
+              __nv_bfloat16* out = static_cast<__nv_bfloat16*>(p.logits);
+              for (int i = 0; i < rows_here; ++i)
+                if (col_ok) out[(out_row0 + i) * p.ldc + col] = __float2bfloat16_rn(stage[i * F_PITCH + lane]);
             } else {
-              float* out = static_cast<float*>(p.logits) + out_row0 * p.ldc + col;
-#pragma unroll
-              for (int i = 0; i < 32; ++i)
-                if (i < rows_here && col_ok) out[(long long)i * p.ldc] = stage[i * F_PITCH + lane];
+              float* out = static_cast<float*>(p.logits);
+              for (int i = 0; i < rows_here; ++i)
+                if (col_ok) out[(out_row0 + i) * p.ldc + col] = stage[i * F_PITCH + lane];
             }
             __syncwarp();
           }
