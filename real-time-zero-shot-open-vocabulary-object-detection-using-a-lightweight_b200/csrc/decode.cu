@@ -211,6 +211,7 @@ extern "C" int ovdet_decode_filter(const float* const* box_preds, const int32_t*
   if (pass_mask && !scores) return OVDET_ERR_INVALID_ARG;
   if (boxes && ((uintptr_t)boxes & 15)) return OVDET_ERR_INVALID_ARG;
   if (int rc = check_device()) return rc;
+  if (batch == 0) return OVDET_OK;                  // an empty batch is a no-op (its pointers may be null)
   DecodeParams p{};
   long long total = 0;
   for (int l = 0; l < num_levels; ++l) {

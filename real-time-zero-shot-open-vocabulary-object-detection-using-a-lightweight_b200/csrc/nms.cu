@@ -487,6 +487,7 @@ extern "C" int ovdet_nms_batched(const float* boxes, const float* scores, const 
                                  int32_t* out_keep, int32_t* out_count, int32_t* out_candidates,
                                  void* workspace, size_t workspace_bytes, void* stream) {
   using namespace ovdet;
+  if (batch == 0) return check_device();            // an empty batch is a no-op (its pointers may be null)
   if (!boxes || !scores || !out_boxes || !out_count || batch < 0 || anchors < 0 || max_det <= 0 || topk < 0)
     return OVDET_ERR_INVALID_ARG;
   if (class_aware && !classes) return OVDET_ERR_INVALID_ARG;

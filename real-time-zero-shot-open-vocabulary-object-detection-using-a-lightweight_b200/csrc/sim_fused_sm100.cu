@@ -752,6 +752,7 @@ int fused_launch(const float* const* obj_embeds, const int64_t* hw, const int64_
                  int normalize, int split3, float alpha, float beta, void* logits, int logits_dtype,
                  int64_t ldc, float* row_max, int32_t* row_arg, float* inv_norm, void* stream) {
   const int proj = level_ops != nullptr;
+  if (batch == 0) return check_device();            // an empty batch is a no-op (its pointers may be null)
   if (!obj_embeds || !hw || !stride_b || !stride_d || (!text_op && !proj) || batch < 0 || classes <= 0 || dim <= 0)
     return OVDET_ERR_INVALID_ARG;
   if (num_levels <= 0) return OVDET_ERR_INVALID_ARG;
@@ -763,6 +764,7 @@ int fused_launch(const float* const* obj_embeds, const int64_t* hw, const int64_
   const int kb_in = (int)ceil_div<int64_t>(dim, F_BLOCK_K);
   const int kb = proj ? kb_in + 1 : kb_in * (split3 ? 3 : 1);
   if (num_levels > F_MAX_LEVELS || kb > F_MAX_KB || batch > 65535) return OVDET_ERR_UNSUPPORTED_SHAPE;
+
   if (!proj && ((uintptr_t)text_op & 15)) return OVDET_ERR_INVALID_ARG;
   // CTA pairs (cta_group::2) for the dim = 512 similarity and the hidden = 256 projected one;
   // OVDET_FUSED_CG=1 forces single CTAs

@@ -764,3 +764,38 @@ def test_projected_pipeline_vs_oracle(ov, cuda_device):
         np.testing.assert_array_equal(res.boxes[i, :k].cpu().numpy(), ref[i]["boxes"])
         np.testing.assert_array_equal(res.classes[i, :k].cpu().numpy(), ref[i]["class_ids"])
     assert kept > 0
+
+
+def test_edge_shapes_empty_and_huge(ov, cuda_device):
+    """Empty batch through every stage (a no-op, not an error); more anchors than the resident NMS
+    path addresses (> 65536: workspace path with a sparse pass mask); an image with no survivor."""
+    from ovdet import ops
+    from ovdet.detector import _pack_mask
+    dev = cuda_device
+    # ---- empty batch
+    e = [torch.empty(0, 512, 8, 8, device=dev)]
+    top = ops.l2norm_text(torch.randn(5, 512, device=dev))
+    _, m, a = ops.similarity_fused(e, top, want_max=True)
+    assert m.shape == (0, 64) and a.shape == (0, 64)
+    boxes, _, mask = ops.decode_filter([torch.empty(0, 68, 8, 8, device=dev)], (8,), scores=m, conf=0.25)
+    assert boxes.shape == (0, 64, 4)
+    res = ops.nms_batched(boxes, m, max_det=8)
+    torch.cuda.synchronize()
+    assert res.count.numel() == 0
+    # ---- 70 000 anchors, 300 candidates + one image with none
+    rng = np.random.default_rng(5)
+    n = 70_000
+    bx = torch.from_numpy(np.stack([_rand_boxes(rng, n, 3000, 120) for _ in range(2)])).to(dev)
+    sc = torch.from_numpy(np.stack([rng.permutation(np.linspace(0.0, 1.0, n)).astype(np.float32) for _ in range(2)])).to(dev)
+    passed = sc > (1.0 - 300.5 / n)
+    passed[1] = False
+    res = ops.nms_batched(bx, sc, pass_mask=_pack_mask(passed), iou_thr=0.45)
+    torch.cuda.synchronize()
+    n_pass = int(passed[0].sum())
+    assert 290 <= n_pass <= 310
+    assert int(res.candidates[0]) == n_pass and int(res.candidates[1]) == 0 and int(res.count[1]) == 0
+    idx = torch.nonzero(passed[0]).flatten().cpu().numpy()
+    want = ref_port.nms(bx[0].cpu().numpy()[idx], sc[0].cpu().numpy()[idx], 0.45)
+    k = int(res.count[0])
+    np.testing.assert_array_equal(res.keep[0, :k].cpu().numpy(), np.asarray(want))
+    np.testing.assert_array_equal(res.anchor[0, :k].cpu().numpy(), idx[np.asarray(want)])
