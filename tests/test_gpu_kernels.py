@@ -623,9 +623,9 @@ def test_graph_replay_equals_eager(ov, cuda_device):
     the CURRENT contents of the captured input tensors."""
     from ovdet import synth
     from ovdet.pipeline import HeadConfig, HeadPipeline
-    shapes = [(20, 20), (10, 10), (5, 5)]
-    a = synth.make_inputs(batch=2, image_size=160, num_classes=90, seed=31, device=cuda_device)
-    b = synth.make_inputs(batch=2, image_size=160, num_classes=90, seed=32, device=cuda_device)
+    shapes = [(32, 32), (16, 16), (8, 8)]            # TMA-addressable: the fused CTA-pair kernel is captured
+    a = synth.make_inputs(batch=2, image_size=256, num_classes=90, seed=31, device=cuda_device)
+    b = synth.make_inputs(batch=2, image_size=256, num_classes=90, seed=32, device=cuda_device)
     pipe = HeadPipeline(2, shapes, 90, HeadConfig(precision="bf16", max_det=64), device=cuda_device)
     pipe.set_vocabulary(a.text)
 
@@ -639,6 +639,7 @@ def test_graph_replay_equals_eager(ov, cuda_device):
     bufs_e = [t.clone() for t in a.obj_embeds]
     bufs_p = [t.clone() for t in a.box_preds]
     pipe.capture(bufs_e, bufs_p)
+    assert pipe.last_path == "fused"
     def same(got, want):                      # rows past count[b] are not written by a step
         assert torch.equal(got[0], want[0])
         for i in range(2):
