@@ -221,6 +221,19 @@ OVDET_API int ovdet_nms_batched(const float* boxes, const float* scores, const i
                       int32_t* out_candidates, void* workspace, size_t workspace_bytes,
                       void* stream);
 
+/* K4 with the confidence threshold inside: candidates are the anchors with scores > conf (strict,
+ * NaN never passes - inference/detector.py:184), evaluated by the kernel itself instead of read
+ * from a pass mask.  The box decode then no longer depends on the scores and can run beside the
+ * similarity kernel (HeadPipeline's captured graph forks it).  Same outputs as ovdet_nms_batched;
+ * anchors <= 65536, else OVDET_ERR_UNSUPPORTED_SHAPE. */
+OVDET_API int ovdet_nms_batched_conf(const float* boxes, const float* scores, const int32_t* classes,
+                                     float conf, int64_t batch, int64_t anchors, const float* scale,
+                                     const float* clip_wh, float iou_thr, int class_aware, int topk,
+                                     int64_t max_det, float* out_boxes, float* out_scores,
+                                     int32_t* out_classes, int32_t* out_anchor, int32_t* out_keep,
+                                     int32_t* out_count, int32_t* out_candidates, void* workspace,
+                                     size_t workspace_bytes, void* stream);
+
 /* ------------------------------------------------------------------------------------------
  * P1  letterbox pre-processing ("next" row f-4 of SURVEY.md section 8).
  * Replaces: inference/detector.py:139-156 - cv2.resize(image, (resized_w, resized_h)) with the

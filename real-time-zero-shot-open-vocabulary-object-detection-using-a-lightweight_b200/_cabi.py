@@ -48,6 +48,10 @@ PROTOTYPES = {
                                   c_void_p, c_void_p, c_float, c_int, c_int, c_int64,
                                   c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                                   c_void_p, c_void_p, c_size_t, c_void_p]),
+    "ovdet_nms_batched_conf": (c_int, [c_void_p, c_void_p, c_void_p, c_float, c_int64, c_int64,
+                                       c_void_p, c_void_p, c_float, c_int, c_int, c_int64,
+                                       c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+                                       c_void_p, c_void_p, c_size_t, c_void_p]),
     "ovdet_letterbox_u8": (c_int, [POINTER(c_void_p), POINTER(c_int32), POINTER(c_int32),
                                    POINTER(c_int64), POINTER(c_int32), POINTER(c_int32), c_int,
                                    c_int, c_int, c_void_p, c_void_p]),

@@ -35,7 +35,7 @@ constexpr int SORT_CAP = 4096;                 // keys per shared-memory sort bl
 constexpr int CHUNK = 512;                     // candidates per NMS chunk
 constexpr int CHUNK_WORDS = CHUNK / 32;        // 16
 constexpr int FAST_WORDS = 2048;               // resident path: pass-mask words per image (anchors <= 65536)
-constexpr int NMS_SMEM_BYTES = SORT_CAP * 8 + CHUNK * 16 + 4 * CHUNK * 4 + NMS_THREADS * 4 + FAST_WORDS * 4;
+constexpr int NMS_SMEM_BYTES = SORT_CAP * 8 + CHUNK * 16 + 4 * CHUNK * 4 + NMS_THREADS * 4 + 2 * FAST_WORDS * 4;
 static_assert(CHUNK * CHUNK_WORDS * 4 <= SORT_CAP * 8, "mask must fit in the sort block");
 static_assert(CHUNK == NMS_THREADS, "one thread per chunk candidate");
 
@@ -44,6 +44,8 @@ struct NmsParams {
   const float* scores;
   const int* classes;
   const uint32_t* pass_mask;
+  int use_conf;                                // 1: candidates = scores > conf (computed here, no pass mask)
+  float conf;
   int anchors;
   int words;
   const float* scale;
@@ -162,6 +164,7 @@ nms_batched_kernel(const NmsParams p) {
   int* s_kept_pos = s_anchor + CHUNK;           // positions (inside the chunk) kept by this chunk
   int* s_scan = s_kept_pos + CHUNK;             // NMS_THREADS entries
   int* s_prefix = s_scan + NMS_THREADS;         // FAST_WORDS entries (resident path)
+  uint32_t* s_mask = reinterpret_cast<uint32_t*>(s_prefix + FAST_WORDS);   // FAST_WORDS entries (use_conf)
   __shared__ uint32_t s_removed[CHUNK_WORDS];
   __shared__ int s_count, s_kept_total, s_kept_chunk, s_carry;
 
@@ -185,7 +188,21 @@ nms_batched_kernel(const NmsParams p) {
   __syncthreads();
 
   const uint32_t tail_bits = (A & 31) ? ((1u << (A & 31)) - 1u) : 0xffffffffu;
+  // use_conf: the confidence threshold of detector.py:184 evaluated here (strict >, NaN never
+  // passes), coalesced over the scores, one ballot per 32 anchors into shared memory - so that the
+  // box decode does not have to wait for the scores (it runs beside the similarity kernel)
+  const bool own_mask = p.use_conf && W <= FAST_WORDS;
+  if (own_mask) {
+    for (int a0 = 0; a0 < W * 32; a0 += NMS_THREADS) {
+      const int a = a0 + tid;
+      const bool pass = a < A && scores[a] > p.conf;
+      const uint32_t bits = __ballot_sync(0xffffffffu, pass);
+      if (lane == 0 && (a >> 5) < W) s_mask[a >> 5] = bits;
+    }
+    __syncthreads();
+  }
   auto mask_word = [&](int w) -> uint32_t {
+    if (own_mask) return s_mask[w];
     uint32_t bits = pm ? pm[w] : 0xffffffffu;
     if (w == W - 1) bits &= tail_bits;
     return bits;
@@ -479,7 +496,7 @@ extern "C" size_t ovdet_nms_workspace_bytes(int64_t batch, int64_t anchors) {
   return (size_t)batch * L.total;
 }
 
-extern "C" int ovdet_nms_batched(const float* boxes, const float* scores, const int32_t* classes,
+static int nms_launch(int use_conf, float conf, const float* boxes, const float* scores, const int32_t* classes,
                                  const uint32_t* pass_mask, int64_t batch, int64_t anchors,
                                  const float* scale, const float* clip_wh, float iou_thr,
                                  int class_aware, int topk, int64_t max_det, float* out_boxes,
@@ -504,6 +521,8 @@ extern "C" int ovdet_nms_batched(const float* boxes, const float* scores, const 
   if (!workspace || workspace_bytes < need || ((uintptr_t)workspace & 15)) return OVDET_ERR_WORKSPACE;
   NmsParams p{};
   p.boxes = boxes; p.scores = scores; p.classes = classes; p.pass_mask = pass_mask;
+  p.use_conf = use_conf; p.conf = conf;
+  if (use_conf && (pass_mask || (anchors + 31) / 32 > ovdet::FAST_WORDS)) return OVDET_ERR_UNSUPPORTED_SHAPE;
   p.anchors = (int)anchors; p.words = (int)((anchors + 31) / 32);
   p.scale = scale; p.clip_wh = clip_wh; p.iou_thr = iou_thr;
   p.class_aware = class_aware; p.topk = topk; p.max_det = (int)max_det;
@@ -519,4 +538,28 @@ extern "C" int ovdet_nms_batched(const float* boxes, const float* scores, const 
   nms_batched_kernel<<<(unsigned)batch, NMS_THREADS, NMS_SMEM_BYTES, as_stream(stream)>>>(p);
   OVDET_LAUNCH_CHECK();
   return OVDET_OK;
+}
+
+extern "C" int ovdet_nms_batched(const float* boxes, const float* scores, const int32_t* classes,
+                                 const uint32_t* pass_mask, int64_t batch, int64_t anchors,
+                                 const float* scale, const float* clip_wh, float iou_thr,
+                                 int class_aware, int topk, int64_t max_det, float* out_boxes,
+                                 float* out_scores, int32_t* out_classes, int32_t* out_anchor,
+                                 int32_t* out_keep, int32_t* out_count, int32_t* out_candidates,
+                                 void* workspace, size_t workspace_bytes, void* stream) {
+  return nms_launch(0, 0.f, boxes, scores, classes, pass_mask, batch, anchors, scale, clip_wh, iou_thr,
+                    class_aware, topk, max_det, out_boxes, out_scores, out_classes, out_anchor, out_keep,
+                    out_count, out_candidates, workspace, workspace_bytes, stream);
+}
+
+extern "C" int ovdet_nms_batched_conf(const float* boxes, const float* scores, const int32_t* classes,
+                                      float conf, int64_t batch, int64_t anchors, const float* scale,
+                                      const float* clip_wh, float iou_thr, int class_aware, int topk,
+                                      int64_t max_det, float* out_boxes, float* out_scores,
+                                      int32_t* out_classes, int32_t* out_anchor, int32_t* out_keep,
+                                      int32_t* out_count, int32_t* out_candidates, void* workspace,
+                                      size_t workspace_bytes, void* stream) {
+  return nms_launch(1, conf, boxes, scores, classes, nullptr, batch, anchors, scale, clip_wh, iou_thr,
+                    class_aware, topk, max_det, out_boxes, out_scores, out_classes, out_anchor, out_keep,
+                    out_count, out_candidates, workspace, workspace_bytes, stream);
 }

@@ -300,12 +300,14 @@ def nms_batched(boxes: torch.Tensor, scores: torch.Tensor, classes: Optional[tor
                 pass_mask: Optional[torch.Tensor] = None, scale: Optional[torch.Tensor] = None,
                 clip_wh: Optional[torch.Tensor] = None, iou_thr: float = 0.45,
                 class_aware: bool = False, topk: int = 0, max_det: Optional[int] = None,
-                out: Optional[NmsResult] = None, workspace: Optional[torch.Tensor] = None) -> NmsResult:
+                out: Optional[NmsResult] = None, workspace: Optional[torch.Tensor] = None,
+                conf: Optional[float] = None) -> NmsResult:
     """detector.py:185-208 + _nms :225-256 + _compute_iou :258-287, for every image.
 
     boxes ``[B, A, 4]`` fp32, scores ``[B, A]`` fp32, classes ``[B, A]`` int32 (optional),
     pass_mask ``[B, ceil(A/32)]`` int32 bit mask (optional: all anchors), scale ``[B]`` fp32,
-    clip_wh ``[B, 2]`` fp32 (w, h).  Result rows are in kept order (score desc).
+    clip_wh ``[B, 2]`` fp32 (w, h).  Result rows are in kept order (score desc).  ``conf`` (instead
+    of ``pass_mask``): the kernel thresholds ``scores > conf`` itself (detector.py:184).
     """
     _require_cuda(boxes, "boxes", torch.float32)
     _require_cuda(scores, "scores", torch.float32)
@@ -329,6 +331,19 @@ def nms_batched(boxes: torch.Tensor, scores: torch.Tensor, classes: Optional[tor
     need = nms_workspace_bytes(batch, anchors)
     if workspace is None:
         workspace = torch.empty(max(need, 16), device=dev, dtype=torch.uint8)
+    if conf is not None:
+        if pass_mask is not None:
+            raise ValueError("ovdet: give either pass_mask or conf")
+        with torch.cuda.device(dev):
+            check(lib().ovdet_nms_batched_conf(boxes.data_ptr(), scores.data_ptr(), _ptr(classes), float(conf),
+                                               batch, anchors, _ptr(scale), _ptr(clip_wh), float(iou_thr),
+                                               int(class_aware), int(topk), int(max_det),
+                                               out.boxes.data_ptr(), out.scores.data_ptr(),
+                                               out.classes.data_ptr(), out.anchor.data_ptr(),
+                                               out.keep.data_ptr(), out.count.data_ptr(),
+                                               out.candidates.data_ptr(), workspace.data_ptr(),
+                                               workspace.numel(), _stream(boxes)), "ovdet_nms_batched_conf")
+        return out
     with torch.cuda.device(dev):
         check(lib().ovdet_nms_batched(boxes.data_ptr(), scores.data_ptr(), _ptr(classes),
                                       _ptr(pass_mask), batch, anchors, _ptr(scale), _ptr(clip_wh),

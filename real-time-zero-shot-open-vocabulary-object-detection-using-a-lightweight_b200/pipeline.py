@@ -104,6 +104,9 @@ class HeadPipeline:
         self.use_geometry = False
         self._vocab_ready = False
         self.last_path = None              # "fused" | "split": what the previous run() launched
+        self._parallel_decode = False      # set by capture(): decode forked beside the similarity kernel
+        self._side = None
+        self._fork = None
         self.launches_per_step = ((3 if self.want_fused else len(self.level_shapes) + 3)
                                   + (1 if per_image_text else 0))
 
@@ -144,6 +147,17 @@ class HeadPipeline:
                 else:
                     events[name][1] = ev
 
+        self._fork = None
+        if self._parallel_decode:
+            # fork: decode needs nothing from the similarity kernel once K4 owns the threshold
+            main = torch.cuda.current_stream(self.device)
+            start = torch.cuda.Event()
+            start.record(main)
+            with torch.cuda.stream(self._side):
+                self._side.wait_event(start)
+                ops.decode_filter(box_preds, cfg.strides, boxes=self.boxes)
+                self._fork = torch.cuda.Event()
+                self._fork.record(self._side)
         if self.projections is not None:
             return self._run_projected(obj_embeds, box_preds, text, mark)
         fused = self.want_fused and ops.fused_supported(obj_embeds)
@@ -192,6 +206,18 @@ class HeadPipeline:
 
     def _decode_and_nms(self, box_preds, mark) -> ops.NmsResult:
         cfg = self.cfg
+        fork = getattr(self, "_fork", None)
+        if fork is not None:
+            # latency path (captured graph): the boxes were decoded on the side stream beside the
+            # similarity kernel; K4 evaluates the confidence threshold itself
+            main = torch.cuda.current_stream(self.device)
+            main.wait_event(fork)
+            return ops.nms_batched(self.boxes, self.scores, self.class_ids, None,
+                                   scale=self.scale if self.use_geometry else None,
+                                   clip_wh=self.clip_wh if self.use_geometry else None,
+                                   iou_thr=cfg.iou_threshold, class_aware=cfg.class_aware,
+                                   topk=cfg.topk, max_det=self.max_det, out=self.result,
+                                   workspace=self.workspace, conf=cfg.conf_threshold)
         mark("decode", True)
         ops.decode_filter(box_preds, cfg.strides, scores=self.scores, conf=cfg.conf_threshold,
                           activation=cfg.activation, boxes=self.boxes, scores_act=self.scores_act,
@@ -210,13 +236,21 @@ class HeadPipeline:
 
     # -- CUDA-graph replay (latency path) -----------------------------------------------------
     def capture(self, obj_embeds: Sequence[torch.Tensor], box_preds: Sequence[torch.Tensor],
-                text: Optional[torch.Tensor] = None) -> None:
+                text: Optional[torch.Tensor] = None, parallel_decode: bool = False) -> None:
         """Capture one step (its 3-5 launches) into a CUDA graph bound to THESE input tensors:
         every ``replay()`` reads their storage again, so a serving loop writes the next image's
         conv outputs into the same tensors and replays.  Every intermediate and output buffer is
         owned by the pipeline, so the captured addresses stay valid.  At batch 1 the step is
         launch-bound from Python (host time per call > GPU time); the replay halves its p50."""
         self._graph_inputs = (list(obj_embeds), list(box_preds), text)      # keep the storage alive
+        # parallel_decode: the decode kernel runs on a second graph branch, concurrently with the
+        # similarity kernel (at batch 1 that kernel occupies 68 of the 148 SMs), and K4 applies the
+        # confidence threshold itself (ovdet_nms_batched_conf).  Measured: no gain (batch-1 p50
+        # 0.054 vs 0.053 ms - the fork/join costs what the overlap saves), so it is off by default.
+        # Only without a score activation and for pyramids K4's resident path addresses.
+        self._parallel_decode = (parallel_decode and self.cfg.activation == "none" and self.anchors <= 65536)
+        if self._parallel_decode and self._side is None:
+            self._side = torch.cuda.Stream(self.device)
         stream = torch.cuda.Stream(self.device)
         stream.wait_stream(torch.cuda.current_stream(self.device))
         with torch.cuda.stream(stream):
@@ -227,6 +261,7 @@ class HeadPipeline:
                 self.run(obj_embeds, box_preds, text)
         torch.cuda.current_stream(self.device).wait_stream(stream)
         self._graph = graph
+        self._parallel_decode = False       # eager run() keeps the sequential launch order
 
     def replay(self) -> ops.NmsResult:
         """Re-run the captured step on the current contents of the captured input tensors."""

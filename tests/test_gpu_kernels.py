@@ -651,6 +651,9 @@ def test_graph_replay_equals_eager(ov, cuda_device):
     for dst, src in zip(bufs_e + bufs_p, b.obj_embeds + b.box_preds):
         dst.copy_(src)
     same(snapshot(pipe.replay()), want_b)
+    # the forked variant (decode beside the similarity kernel, threshold inside K4) gives the same lists
+    pipe.capture(bufs_e, bufs_p, parallel_decode=True)
+    same(snapshot(pipe.replay()), want_b)
 
 
 # ------------------------------------------------------------------------------------------
@@ -833,3 +836,27 @@ def test_bench_size_fused_equals_two_kernel_path(ov, cuda_device):
             agree += 1
     assert agree >= 250          # a threshold-straddling score may flip a candidate in a few images
     assert int(rf.count.sum()) > 30_000
+
+
+def test_nms_conf_equals_pass_mask(ov, cuda_device):
+    """K4 thresholding the scores itself == K4 fed with the packed `scores > conf` mask (NaN and
+    the exact-threshold value never pass); resident, multi-chunk and top-k / class-aware paths."""
+    from ovdet import ops
+    from ovdet.detector import _pack_mask
+    rng = np.random.default_rng(11)
+    b, a = 3, 8400
+    boxes = torch.from_numpy(np.stack([_rand_boxes(rng, a, 640, 120) for _ in range(b)])).to(cuda_device)
+    scores = torch.from_numpy(rng.uniform(-0.2, 1.0, (b, a)).astype(np.float32)).to(cuda_device)
+    scores[0, 7] = float("nan")
+    scores[0, 9] = 0.25
+    scores[2] = 0.1                                               # no survivor
+    classes = torch.from_numpy(rng.integers(0, 5, (b, a)).astype(np.int32)).to(cuda_device)
+    for conf, kw in ((0.25, {}), (0.9, {}), (0.25, {"topk": 300}), (0.5, {"class_aware": True})):
+        want = ops.nms_batched(boxes, scores, classes, _pack_mask(scores > conf), iou_thr=0.45, **kw)
+        got = ops.nms_batched(boxes, scores, classes, conf=conf, iou_thr=0.45, **kw)
+        torch.cuda.synchronize()
+        assert torch.equal(got.count, want.count) and torch.equal(got.candidates, want.candidates)
+        for i in range(b):
+            k = int(want.count[i])
+            for f in ("boxes", "scores", "classes", "anchor", "keep"):
+                assert torch.equal(getattr(got, f)[i, :k], getattr(want, f)[i, :k]), (conf, kw, f)
