@@ -373,10 +373,12 @@ def run_ours(args):
         flops = 2.0 * batch * anchors * NUM_CLASSES * EMBED_DIM * (3 if args.precision == "fp32" else 1)
         achieved = flops / (stages["similarity"] * 1e-3) / 1e12
         proj = pipe.last_path == "projected"
-        fused = pipe.last_path == "fused"
+        fused = pipe.last_path in ("fused", "fused_fp32")
         launches = (3 if (fused or proj) else len(shapes) + 3)
         kernel = ("sim_fused_kernel, projected mode (1x1 projection folded: hidden fp32 NCHW in, quadratic-form "
                   "norm, tcgen05 GEMM K = 272, class max/argmax)" if proj else
+                  "sim_fused_kernel, streaming three-pass mode (fp32-accurate, <= 128 classes)"
+                  if pipe.last_path == "fused_fp32" else
                   "sim_fused_kernel (K1+K2: fp32 NCHW in, L2 norm, tcgen05 GEMM, class max/argmax)" if fused
                   else "sim_gemm_kernel (K2)")
         if proj:

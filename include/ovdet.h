@@ -135,6 +135,22 @@ OVDET_API int ovdet_similarity_fused(const float* const* obj_embeds, const int64
                                      int64_t ldc, float* row_max, int32_t* row_arg,
                                      float* inv_norm, void* stream);
 
+/* K1+K2 fused, fp32-accurate: the same kernel with the three-pass recipe (x = hi + lo in bf16,
+ * hi*hi + hi*lo + lo*hi accumulated in fp32, |dlogit| ~ 1e-5) for vocabularies of at most 128
+ * classes (BASELINE configs[1]: 80 COCO prompts): with a single N tile every converted activation
+ * block is consumed once, so the blocks STREAM through an 8-slot ring of tensor memory and dim = 512
+ * fits.  Larger vocabularies: ovdet_l2norm_regions(split = 1) + ovdet_similarity(split = 1).
+ *   text_op3   bf16 [text_batch, classes, 3 * dim]: unit-norm rows laid out [hi | lo | hi]
+ *   other arguments as ovdet_similarity_fused; dim % 64 == 0, dim <= 512, classes <= 128
+ *   (dim <= 128: any class count). */
+OVDET_API int ovdet_similarity_fused_fp32(const float* const* obj_embeds, const int64_t* hw,
+                                          const int64_t* stride_b, const int64_t* stride_d,
+                                          int num_levels, int64_t batch, int64_t dim,
+                                          const void* text_op3, int64_t classes, int text_batched,
+                                          float alpha, float beta, void* logits, int logits_dtype,
+                                          int64_t ldc, float* row_max, int32_t* row_arg,
+                                          float* inv_norm, void* stream);
+
 /* K1+K2 projected ("next" row f-2)  the head's last layer - nn.Conv2d(hidden_dim, embed_dim, 1),
  * model/heads/text_contrastive.py:67 applied at :112 - folded into the similarity: the kernel
  * reads the HIDDEN features and never forms the embed_dim-wide embedding.

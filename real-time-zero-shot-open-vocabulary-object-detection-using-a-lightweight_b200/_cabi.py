@@ -34,6 +34,10 @@ PROTOTYPES = {
                                        POINTER(c_int64), c_int, c_int64, c_int64, c_void_p, c_int64,
                                        c_int, c_float, c_float, c_void_p, c_int, c_int64,
                                        c_void_p, c_void_p, c_void_p, c_void_p]),
+    "ovdet_similarity_fused_fp32": (c_int, [POINTER(c_void_p), POINTER(c_int64), POINTER(c_int64),
+                                            POINTER(c_int64), c_int, c_int64, c_int64, c_void_p, c_int64,
+                                            c_int, c_float, c_float, c_void_p, c_int, c_int64,
+                                            c_void_p, c_void_p, c_void_p, c_void_p]),
     "ovdet_similarity_projected": (c_int, [POINTER(c_void_p), POINTER(c_int64), POINTER(c_int64),
                                            POINTER(c_int64), c_int, c_int64, c_int64, POINTER(c_void_p),
                                            c_int64, c_int, c_float, c_float, c_void_p, c_void_p, c_void_p,

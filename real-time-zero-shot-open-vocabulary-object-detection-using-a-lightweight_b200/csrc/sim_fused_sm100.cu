@@ -143,7 +143,8 @@ __device__ __forceinline__ TileCoord decode_tile(const FusedParams& p, int tile)
 }
 
 // KB_T  8: dim == 512, every k-block loop unrolled; 0: run-time block count.
-// SPLIT3 (dim <= 128): fp32-accurate product from three bf16 passes.  x = hi + lo with
+// SPLIT3: fp32-accurate product from three bf16 passes (resident for dim <= 128 - the attention
+// row -, streaming through an 8-slot ring of the A region for dim <= 512 and classes <= 128).  x = hi + lo with
 // hi = bf16(x), lo = bf16(x - hi); the activation blocks are written to tensor memory as
 // [hi | hi | lo] and the text operand is laid out [hi | lo | hi] (ovdet_cast_text), so the plain
 // block loop accumulates hi*hi + hi*lo + lo*hi (the lo*lo term is < 2^-16 relative).
@@ -228,6 +229,16 @@ sim_fused_kernel(const __grid_constant__ LevelMaps amaps, const __grid_constant_
   const int KB_IN = KB_T ? KB_T : p.kb_in;                       // fp32 input blocks per anchor tile
   const int KB = PROJ ? KB_IN + 1 : (KB_T ? KB_T : p.kb);        // k blocks the MMA walks
   const int KB_A = PROJ ? KB_IN : KB;                            // A blocks rewritten per anchor tile
+  // The A region is a ring of R slots of 32 columns.  Resident modes: R = KB_A, block i lives in
+  // slot i for the whole anchor tile.  Streaming (SPLIT3 with more than 8 blocks, one N tile only):
+  // R = 8 and block i of tile lt takes slot (lt * KB_A + i) % 8 - every block is consumed exactly
+  // once, so its slot is handed back as soon as its MMAs retire.
+  const int R = (SPLIT3 && KB_A > F_MAX_KB) ? F_MAX_KB : KB_A;
+  auto a_slot = [&](uint32_t lt_, int i) { return (int)((lt_ * (uint32_t)KB_A + (uint32_t)i) % (uint32_t)R); };
+  auto a_phase = [&](uint32_t lt_, int i) { return ((lt_ * (uint32_t)KB_A + (uint32_t)i) / (uint32_t)R) & 1u; };
+  // SPLIT3 visits the blocks input-block-major: i = 3 * j + part, parts (hi, hi, lo) against the
+  // text segments (hi, lo, hi) of the operand layout [hi | lo | hi]
+  auto b_kblock = [&](int i) { return SPLIT3 ? (i % 3) * KB_IN + i / 3 : i; };
   const int NSTAGE = (KB + KPS - 1) / KPS;                       // text stages per N tile
   const int NT = p.n_tiles;
   const int NG = PROJ ? p.ng_tiles : 0;
@@ -263,7 +274,7 @@ sim_fused_kernel(const __grid_constant__ LevelMaps amaps, const __grid_constant_
           if constexpr (CG == 1) {
             ptx::mbar_arrive_expect_tx_if(issue, b_full0 + 8u * s, F_B_STAGE_BYTES);
             ptx::tma_load_3d_if(issue, smem_b + s * F_B_STAGE_BYTES, bmap, b_full0 + 8u * s,
-                                sb * F_BLOCK_K, row0, tb);
+                                b_kblock(sb) * F_BLOCK_K, row0, tb);
           } else {
             // this CTA's half of the N tile (rows [rank * n/2, (rank + 1) * n/2) of it) lands in its
             // own shared memory; both halves complete on the LEADER's barrier, which expects both
@@ -302,7 +313,8 @@ sim_fused_kernel(const __grid_constant__ LevelMaps amaps, const __grid_constant_
           if (first_nt) {                                                // A blocks converted (both CTAs)?
 #pragma unroll
             for (int j = 0; j < KPS; ++j)
-              if (sb * KPS + j < KB_A) ptx::mbar_wait(a_ready0 + 8u * (sb * KPS + j), lt & 1u);
+              if (sb * KPS + j < KB_A)
+                ptx::mbar_wait(a_ready0 + 8u * a_slot(lt, sb * KPS + j), a_phase(lt, sb * KPS + j));
           }
           ptx::mbar_wait_if_not(ready, b_full0 + 8u * s, ph);
           ptx::tc_fence_after();
@@ -314,7 +326,7 @@ sim_fused_kernel(const __grid_constant__ LevelMaps amaps, const __grid_constant_
               const int kb = sb * KPS + j;
               if (kb < KB) {
                 const uint64_t b_desc = ptx::umma_desc_k_sw128(smem_b_u + s * F_B_STAGE_BYTES + j * F_B_SUB_BYTES);
-                const uint32_t a_tmem = tmem_u + (uint32_t)(F_A_COL + kb * 32);
+                const uint32_t a_tmem = tmem_u + (uint32_t)(F_A_COL + (kb < KB_A ? a_slot(lt, kb) : kb) * 32);
                 // projected: the last block is the 16-wide constant block of x' = [x, 1]
                 const int ksteps = (PROJ && kb == KB - 1) ? 1 : F_BLOCK_K / 16;
 #pragma unroll
@@ -327,7 +339,7 @@ sim_fused_kernel(const __grid_constant__ LevelMaps amaps, const __grid_constant_
             if (last_nt) {                                               // these A blocks may be overwritten
 #pragma unroll
               for (int j = 0; j < KPS; ++j)
-                if (sb * KPS + j < KB_A) ptx::umma_commit_cg<CG>(a_free0 + 8u * (sb * KPS + j));
+                if (sb * KPS + j < KB_A) ptx::umma_commit_cg<CG>(a_free0 + 8u * a_slot(lt, sb * KPS + j));
             }
           }
           __syncwarp();
@@ -398,8 +410,9 @@ sim_fused_kernel(const __grid_constant__ LevelMaps amaps, const __grid_constant_
       const TileCoord tc = decode_tile(p, tile);
       float ss0 = 0.f, ss1 = 0.f, ss2 = 0.f, ss3 = 0.f;
       // block `t` of the A region: wait until the previous tile's MMAs have read it, store, publish
-      auto publish = [&](int t, const uint32_t (&regs)[32]) {
-        ptx::mbar_wait_lazy(a_free0 + 8u * t, (lt & 1u) ^ 1u, lazy_ns >> 1);
+      auto publish = [&](int i, const uint32_t (&regs)[32]) {
+        const int t = a_slot(lt, i);
+        ptx::mbar_wait_lazy(a_free0 + 8u * t, a_phase(lt, i) ^ 1u, lazy_ns >> 1);
         ptx::tc_fence_after();
         ptx::tmem_st_32x32(tmem_base + ((uint32_t)(lg * 32) << 16) + (uint32_t)(F_A_COL + t * 32), regs);
         ptx::tmem_st_wait();
@@ -435,10 +448,12 @@ sim_fused_kernel(const __grid_constant__ LevelMaps amaps, const __grid_constant_
         }
         __syncwarp();
         if (lane == 0) ptx::mbar_arrive(as_empty0 + 8u * s);   // staging slot may be refilled
-        publish(kb, packed);
         if constexpr (SPLIT3) {
-          publish(KB_IN + kb, packed);
-          publish(2 * KB_IN + kb, packed_lo);
+          publish(3 * kb, packed);
+          publish(3 * kb + 1, packed);
+          publish(3 * kb + 2, packed_lo);
+        } else {
+          publish(kb, packed);
         }
       }
       const float inv = 1.0f / fmaxf(sqrtf((ss0 + ss1) + (ss2 + ss3)), 1e-12f);
@@ -763,7 +778,10 @@ int fused_launch(const float* const* obj_embeds, const int64_t* hw, const int64_
   if (proj && (logits || split3 || alpha < 0.f || !row_max)) return OVDET_ERR_INVALID_ARG;
   const int kb_in = (int)ceil_div<int64_t>(dim, F_BLOCK_K);
   const int kb = proj ? kb_in + 1 : kb_in * (split3 ? 3 : 1);
-  if (num_levels > F_MAX_LEVELS || kb > F_MAX_KB || batch > 65535) return OVDET_ERR_UNSUPPORTED_SHAPE;
+  // more than 8 k blocks only in the streaming three-pass mode: one N tile (classes <= 128), dim <= 512
+  const bool streaming = split3 && kb > F_MAX_KB && kb <= 3 * F_MAX_KB && classes <= F_BLOCK_N;
+  if (num_levels > F_MAX_LEVELS || (kb > F_MAX_KB && !streaming) || batch > 65535)
+    return OVDET_ERR_UNSUPPORTED_SHAPE;
 
   if (!proj && ((uintptr_t)text_op & 15)) return OVDET_ERR_INVALID_ARG;
   // CTA pairs (cta_group::2) for the dim = 512 similarity and the hidden = 256 projected one;
@@ -901,6 +919,19 @@ extern "C" int ovdet_similarity_fused(const float* const* obj_embeds, const int6
   if (dim % 64 != 0) return OVDET_ERR_UNSUPPORTED_SHAPE;   // the text operand has exactly `dim` columns
   return ovdet::fused_launch(obj_embeds, hw, stride_b, stride_d, num_levels, batch, dim, text_op, nullptr,
                              classes, text_batched, /*normalize=*/1, /*split3=*/0, alpha, beta, logits,
+                             logits_dtype, ldc, row_max, row_arg, inv_norm, stream);
+}
+
+extern "C" int ovdet_similarity_fused_fp32(const float* const* obj_embeds, const int64_t* hw,
+                                           const int64_t* stride_b, const int64_t* stride_d,
+                                           int num_levels, int64_t batch, int64_t dim,
+                                           const void* text_op3, int64_t classes, int text_batched,
+                                           float alpha, float beta, void* logits, int logits_dtype,
+                                           int64_t ldc, float* row_max, int32_t* row_arg,
+                                           float* inv_norm, void* stream) {
+  if (dim % 64 != 0) return OVDET_ERR_UNSUPPORTED_SHAPE;
+  return ovdet::fused_launch(obj_embeds, hw, stride_b, stride_d, num_levels, batch, dim, text_op3, nullptr,
+                             classes, text_batched, /*normalize=*/1, /*split3=*/1, alpha, beta, logits,
                              logits_dtype, ldc, row_max, row_arg, inv_norm, stream);
 }
 

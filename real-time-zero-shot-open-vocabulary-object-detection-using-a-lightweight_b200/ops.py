@@ -156,11 +156,25 @@ def fused_supported(obj_embeds: Sequence[torch.Tensor]) -> bool:
     return True
 
 
+def text_operand_fp32(text: torch.Tensor) -> torch.Tensor:
+    """Unit-norm text rows as the ``[hi | lo | hi]`` bf16 operand of ``similarity_fused(fp32=True)``
+    (built from the K1b kernel's ``[hi | lo]`` output; once per vocabulary)."""
+    op = l2norm_text(text, split=True)
+    dim = op.shape[-1] // 2
+    return torch.cat([op, op[..., :dim]], dim=-1).contiguous()
+
+
+def fused_fp32_supported(obj_embeds: Sequence[torch.Tensor], classes: int) -> bool:
+    """Shapes of the fused fp32-accurate kernel: TMA-addressable levels and a single class tile
+    (or an embedding of at most 128 values)."""
+    return fused_supported(obj_embeds) and (classes <= 128 or obj_embeds[0].shape[1] <= 128)
+
+
 def similarity_fused(obj_embeds: Sequence[torch.Tensor], text_op: torch.Tensor, alpha: float = 1.0,
                      beta: float = 0.0, logits_dtype: Optional[torch.dtype] = None,
                      want_max: bool = True, logits: Optional[torch.Tensor] = None,
                      row_max: Optional[torch.Tensor] = None, row_arg: Optional[torch.Tensor] = None,
-                     inv_norm: Optional[torch.Tensor] = None, want_arg: bool = True):
+                     inv_norm: Optional[torch.Tensor] = None, want_arg: bool = True, fp32: bool = False):
     """text_contrastive.py:134-147 for all levels + yolo_clip.py:198-206 in one launch, reading
     the fp32 NCHW ``obj_embeds`` directly.  ``text_op`` comes from ``l2norm_text(split=False)``.
     Returns ``(logits [B, A, C] or None, row_max, row_arg)``; ``want_arg=False`` skips the
@@ -175,7 +189,9 @@ def similarity_fused(obj_embeds: Sequence[torch.Tensor], text_op: torch.Tensor, 
     n = len(obj_embeds)
     anchors = sum(e.shape[2] * e.shape[3] for e in obj_embeds)
     bt, classes, kop = text_op.shape
-    assert kop == dim and bt in (1, batch)
+    assert kop == dim * (3 if fp32 else 1) and bt in (1, batch)
+    if fp32 and not fused_fp32_supported(obj_embeds, classes):
+        raise ValueError("ovdet: the fused fp32-accurate kernel takes at most 128 classes (or dim <= 128)")
     dev = first.device
     if logits is None and logits_dtype is not None:
         logits = torch.empty(batch, anchors, classes, device=dev, dtype=logits_dtype)
@@ -193,12 +209,13 @@ def similarity_fused(obj_embeds: Sequence[torch.Tensor], text_op: torch.Tensor, 
     hw = (ctypes.c_int64 * n)(*[e.shape[2] * e.shape[3] for e in obj_embeds])
     sb = (ctypes.c_int64 * n)(*[e.stride(0) for e in obj_embeds])
     sd = (ctypes.c_int64 * n)(*[e.stride(1) for e in obj_embeds])
+    entry = lib().ovdet_similarity_fused_fp32 if fp32 else lib().ovdet_similarity_fused
     with torch.cuda.device(dev):
-        check(lib().ovdet_similarity_fused(ptrs, hw, sb, sd, n, batch, dim, text_op.data_ptr(),
-                                           classes, int(bt == batch and batch > 1), float(alpha),
-                                           float(beta), _ptr(logits), ldt, ldc, _ptr(row_max),
-                                           _ptr(row_arg), _ptr(inv_norm), _stream(first)),
-              "ovdet_similarity_fused")
+        check(entry(ptrs, hw, sb, sd, n, batch, dim, text_op.data_ptr(),
+                    classes, int(bt == batch and batch > 1), float(alpha),
+                    float(beta), _ptr(logits), ldt, ldc, _ptr(row_max),
+                    _ptr(row_arg), _ptr(inv_norm), _stream(first)),
+              "ovdet_similarity_fused_fp32" if fp32 else "ovdet_similarity_fused")
     return logits, row_max, row_arg
 
 

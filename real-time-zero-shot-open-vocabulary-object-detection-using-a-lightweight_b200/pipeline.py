@@ -68,6 +68,10 @@ class HeadPipeline:
         d, a, dev = config.embed_dim, self.anchors, self.device
         kop = d * (2 if self.split else 1)
         self.want_fused = config.fused and not self.split and d % 64 == 0 and d <= 512
+        # fp32 precision with a single class tile: the fused kernel's streaming three-pass mode
+        self.want_fused_fp32 = (config.fused and self.split and d % 64 == 0 and d <= 512 and
+                                (num_classes <= 128 or d <= 128))
+        self.text_op3 = None
         self._kop = kop
         self.regions_op = None             # bf16 operand of the two-kernel path, allocated on first use
         self.inv_norm = torch.empty(batch, a, device=dev, dtype=torch.float32)
@@ -119,6 +123,8 @@ class HeadPipeline:
             self.level_ops = [ops.project_vocabulary(text, w, b) for w, b in self.projections]
         else:
             ops.l2norm_text(text, split=self.split, operand=self.text_op)
+            if self.want_fused_fp32:
+                self.text_op3 = torch.cat([self.text_op, self.text_op[..., :self.cfg.embed_dim]], dim=-1).contiguous()
         self._vocab_ready = True
 
     def set_geometry(self, orig_sizes: Sequence[Tuple[int, int]], scale_factors: Sequence[float]) -> None:
@@ -161,22 +167,29 @@ class HeadPipeline:
         if self.projections is not None:
             return self._run_projected(obj_embeds, box_preds, text, mark)
         fused = self.want_fused and ops.fused_supported(obj_embeds)
-        self.last_path = "fused" if fused else "split"
+        fused32 = self.want_fused_fp32 and ops.fused_supported(obj_embeds)
+        self.last_path = "fused" if fused else ("fused_fp32" if fused32 else "split")
         mark("l2norm", True)
-        if not fused:
+        if not fused and not fused32:
             if self.regions_op is None:
                 self.regions_op = torch.empty(self.batch, self.anchors, self._kop, device=self.device,
                                               dtype=torch.bfloat16)
             ops.l2norm_regions(obj_embeds, split=self.split, operand=self.regions_op, inv_norm=self.inv_norm)
         if self.per_image_text:
             ops.l2norm_text(text, split=self.split, operand=self.text_op)
+            if fused32:
+                self.text_op3 = torch.cat([self.text_op, self.text_op[..., :cfg.embed_dim]], dim=-1).contiguous()
         elif text is not None:
             self.set_vocabulary(text)
         elif not self._vocab_ready:
             raise RuntimeError("ovdet: no vocabulary set (call set_vocabulary or pass text)")
         mark("l2norm", False)
         mark("similarity", True)
-        if fused:
+        if fused32:
+            ops.similarity_fused(obj_embeds, self.text_op3, cfg.cls_alpha, cfg.cls_beta, logits_dtype=None,
+                                 logits=self.logits, want_max=True, row_max=self.scores,
+                                 row_arg=self.class_ids, inv_norm=self.inv_norm, fp32=True)
+        elif fused:
             ops.similarity_fused(obj_embeds, self.text_op, cfg.cls_alpha, cfg.cls_beta, logits_dtype=None,
                                  logits=self.logits, want_max=True, row_max=self.scores,
                                  row_arg=self.class_ids, inv_norm=self.inv_norm)

@@ -860,3 +860,32 @@ def test_nms_conf_equals_pass_mask(ov, cuda_device):
             k = int(want.count[i])
             for f in ("boxes", "scores", "classes", "anchor", "keep"):
                 assert torch.equal(getattr(got, f)[i, :k], getattr(want, f)[i, :k]), (conf, kw, f)
+
+
+@pytest.mark.parametrize("classes,batched,dim", [(80, False, 512), (128, True, 512), (17, False, 256), (5, True, 64)])
+def test_similarity_fused_fp32_streaming(ov, cuda_device, classes, batched, dim):
+    """The fused kernel's fp32-accurate mode for small vocabularies (BASELINE configs[1]: 80
+    prompts): activation blocks stream through the 8-slot TMEM ring, three bf16 passes."""
+    from ovdet import ops
+    torch.manual_seed(classes + dim)
+    b = 3
+    shapes = [(20, 20), (10, 12), (4, 5)]
+    embs = [torch.randn(b, dim, h, w) * (0.5 + l) for l, (h, w) in enumerate(shapes)]
+    embs[2][1, :, 1, 1] = 0.0
+    text = torch.randn(b, classes, dim) if batched else torch.randn(classes, dim).unsqueeze(0).expand(b, -1, -1)
+    alpha, beta = 1.7, -0.2
+    ref = torch.cat([ref_port.compute_similarity(e, text, alpha, beta).flatten(2).transpose(1, 2)
+                     for e in embs], dim=1)
+    dev_embs = [e.to(cuda_device) for e in embs]
+    top3 = ops.text_operand_fp32(text.to(cuda_device) if batched else text[0].to(cuda_device))
+    assert top3.shape[-1] == 3 * dim
+    logits, rmax, rarg = ops.similarity_fused(dev_embs, top3, alpha, beta, logits_dtype=torch.float32,
+                                              want_max=True, fp32=True)
+    torch.cuda.synchronize()
+    assert_logits_close(logits, ref, "fp32", alpha)            # the fp32 bar: 1e-3 relative (measured ~1e-5)
+    assert (logits.cpu() - ref).abs().max().item() <= 3e-5 * alpha
+    m, a = logits.max(dim=-1)
+    assert torch.equal(rmax, m) and torch.equal(rarg.long(), a)
+    _, m0, a0 = ops.similarity_fused(dev_embs, top3, alpha, beta, logits_dtype=None, want_max=True, fp32=True)
+    assert torch.equal(m0, rmax)
+    assert (a0 == rarg).float().mean().item() >= 0.999
