@@ -98,7 +98,15 @@ class TextContrastiveHead(nn.Module):
         b, d, h, w = obj_embed.shape
         c = text_embed.shape[-2]
         split = self.precision == "fp32"
-        regions_op, inv_norm = ops.l2norm_regions([obj_embed.float()], split=split)
+        level = [obj_embed.float()]
+        # one fused launch (L2 norm + similarity, fp32 NCHW read in place) when the shape allows:
+        # bf16 always, fp32-accurate for a single class tile; else K1 -> K2
+        if d % 64 == 0 and d <= 512 and (ops.fused_fp32_supported(level, c) if split else ops.fused_supported(level)):
+            text_op = ops.text_operand_fp32(text_embed.float()) if split else ops.l2norm_text(text_embed.float())
+            logits, _, _ = ops.similarity_fused(level, text_op, self.cls_alpha, self.cls_beta,
+                                                logits_dtype=torch.float32, want_max=False, fp32=split)
+            return logits.transpose(1, 2).reshape(b, c, h, w)
+        regions_op, inv_norm = ops.l2norm_regions(level, split=split)
         text_op = ops.l2norm_text(text_embed.float(), split=split)
         logits, _, _ = ops.similarity(regions_op, text_op, inv_norm, d, self.cls_alpha,
                                       self.cls_beta, split=split, logits_dtype=torch.float32)
