@@ -26,6 +26,7 @@ import subprocess
 import sys
 import threading
 import time
+from types import SimpleNamespace
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
@@ -225,10 +226,8 @@ def run_ours(args):
         pin = synth.make_projected_inputs(batch=batch, image_size=IMAGE_SIZE, num_classes=NUM_CLASSES,
                                           embed_dim=EMBED_DIM, device=dev, seed=1234 + rank)
         projections = pin.projections()
-
-        class _In:                      # same field names as HeadInputs; obj_embeds = hidden features
-            obj_embeds, box_preds, text = pin.hidden, pin.box_preds, pin.text
-        inp = _In
+        # same field names as HeadInputs; obj_embeds = the hidden features
+        inp = SimpleNamespace(obj_embeds=pin.hidden, box_preds=pin.box_preds, text=pin.text)
     else:
         inp = synth.make_inputs(batch=batch, image_size=IMAGE_SIZE, num_classes=NUM_CLASSES,
                                 embed_dim=EMBED_DIM, device=dev, seed=1234 + rank)
@@ -322,9 +321,7 @@ def run_ours(args):
         if args.projected:
             pone = synth.make_projected_inputs(batch=1, image_size=IMAGE_SIZE, num_classes=NUM_CLASSES,
                                                embed_dim=EMBED_DIM, device=dev, seed=1234 + rank)
-
-            class one:
-                obj_embeds, box_preds = pone.hidden, pone.box_preds
+            one = SimpleNamespace(obj_embeds=pone.hidden, box_preds=pone.box_preds)
         else:
             one = synth.make_inputs(batch=1, image_size=IMAGE_SIZE, num_classes=NUM_CLASSES,
                                     embed_dim=EMBED_DIM, device=dev, seed=77)
