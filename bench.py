@@ -219,6 +219,8 @@ def run_ours(args):
     shapes = [(IMAGE_SIZE // s, IMAGE_SIZE // s) for s in STRIDES]
     anchors = sum(h * w for h, w in shapes)
 
+    global MAX_DET
+    MAX_DET = args.max_det
     cfg = HeadConfig(precision=args.precision, max_det=MAX_DET, fused=not args.no_fused,
                      logits_dtype=None if args.logits == "none" else args.logits)
     projections = None
@@ -466,6 +468,9 @@ def main():
     ap.add_argument("--no-fused", action="store_true", help="two-kernel K1 -> K2 path instead of the fused kernel")
     ap.add_argument("--profile", action="store_true",
                     help="device-resident loop only (for ncu): no e2e, latency or CPU legs")
+    ap.add_argument("--max-det", type=int, default=MAX_DET,
+                    help="rows of the per-image output (the reference has no cap; the line reports how many "
+                         "images reached it - 0 at the default configuration)")
     ap.add_argument("--projected", action="store_true",
                     help="SURVEY 8f-2: start the step at the hidden features and fold the head's 1x1 projection "
                          "into the similarity (both arms)")

@@ -138,17 +138,35 @@ __device__ __forceinline__ float box_area(const float4 b) {
   return __fmul_rn(__fsub_rn(b.z, b.x), __fsub_rn(b.w, b.y));
 }
 
+// The threshold test `RN(inter / denom) <= thr` (float32 division, as numpy computes the IoU)
+// without the division: for denom > 0 the rounded quotient is <= thr exactly when the real
+// quotient is below the midpoint m between thr and the next float above it (or equal to it when
+// the tie rounds down to thr, i.e. thr's mantissa is even).  m has a 25-bit mantissa and denom a
+// 24-bit one, so denom * m is exact in double and the comparison is exact.
+struct IouTest {
+  double mid;        // (thr + nextafter(thr, +inf)) / 2
+  int tie_down;      // a quotient exactly at `mid` rounds to thr
+  int exact_ok;      // thr finite and >= 0: the double test applies
+  float thr;
+};
+
 // true when `b` must be dropped because of the already kept `a`: NOT (iou <= thr)
 __device__ __forceinline__ bool suppresses(const float4 a, const float area_a, const float4 b,
-                                           const float area_b, const float thr) {
+                                           const float area_b, const IouTest& t) {
   const float ix1 = fmaxf(a.x, b.x), iy1 = fmaxf(a.y, b.y);
   const float ix2 = fminf(a.z, b.z), iy2 = fminf(a.w, b.w);
   const float iw = fmaxf(0.f, __fsub_rn(ix2, ix1));
   const float ih = fmaxf(0.f, __fsub_rn(iy2, iy1));
   const float inter = __fmul_rn(iw, ih);
   const float uni = __fsub_rn(__fadd_rn(area_a, area_b), inter);
-  const float iou = __fdiv_rn(inter, __fadd_rn(uni, 1e-7f));
-  return !(iou <= thr);
+  const float denom = __fadd_rn(uni, 1e-7f);
+  if (t.exact_ok && denom > 0.f && inter <= 3.0e38f) {          // the common case (NaN fails both tests)
+    const double lhs = (double)inter, rhs = __dmul_rn((double)denom, t.mid);
+    const bool keep = lhs < rhs || (t.tie_down && lhs == rhs);
+    return !keep;
+  }
+  const float iou = __fdiv_rn(inter, denom);
+  return !(iou <= t.thr);
 }
 
 __global__ void __launch_bounds__(NMS_THREADS)
@@ -356,7 +374,14 @@ nms_batched_kernel(const NmsParams p) {
   const bool do_clip = p.clip_wh != nullptr;
   const float clip_w = do_clip ? p.clip_wh[2 * b] : 0.f;
   const float clip_h = do_clip ? p.clip_wh[2 * b + 1] : 0.f;
-  const float thr = p.iou_thr;
+  IouTest thr;
+  thr.thr = p.iou_thr;
+  thr.exact_ok = (p.iou_thr >= 0.f && p.iou_thr < 3.0e38f) ? 1 : 0;
+  {
+    const float up = __uint_as_float(__float_as_uint(p.iou_thr) + 1u);      // next float above (thr >= 0)
+    thr.mid = 0.5 * ((double)p.iou_thr + (double)up);
+    thr.tie_down = (__float_as_uint(p.iou_thr) & 1u) == 0u;
+  }
   const bool aware = p.class_aware && classes != nullptr;
   uint32_t* mask = reinterpret_cast<uint32_t*>(s_big);           // [CHUNK][CHUNK_WORDS]
 
@@ -387,14 +412,51 @@ nms_batched_kernel(const NmsParams p) {
     s_box[tid] = mine;
     s_area[tid] = my_area;
     s_cls[tid] = my_cls;
-    // 4b. candidates beyond n are born removed; later chunks: test against everything kept
+    // 4b. candidates beyond n are born removed; later chunks: test against everything kept.  The
+    // kept boxes are staged through shared memory 512 at a time (box + area + class, in the sort
+    // block, which is free until 4c), and when the chunk has fewer than 512 candidates the idle
+    // threads take slices of the kept list: thread = (slice, candidate).
     bool dead = tid >= n;
-    if (!dead && kept_before > 0) {
-      for (int k = 0; k < kept_before; ++k) {
-        const float4 kb = kept_boxes[k];
-        if (aware && kept_cls[k] != my_cls) continue;
-        if (suppresses(kb, box_area(kb), mine, my_area, thr)) { dead = true; break; }
+    if (kept_before > 0) {
+      float4* k_box = reinterpret_cast<float4*>(s_big);                 // [512]
+      float* k_area = reinterpret_cast<float*>(k_box + CHUNK);          // [512]
+      int* k_cls = reinterpret_cast<int*>(k_area + CHUNK);              // [512]
+      const int n_pad = (n + 31) & ~31;
+      const int slices = NMS_THREADS / n_pad;                           // >= 1
+      const int cand = tid % n_pad, slice = tid / n_pad;
+      const bool active = slice < slices && cand < n;
+      __syncthreads();                                                  // s_box / s_area / s_cls of this chunk are visible
+      const float4 cb = s_box[active ? cand : 0];
+      const float ca = s_area[active ? cand : 0];
+      const int cc = s_cls[active ? cand : 0];
+      bool hit = false;
+      for (int k0 = 0; k0 < kept_before; k0 += CHUNK) {
+        const int kn = min(CHUNK, kept_before - k0);
+        if (tid < kn) {
+          const float4 kb = kept_boxes[k0 + tid];
+          k_box[tid] = kb;
+          k_area[tid] = box_area(kb);
+          k_cls[tid] = kept_cls[k0 + tid];
+        }
+        __syncthreads();
+        if (active && !hit) {
+          const int per = (kn + slices - 1) / slices;
+          const int k_end = min(kn, (slice + 1) * per);
+          for (int k = slice * per; k < k_end; ++k) {
+            if (aware && k_cls[k] != cc) continue;
+            if (suppresses(k_box[k], k_area[k], cb, ca, thr)) { hit = true; break; }
+          }
+        }
+        __syncthreads();
       }
+      // combine the slices: one flag per candidate
+      int* s_hit = s_scan;                                              // NMS_THREADS ints, free here
+      s_hit[tid] = 0;
+      __syncthreads();
+      if (hit) s_hit[cand] = 1;
+      __syncthreads();
+      if (tid < n && s_hit[tid]) dead = true;
+      __syncthreads();
     }
     const uint32_t dead_bits = __ballot_sync(0xffffffffu, dead);
     if (lane == 0) s_removed[warp] = dead_bits;
