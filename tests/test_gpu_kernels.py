@@ -889,3 +889,35 @@ def test_similarity_fused_fp32_streaming(ov, cuda_device, classes, batched, dim)
     _, m0, a0 = ops.similarity_fused(dev_embs, top3, alpha, beta, logits_dtype=None, want_max=True, fp32=True)
     assert torch.equal(m0, rmax)
     assert (a0 == rarg).float().mean().item() >= 0.999
+
+
+def test_fused_modes_are_deterministic_under_load(ov, cuda_device):
+    """Race detector of last resort (compute-sanitizer is closed on this pool): every mode of the
+    fused kernel - CTA-pair cosine, projected, streaming fp32, attention - run 12 times on the same
+    mid-size input (thousands of tiles per launch, persistent CTAs recycling TMEM / smem rings)
+    must give bit-identical scores and classes every time."""
+    from ovdet import ops, synth
+    torch.manual_seed(5)
+    dev = cuda_device
+    inp = synth.make_inputs(batch=37, image_size=640, num_classes=1203, device=dev, seed=9)
+    top = ops.l2norm_text(inp.text)
+    pin = synth.make_projected_inputs(batch=37, image_size=640, num_classes=1203, device=dev, seed=9)
+    lops = [ops.project_vocabulary(pin.text, w, b) for w, b in pin.projections()]
+    inp80 = synth.make_inputs(batch=37, image_size=640, num_classes=80, device=dev, seed=9)
+    top3 = ops.text_operand_fp32(inp80.text)
+    y = torch.randn(16, 64, 80, 80, device=dev)
+    tproj = torch.randn(1203, 64, device=dev)
+
+    def runs():
+        yield "cosine", lambda: ops.similarity_fused(inp.obj_embeds, top, want_max=True)[1:]
+        yield "projected", lambda: ops.similarity_projected(pin.hidden, lops, 1203)
+        yield "fp32_stream", lambda: ops.similarity_fused(inp80.obj_embeds, top3, want_max=True, fp32=True)[1:]
+        yield "attention", lambda: ops.max_sigmoid_attention(y, tproj, precise=True, return_scores=True)
+
+    for name, fn in runs():
+        first = [t.clone() for t in fn()]
+        for _ in range(11):
+            again = fn()
+            torch.cuda.synchronize()
+            for a, b in zip(first, again):
+                assert torch.equal(a, b), name
