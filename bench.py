@@ -406,6 +406,8 @@ def run_ours(args):
             gbs = alg_bytes / (stages["similarity"] * 1e-3) / 1e9
             roofline = {"bound": "hbm", "kernel": kernel, "achieved": gbs, "peak": peaks["hbm_gbs"],
                         "unit": "GB/s", "frac": gbs / peaks["hbm_gbs"], "peak_source": peaks["source"] + " (hbm_gbs)"}
+        # north_star quotes nominal figures too: 2.25 PFLOP/s dense bf16, ~8 TB/s HBM3e
+        roofline["frac_of_nominal"] = roofline["achieved"] / (2250.0 if roofline["bound"] == "tensor" else 8000.0)
         roofline.update({"traffic": None if proj else ncu_traffic("sim_fused" if fused else "sim_gemm", batch),
                          "traffic_source": "profiles/r1_ncu_full_pipeline_b256_v4.json (ncu --set full, bytes per launch)",
                          "algorithmic_bytes": alg_bytes, "algorithmic_flops": flops,
@@ -442,7 +444,11 @@ def run_ours(args):
                                     k1_bytes / (stages["l2norm"] * 1e-3) / 1e9 / peaks["hbm_gbs"]),
                 "similarity_hbm_frac_fp32_input": batch * anchors * EMBED_DIM * 4 / (stages["similarity"] * 1e-3)
                                                   / 1e9 / peaks["hbm_gbs"],
-                "decode_hbm_frac": k3_bytes / (stages["decode"] * 1e-3) / 1e9 / peaks["hbm_gbs"]},
+                "decode_hbm_frac": k3_bytes / (stages["decode"] * 1e-3) / 1e9 / peaks["hbm_gbs"],
+                "decode_hbm_frac_of_nominal_8TBps": k3_bytes / (stages["decode"] * 1e-3) / 1e9 / 8000.0,
+                # K4 is latency/compute-shaped: IoU pairs resolved per second (candidates^2 / 2 per image)
+                "nms_iou_pairs_per_s": batch * cand * cand / 2.0 / (stages["nms"] * 1e-3),
+                "nms_images_per_s": batch / (stages["nms"] * 1e-3)},
             "latency_ms_p50_batch1": p50_graph,
             "latency_ms_p50_batch1_eager_python": p50,
             "latency_note": "batch-1 K1..K4 step, CUDA events; graph = HeadPipeline.replay() of the captured "
