@@ -302,6 +302,45 @@ OVDET_API int ovdet_max_sigmoid_attention(const float* y, int64_t batch, int64_t
                                           float* row_max, float* out, int64_t out_stride_b,
                                           int64_t out_stride_c, void* stream);
 
+/* ------------------------------------------------------------------------------------------
+ * The whole bf16 step in ONE call: K1+K2 fused -> K3 -> K4 enqueued on `stream`.
+ * Replaces: model/yolo_clip.py:173-214 followed by inference/detector.py:184-208, every image.
+ * Same kernels, same argument meaning as ovdet_similarity_fused / ovdet_decode_filter /
+ * ovdet_nms_batched (intermediates `scores`, `class_ids`, `boxes`, `pass_mask` are caller buffers
+ * too: [batch, anchors], [batch, anchors], [batch, anchors, 4], [batch, ceil(anchors / 32)]).
+ * A binding layer that pays per call (ctypes: ~20 us) launches the step for the price of one.
+ * ---------------------------------------------------------------------------------------- */
+typedef struct ovdet_head_step_args {
+  int32_t num_levels;              /* <= 4 */
+  int32_t bins;                    /* reg_max + 1 */
+  int64_t batch, dim, classes;
+  const float* obj_embeds[4];      /* fp32 [batch, dim, h, w] per level */
+  const float* box_preds[4];       /* fp32 [batch, 4 * bins, h, w] per level */
+  int32_t heights[4], widths[4], strides[4];
+  int64_t emb_stride_b[4], emb_stride_d[4], box_stride_b[4];
+  const void* text_op;             /* bf16 [text_batch, classes, dim], unit-norm rows */
+  int32_t text_batched;
+  int32_t activation;              /* ovdet_activation */
+  int32_t class_aware, topk;
+  float alpha, beta, conf, iou_thr;
+  int64_t max_det;
+  float* scores;                   /* out, also K3/K4 input */
+  int32_t* class_ids;
+  float* inv_norm;                 /* optional */
+  float* boxes;
+  float* scores_act;               /* sigmoid activation only */
+  uint32_t* pass_mask;
+  const float* scale;              /* optional [batch] */
+  const float* clip_wh;            /* optional [batch, 2] */
+  float* out_boxes; float* out_scores; int32_t* out_classes; int32_t* out_anchor; int32_t* out_keep;
+  int32_t* out_count; int32_t* out_candidates;
+  void* workspace; size_t workspace_bytes;
+} ovdet_head_step_args;
+
+OVDET_API int ovdet_head_step(const ovdet_head_step_args* args, void* stream);
+/* sizeof(ovdet_head_step_args) as compiled into the library (binding layers check their mirror). */
+OVDET_API size_t ovdet_head_step_args_size(void);
+
 #ifdef __cplusplus
 }
 #endif

@@ -17,6 +17,26 @@ OVDET_F32, OVDET_BF16 = 0, 1
 ACT_NONE, ACT_SIGMOID = 0, 1
 MAX_LEVELS = 8
 
+class HeadStepArgs(ctypes.Structure):
+    """``ovdet_head_step_args`` of include/ovdet.h, field for field."""
+    _fields_ = [
+        ("num_levels", c_int32), ("bins", c_int32),
+        ("batch", c_int64), ("dim", c_int64), ("classes", c_int64),
+        ("obj_embeds", c_void_p * 4), ("box_preds", c_void_p * 4),
+        ("heights", c_int32 * 4), ("widths", c_int32 * 4), ("strides", c_int32 * 4),
+        ("emb_stride_b", c_int64 * 4), ("emb_stride_d", c_int64 * 4), ("box_stride_b", c_int64 * 4),
+        ("text_op", c_void_p), ("text_batched", c_int32), ("activation", c_int32),
+        ("class_aware", c_int32), ("topk", c_int32),
+        ("alpha", c_float), ("beta", c_float), ("conf", c_float), ("iou_thr", c_float),
+        ("max_det", c_int64),
+        ("scores", c_void_p), ("class_ids", c_void_p), ("inv_norm", c_void_p), ("boxes", c_void_p),
+        ("scores_act", c_void_p), ("pass_mask", c_void_p), ("scale", c_void_p), ("clip_wh", c_void_p),
+        ("out_boxes", c_void_p), ("out_scores", c_void_p), ("out_classes", c_void_p),
+        ("out_anchor", c_void_p), ("out_keep", c_void_p), ("out_count", c_void_p),
+        ("out_candidates", c_void_p), ("workspace", c_void_p), ("workspace_bytes", c_size_t),
+    ]
+
+
 # name -> (restype, argtypes); mirrors include/ovdet.h one to one
 PROTOTYPES = {
     "ovdet_version": (c_int, []),
@@ -64,6 +84,8 @@ PROTOTYPES = {
     "ovdet_max_sigmoid_attention": (c_int, [c_void_p, c_int64, c_int64, c_int64, c_int64, c_int64, c_void_p,
                                             c_int64, c_int, c_int, c_void_p, c_void_p, c_int64, c_int64,
                                             c_void_p]),
+    "ovdet_head_step": (c_int, [POINTER(HeadStepArgs), c_void_p]),
+    "ovdet_head_step_args_size": (c_size_t, []),
     "ovdet_pack_boxes_i32": (c_int, [c_void_p, c_void_p, c_int64, c_int64, c_void_p, c_void_p]),
 }
 

@@ -20,7 +20,7 @@ OBJ = os.path.join(CSRC, "_obj")
 LIB = os.path.join(PKG_DIR, "libovdet.so")
 INCLUDE = os.path.join(os.path.dirname(PKG_DIR), "include")
 
-SOURCES = ["runtime.cu", "l2norm.cu", "sim_gemm_sm100.cu", "sim_fused_sm100.cu", "rowmax.cu", "decode.cu", "nms.cu", "preprocess.cu", "attention.cu"]
+SOURCES = ["runtime.cu", "l2norm.cu", "sim_gemm_sm100.cu", "sim_fused_sm100.cu", "rowmax.cu", "decode.cu", "nms.cu", "preprocess.cu", "attention.cu", "step.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
     "-Xcompiler", "-fPIC,-fvisibility=hidden", "-I", INCLUDE,

@@ -1,0 +1,33 @@
+// One C call for the whole bf16 step: K1+K2 fused -> K3 -> K4 on one stream.  The kernels are the
+// ones behind ovdet_similarity_fused / ovdet_decode_filter / ovdet_nms_batched; this entry only
+// removes the per-kernel host round trips of a binding layer (from Python a ctypes call costs
+// ~20 us, more than each kernel at batch 1).  Replaces model/yolo_clip.py:173-214 followed by
+// inference/detector.py:184-208 for every image of the batch.
+#include "common.cuh"
+
+extern "C" int ovdet_head_step(const ovdet_head_step_args* a, void* stream) {
+  if (!a) return OVDET_ERR_INVALID_ARG;
+  if (a->num_levels <= 0 || a->num_levels > 4) return OVDET_ERR_UNSUPPORTED_SHAPE;
+  int64_t hw[4];
+  int64_t anchors = 0;
+  for (int l = 0; l < a->num_levels; ++l) {
+    hw[l] = (int64_t)a->heights[l] * a->widths[l];
+    anchors += hw[l];
+  }
+  int rc = ovdet_similarity_fused(a->obj_embeds, hw, a->emb_stride_b, a->emb_stride_d, a->num_levels,
+                                  a->batch, a->dim, a->text_op, a->classes, a->text_batched, a->alpha,
+                                  a->beta, nullptr, OVDET_F32, a->classes, a->scores, a->class_ids,
+                                  a->inv_norm, stream);
+  if (rc != OVDET_OK) return rc;
+  rc = ovdet_decode_filter(a->box_preds, a->heights, a->widths, a->strides, a->box_stride_b,
+                           a->num_levels, a->bins, a->batch, 1.0f, 1.0f, a->scores, a->conf,
+                           a->activation, a->boxes, a->scores_act, a->pass_mask, stream);
+  if (rc != OVDET_OK) return rc;
+  const float* nms_scores = (a->activation == OVDET_ACT_SIGMOID && a->scores_act) ? a->scores_act : a->scores;
+  return ovdet_nms_batched(a->boxes, nms_scores, a->class_ids, a->pass_mask, a->batch, anchors, a->scale,
+                           a->clip_wh, a->iou_thr, a->class_aware, a->topk, a->max_det, a->out_boxes,
+                           a->out_scores, a->out_classes, a->out_anchor, a->out_keep, a->out_count,
+                           a->out_candidates, a->workspace, a->workspace_bytes, stream);
+}
+
+extern "C" size_t ovdet_head_step_args_size(void) { return sizeof(ovdet_head_step_args); }

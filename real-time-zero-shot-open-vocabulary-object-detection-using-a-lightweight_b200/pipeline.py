@@ -16,7 +16,9 @@ from typing import Dict, List, Optional, Sequence, Tuple
 
 import torch
 
-from . import ops
+import ctypes
+
+from . import _cabi, ops
 
 
 @dataclass(frozen=True)
@@ -108,6 +110,7 @@ class HeadPipeline:
         self.use_geometry = False
         self._vocab_ready = False
         self.last_path = None              # "fused" | "split": what the previous run() launched
+        self._step_args = None             # ovdet_head_step_args, filled on first use
         self._parallel_decode = False      # set by capture(): decode forked beside the similarity kernel
         self._side = None
         self._fork = None
@@ -166,6 +169,9 @@ class HeadPipeline:
                 self._fork.record(self._side)
         if self.projections is not None:
             return self._run_projected(obj_embeds, box_preds, text, mark)
+        if (events is None and self.want_fused and self.logits is None and not self._parallel_decode
+                and ops.fused_supported(obj_embeds) and self._single_call_ok(box_preds)):
+            return self._run_single_call(obj_embeds, box_preds, text)
         fused = self.want_fused and ops.fused_supported(obj_embeds)
         fused32 = self.want_fused_fp32 and ops.fused_supported(obj_embeds)
         self.last_path = "fused" if fused else ("fused_fp32" if fused32 else "split")
@@ -199,6 +205,59 @@ class HeadPipeline:
                            want_max=True, row_max=self.scores, row_arg=self.class_ids)
         mark("similarity", False)
         return self._decode_and_nms(box_preds, mark)
+
+    # -- the bf16 step as ONE C call (ovdet_head_step): same kernels, one host round trip ----------
+    def _single_call_ok(self, box_preds) -> bool:
+        for p in box_preds:
+            if p.dtype != torch.float32 or p.stride(3) != 1 or p.stride(2) != p.shape[3] or \
+                    p.stride(1) != p.shape[2] * p.shape[3]:
+                return False
+        return len(box_preds) <= 4
+
+    def _run_single_call(self, obj_embeds, box_preds, text) -> ops.NmsResult:
+        cfg = self.cfg
+        if self.per_image_text:
+            ops.l2norm_text(text, split=False, operand=self.text_op)
+        elif text is not None:
+            self.set_vocabulary(text)
+        elif not self._vocab_ready:
+            raise RuntimeError("ovdet: no vocabulary set (call set_vocabulary or pass text)")
+        a = self._step_args
+        if a is None:
+            a = _cabi.HeadStepArgs()
+            assert ctypes.sizeof(a) == _cabi.lib().ovdet_head_step_args_size()
+            n = len(self.level_shapes)
+            a.num_levels, a.bins = n, cfg.reg_max + 1
+            a.batch, a.dim, a.classes = self.batch, cfg.embed_dim, self.num_classes
+            for l, (h, w) in enumerate(self.level_shapes):
+                a.heights[l], a.widths[l], a.strides[l] = h, w, int(cfg.strides[l])
+            a.text_op = self.text_op.data_ptr()
+            a.text_batched = int(self.per_image_text and self.batch > 1)
+            a.activation = {"none": _cabi.ACT_NONE, "sigmoid": _cabi.ACT_SIGMOID}[cfg.activation]
+            a.class_aware, a.topk = int(cfg.class_aware), int(cfg.topk)
+            a.alpha, a.beta, a.conf, a.iou_thr = cfg.cls_alpha, cfg.cls_beta, cfg.conf_threshold, cfg.iou_threshold
+            a.max_det = self.max_det
+            a.scores, a.class_ids = self.scores.data_ptr(), self.class_ids.data_ptr()
+            a.inv_norm, a.boxes = self.inv_norm.data_ptr(), self.boxes.data_ptr()
+            a.scores_act = None if self.scores_act is None else self.scores_act.data_ptr()
+            a.pass_mask = self.pass_mask.data_ptr()
+            r = self.result
+            a.out_boxes, a.out_scores, a.out_classes = r.boxes.data_ptr(), r.scores.data_ptr(), r.classes.data_ptr()
+            a.out_anchor, a.out_keep = r.anchor.data_ptr(), r.keep.data_ptr()
+            a.out_count, a.out_candidates = r.count.data_ptr(), r.candidates.data_ptr()
+            a.workspace, a.workspace_bytes = self.workspace.data_ptr(), self.workspace.numel()
+            self._step_args = a
+        for l, (e, p) in enumerate(zip(obj_embeds, box_preds)):
+            a.obj_embeds[l], a.box_preds[l] = e.data_ptr(), p.data_ptr()
+            a.emb_stride_b[l], a.emb_stride_d[l], a.box_stride_b[l] = e.stride(0), e.stride(1), p.stride(0)
+        a.scale = self.scale.data_ptr() if self.use_geometry else None
+        a.clip_wh = self.clip_wh.data_ptr() if self.use_geometry else None
+        self.last_path = "fused"
+        with torch.cuda.device(self.device):
+            _cabi.check(_cabi.lib().ovdet_head_step(ctypes.byref(a),
+                                                    torch.cuda.current_stream(self.device).cuda_stream),
+                        "ovdet_head_step")
+        return self.result
 
     def _run_projected(self, hidden, box_preds, text, mark) -> ops.NmsResult:
         cfg = self.cfg

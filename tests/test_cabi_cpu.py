@@ -124,3 +124,10 @@ def test_bench_reference_arm_contract():
     assert line["impl"] == "reference" and line["value"] > 0 and line["gpu_launches"] == 0
     assert line["e2e"]["h2d_bytes_per_step"] == 0 and line["cpu_baseline"]["kind"] == "port"
     assert "workload" in line["config"]
+
+
+def test_head_step_args_mirror(handle):
+    """The ctypes mirror of ovdet_head_step_args has the size the library was compiled with."""
+    from ovdet import _cabi
+    assert ctypes.sizeof(_cabi.HeadStepArgs) == handle.ovdet_head_step_args_size()
+    assert handle.ovdet_head_step(None, None) == -1
