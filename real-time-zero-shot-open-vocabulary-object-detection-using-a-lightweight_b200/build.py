@@ -21,7 +21,9 @@ LIB = os.path.join(PKG_DIR, "libovdet.so")
 INCLUDE = os.path.join(os.path.dirname(PKG_DIR), "include")
 
 SOURCES = ["runtime.cu", "l2norm.cu", "sim_gemm_sm100.cu", "sim_fused_sm100.cu", "rowmax.cu", "decode.cu", "nms.cu", "preprocess.cu", "attention.cu", "step.cu"]
-NVCC_FLAGS = [
+# extra -D definitions for tuning experiments, e.g. OVDET_NVCC_DEFS="-DOVDET_F_A_STAGES=3 -DOVDET_F_B_STAGES=6"
+EXTRA_DEFS = os.environ.get("OVDET_NVCC_DEFS", "").split()
+NVCC_FLAGS = EXTRA_DEFS + [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
     "-Xcompiler", "-fPIC,-fvisibility=hidden", "-I", INCLUDE,
 ]

@@ -50,7 +50,13 @@ constexpr int F_BLOCK_M = 128;
 constexpr int F_BLOCK_N = 128;
 constexpr int F_BLOCK_K = 64;
 constexpr int F_MAX_KB = 8;                       // dim <= 512: A fills 256 TMEM columns
-constexpr int F_A_STAGES = 4;                     // fp32 activation ring
+#ifndef OVDET_F_A_STAGES
+#define OVDET_F_A_STAGES 4
+#endif
+#ifndef OVDET_F_B_STAGES
+#define OVDET_F_B_STAGES 4
+#endif
+constexpr int F_A_STAGES = OVDET_F_A_STAGES;      // fp32 activation ring (tuning: -DOVDET_F_A_STAGES=n)
 constexpr int F_A_STAGE_BYTES = F_BLOCK_K * F_BLOCK_M * 4;     // 32 KiB fp32 [k][anchor]
 constexpr int F_THREADS = 384;
 constexpr int F_TMEM_COLS = 512;
@@ -71,7 +77,7 @@ template <int CG>
 struct FSmem {
   static constexpr int kps = CG;                                     // k blocks per text stage
   static constexpr int b_sub_bytes = (F_BLOCK_N / CG) * F_BLOCK_K * 2;  // one TMA box: [N / CG rows x 64 k]
-  static constexpr int b_stages = 4;
+  static constexpr int b_stages = OVDET_F_B_STAGES;
   static constexpr int b_stage_bytes = kps * b_sub_bytes;            // 16 KiB
   static constexpr int b_off = 0;
   static constexpr int a_off = b_off + b_stages * b_stage_bytes;                     // 64 KiB
