@@ -921,3 +921,33 @@ def test_fused_modes_are_deterministic_under_load(ov, cuda_device):
             torch.cuda.synchronize()
             for a, b in zip(first, again):
                 assert torch.equal(a, b), name
+
+
+def test_predict_host_streams_equal_predict(ov, cuda_device):
+    """Detector.predict_host (pinned host buffers, chunked H2D on a copy stream overlapped with the
+    kernels on a compute stream, D2H of every chunk's detections) returns what predict returns for
+    the same images - with and without the folded projection."""
+    from ovdet import synth
+    from ovdet.detector import Detector
+    from ovdet.pipeline import HeadConfig
+    cfg = HeadConfig(precision="bf16", max_det=64)
+    inp = synth.make_inputs(batch=6, image_size=256, num_classes=90, seed=41)
+    pin = synth.make_projected_inputs(batch=6, image_size=256, num_classes=90, seed=41)
+    for embeds, preds, text, proj in ((inp.obj_embeds, inp.box_preds, inp.text, None),
+                                      (pin.hidden, pin.box_preds, pin.text, pin.projections())):
+        det = Detector(device=str(cuda_device), config=cfg)
+        det.set_vocabulary(text.to(cuda_device))
+        dproj = None if proj is None else [(w.to(cuda_device), b.to(cuda_device)) for w, b in proj]
+        want = det.predict([e.to(cuda_device) for e in embeds], [p.to(cuda_device) for p in preds],
+                           text.to(cuda_device), projections=dproj)
+        torch.cuda.synchronize()
+        want = {k: getattr(want, k).cpu().clone() for k in ("boxes", "scores", "classes", "count")}
+        host_e = [e.pin_memory() for e in embeds]
+        host_p = [p.pin_memory() for p in preds]
+        for _ in range(2):                       # second call reuses the staging buffers / streams
+            got = det.predict_host(host_e, host_p, chunk=2, projections=dproj)
+        assert torch.equal(got["count"], want["count"]) and int(want["count"].sum()) > 0
+        for i in range(6):
+            k = int(want["count"][i])
+            for key in ("boxes", "scores", "classes"):
+                assert torch.equal(got[key][i, :k], want[key][i, :k]), key
