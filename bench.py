@@ -233,6 +233,10 @@ def run_ours(args):
     else:
         inp = synth.make_inputs(batch=batch, image_size=IMAGE_SIZE, num_classes=NUM_CLASSES,
                                 embed_dim=EMBED_DIM, device=dev, seed=1234 + rank)
+    if args.input_dtype == "bf16":
+        # the head convolutions ran under autocast: bf16 region embeddings (box logits stay fp32)
+        inp = SimpleNamespace(obj_embeds=[e.to(torch.bfloat16) for e in inp.obj_embeds], box_preds=inp.box_preds,
+                              text=inp.text)
     pipe = HeadPipeline(batch, shapes, NUM_CLASSES, cfg, device=dev, projections=projections)
     # the vocabulary is replicated: rank 0's copy goes to every GPU once, outside the timed region
     vocab = shard.broadcast_vocabulary(inp.text if rank == 0 else None, NUM_CLASSES, EMBED_DIM, dev)
@@ -242,7 +246,7 @@ def run_ours(args):
     # projected operand (text x the 1x1 conv weights) is a per-vocabulary precompute, like the
     # reference's offline vocabulary.
     step_text = None if args.projected else vocab
-    input_bytes = sum(t.numel() * 4 for t in inp.obj_embeds + inp.box_preds)
+    input_bytes = sum(t.numel() * t.element_size() for t in inp.obj_embeds + inp.box_preds)
 
     def barrier():
         if world > 1:
@@ -327,6 +331,8 @@ def run_ours(args):
         else:
             one = synth.make_inputs(batch=1, image_size=IMAGE_SIZE, num_classes=NUM_CLASSES,
                                     embed_dim=EMBED_DIM, device=dev, seed=77)
+            if args.input_dtype == "bf16":
+                one = SimpleNamespace(obj_embeds=[e.to(torch.bfloat16) for e in one.obj_embeds], box_preds=one.box_preds)
         pipe1 = HeadPipeline(1, shapes, NUM_CLASSES, cfg, device=dev, projections=projections)
         pipe1.set_vocabulary(inp.text)
         lat = []
@@ -392,7 +398,8 @@ def run_ours(args):
         # dominant kernel's algorithmic bytes: the fused kernel reads the fp32 activations once; the
         # two-kernel path's GEMM reads the bf16 operand (hi|lo halves for the fp32 recipe)
         kop_bytes = EMBED_DIM * 2 * (2 if args.precision == "fp32" else 1)
-        alg_bytes = (batch * anchors * (EMBED_DIM * 4 + 12) if fused else batch * anchors * (kop_bytes + 12)) \
+        in_esz = 2 if args.input_dtype == "bf16" else 4
+        alg_bytes = (batch * anchors * (EMBED_DIM * in_esz + 12) if fused else batch * anchors * (kop_bytes + 12)) \
             + NUM_CLASSES * kop_bytes
         if proj:
             alg_bytes = batch * anchors * (256 * 4 + 12) + 3 * (NUM_CLASSES + 272) * 272 * 2
@@ -425,6 +432,7 @@ def run_ours(args):
                        "precision": ("bf16 operands, fp32 accumulate, fused class max/argmax" if args.precision == "bf16"
                                      else "three bf16 passes over hi/lo operand halves (|dlogit| ~ 1e-5), fp32 accumulate"),
                        "path": pipe.last_path, "materialised_logits": args.logits,
+                       "region_embedding_dtype": args.input_dtype,
                        "conf": cfg.conf_threshold, "iou": cfg.iou_threshold, "max_det": MAX_DET,
                        "parallelism": f"batch-sharded x{n_gpus}, vocabulary replicated, no collective",
                        "l2": f"inputs are {input_bytes / 1e9:.2f} GB per step per GPU (> 126 MB L2), no flush needed",
@@ -474,6 +482,9 @@ def main():
     ap.add_argument("--no-fused", action="store_true", help="two-kernel K1 -> K2 path instead of the fused kernel")
     ap.add_argument("--profile", action="store_true",
                     help="device-resident loop only (for ncu): no e2e, latency or CPU legs")
+    ap.add_argument("--input-dtype", default="fp32", choices=["fp32", "bf16"],
+                    help="dtype of the region embeddings handed to the path: fp32 (the reference's convolutions; "
+                         "the metric's configuration) or bf16 (the head ran under autocast)")
     ap.add_argument("--max-det", type=int, default=MAX_DET,
                     help="rows of the per-image output (the reference has no cap; the line reports how many "
                          "images reached it - 0 at the default configuration)")

@@ -135,6 +135,19 @@ OVDET_API int ovdet_similarity_fused(const float* const* obj_embeds, const int64
                                      int64_t ldc, float* row_max, int32_t* row_arg,
                                      float* inv_norm, void* stream);
 
+/* K1+K2 fused, bf16 activations: as ovdet_similarity_fused, but obj_embeds[l] is bf16
+ * [batch, dim, hw[l]] (the head convolutions ran under autocast; the reference's
+ * compute_similarity accepts any float dtype).  The sum of squares is accumulated in fp32; the
+ * tensor-core operand is the input itself, so no rounding is added.  Strides multiples of 8
+ * elements, pointers 16-byte aligned. */
+OVDET_API int ovdet_similarity_fused_bf16in(const void* const* obj_embeds, const int64_t* hw,
+                                            const int64_t* stride_b, const int64_t* stride_d,
+                                            int num_levels, int64_t batch, int64_t dim,
+                                            const void* text_op, int64_t classes, int text_batched,
+                                            float alpha, float beta, void* logits, int logits_dtype,
+                                            int64_t ldc, float* row_max, int32_t* row_arg,
+                                            float* inv_norm, void* stream);
+
 /* K1+K2 fused, fp32-accurate: the same kernel with the three-pass recipe (x = hi + lo in bf16,
  * hi*hi + hi*lo + lo*hi accumulated in fp32, |dlogit| ~ 1e-5) for vocabularies of at most 128
  * classes (BASELINE configs[1]: 80 COCO prompts): with a single N tile every converted activation
@@ -314,7 +327,7 @@ typedef struct ovdet_head_step_args {
   int32_t num_levels;              /* <= 4 */
   int32_t bins;                    /* reg_max + 1 */
   int64_t batch, dim, classes;
-  const float* obj_embeds[4];      /* fp32 [batch, dim, h, w] per level */
+  const void* obj_embeds[4];       /* fp32 or bf16 (embed_dtype) [batch, dim, h, w] per level */
   const float* box_preds[4];       /* fp32 [batch, 4 * bins, h, w] per level */
   int32_t heights[4], widths[4], strides[4];
   int64_t emb_stride_b[4], emb_stride_d[4], box_stride_b[4];
@@ -322,6 +335,7 @@ typedef struct ovdet_head_step_args {
   int32_t text_batched;
   int32_t activation;              /* ovdet_activation */
   int32_t class_aware, topk;
+  int32_t embed_dtype;             /* ovdet_dtype of obj_embeds: OVDET_F32 or OVDET_BF16 */
   float alpha, beta, conf, iou_thr;
   int64_t max_det;
   float* scores;                   /* out, also K3/K4 input */

@@ -163,7 +163,10 @@ __device__ __forceinline__ TileCoord decode_tile(const FusedParams& p, int tile)
 // against G': their epilogue accumulates q = sum_j (x' G')_j x'_j = ||W x + b||^2 with x' read
 // back from the A region of tensor memory; the class tiles keep the raw running max/argmax and
 // the row is scaled by alpha / sqrt(q) once at the end.  No logits in this mode.
-template <int KB_T, bool SPLIT3, int CG, bool PROJ>
+// IN16: the activations arrive as bf16 (the head ran under autocast) instead of fp32: the TMA box
+// is [64 k x 128 anchors] bf16 (16 KiB of the 32 KiB stage), the converter widens, accumulates the
+// sum of squares in fp32 and re-packs - half the HBM and PCIe bytes of the fp32 input.
+template <int KB_T, bool SPLIT3, int CG, bool PROJ, bool IN16 = false>
 __global__ void __launch_bounds__(F_THREADS, 1)
 sim_fused_kernel(const __grid_constant__ LevelMaps amaps, const __grid_constant__ LevelMaps bmaps,
                  const FusedParams p) {
@@ -367,7 +370,7 @@ sim_fused_kernel(const __grid_constant__ LevelMaps amaps, const __grid_constant_
         const uint32_t s = ia % F_A_STAGES;
         const uint32_t ph = (ia / F_A_STAGES) & 1u;
         ptx::mbar_wait_lazy(as_empty0 + 8u * s, ph ^ 1u, lazy_ns);
-        ptx::mbar_arrive_expect_tx_if(issue, as_full0 + 8u * s, F_A_STAGE_BYTES);
+        ptx::mbar_arrive_expect_tx_if(issue, as_full0 + 8u * s, IN16 ? F_A_STAGE_BYTES / 2 : F_A_STAGE_BYTES);
         ptx::tma_load_3d_if(issue, smem_a + s * F_A_STAGE_BYTES, map, as_full0 + 8u * s, tc.m0,
                             kb * F_BLOCK_K, tc.b);
       }
@@ -434,12 +437,17 @@ sim_fused_kernel(const __grid_constant__ LevelMaps amaps, const __grid_constant_
         const uint32_t s = ia % F_A_STAGES;
         ptx::mbar_wait_lazy(as_full0 + 8u * s, (ia / F_A_STAGES) & 1u, lazy_ns >> 1);
         const float* col = a_stage_ptr + s * (F_A_STAGE_BYTES / 4) + arow;
+        const __nv_bfloat16* col16 = reinterpret_cast<const __nv_bfloat16*>(a_stage_ptr + s * (F_A_STAGE_BYTES / 4)) + arow;
+        auto ldx = [&](int k) -> float {
+          if constexpr (IN16) return __bfloat162float(col16[k * F_BLOCK_M]);
+          else return col[k * F_BLOCK_M];
+        };
         uint32_t packed[32];
         uint32_t packed_lo[32];                            // dead (eliminated) unless SPLIT3
 #pragma unroll
         for (int k = 0; k < 64; k += 4) {
-          const float x0 = col[(k + 0) * F_BLOCK_M], x1 = col[(k + 1) * F_BLOCK_M];
-          const float x2 = col[(k + 2) * F_BLOCK_M], x3 = col[(k + 3) * F_BLOCK_M];
+          const float x0 = ldx(k + 0), x1 = ldx(k + 1);
+          const float x2 = ldx(k + 2), x3 = ldx(k + 3);
           ss0 = fmaf(x0, x0, ss0); ss1 = fmaf(x1, x1, ss1);
           ss2 = fmaf(x2, x2, ss2); ss3 = fmaf(x3, x3, ss3);
           packed[(k >> 1) + 0] = pack_bf16x2(x0, x1);
@@ -771,8 +779,10 @@ int fused_launch(const float* const* obj_embeds, const int64_t* hw, const int64_
                  const int64_t* stride_d, int num_levels, int64_t batch, int64_t dim,
                  const void* text_op, const void* const* level_ops, int64_t classes, int text_batched,
                  int normalize, int split3, float alpha, float beta, void* logits, int logits_dtype,
-                 int64_t ldc, float* row_max, int32_t* row_arg, float* inv_norm, void* stream) {
+                 int64_t ldc, float* row_max, int32_t* row_arg, float* inv_norm, void* stream,
+                 int in_bf16) {
   const int proj = level_ops != nullptr;
+  if (in_bf16 && (proj || split3)) return OVDET_ERR_UNSUPPORTED_SHAPE;   // bf16 activations: cosine mode only
   if (batch == 0) return check_device();            // an empty batch is a no-op (its pointers may be null)
   if (!obj_embeds || !hw || !stride_b || !stride_d || (!text_op && !proj) || batch < 0 || classes <= 0 || dim <= 0)
     return OVDET_ERR_INVALID_ARG;
@@ -802,7 +812,8 @@ int fused_launch(const float* const* obj_embeds, const int64_t* hw, const int64_
     if (!obj_embeds[l] || hw[l] <= 0) return OVDET_ERR_INVALID_ARG;
     if (proj && (!level_ops[l] || ((uintptr_t)level_ops[l] & 15))) return OVDET_ERR_INVALID_ARG;
     // TMA needs 16-byte aligned base and strides
-    if (((uintptr_t)obj_embeds[l] & 15) || (stride_d[l] & 3) || (stride_b[l] & 3) || stride_d[l] < hw[l])
+    const int64_t amask = in_bf16 ? 7 : 3;
+    if (((uintptr_t)obj_embeds[l] & 15) || (stride_d[l] & amask) || (stride_b[l] & amask) || stride_d[l] < hw[l])
       return OVDET_ERR_UNSUPPORTED_SHAPE;
     p.hw[l] = (int)hw[l];
     p.mt[l] = (int)ceil_div<int64_t>(hw[l], F_BLOCK_M);
@@ -821,11 +832,13 @@ int fused_launch(const float* const* obj_embeds, const int64_t* hw, const int64_
   if (!enc) return OVDET_ERR_DRIVER;
   for (int l = 0; l < num_levels; ++l) {
     cuuint64_t dims[3] = {(cuuint64_t)hw[l], (cuuint64_t)dim, (cuuint64_t)batch};
-    cuuint64_t strides[2] = {(cuuint64_t)stride_d[l] * 4, (cuuint64_t)stride_b[l] * 4};
+    const cuuint64_t esz = in_bf16 ? 2 : 4;
+    cuuint64_t strides[2] = {(cuuint64_t)stride_d[l] * esz, (cuuint64_t)stride_b[l] * esz};
     cuuint32_t box[3] = {(cuuint32_t)F_BLOCK_M, (cuuint32_t)F_BLOCK_K, 1};
     cuuint32_t estr[3] = {1, 1, 1};
-    if (batch == 1) strides[1] = (cuuint64_t)dim * stride_d[l] * 4;      // unused but must be valid
-    CUresult r = enc(&maps.m[l], CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(obj_embeds[l]),
+    if (batch == 1) strides[1] = (cuuint64_t)dim * stride_d[l] * esz;    // unused but must be valid
+    CUresult r = enc(&maps.m[l], in_bf16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3,
+                     const_cast<float*>(obj_embeds[l]),
                      dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
                      CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) return OVDET_ERR_DRIVER;
@@ -881,6 +894,8 @@ int fused_launch(const float* const* obj_embeds, const int64_t* hw, const int64_
     OVDET_CUDA_TRY(cudaFuncSetAttribute(sim_fused_kernel<8, false, 2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, FSmem<2>::bytes));
     OVDET_CUDA_TRY(cudaFuncSetAttribute(sim_fused_kernel<0, false, 1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, FSmem<1>::bytes));
     OVDET_CUDA_TRY(cudaFuncSetAttribute(sim_fused_kernel<4, false, 2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, FSmem<2>::bytes));
+    OVDET_CUDA_TRY(cudaFuncSetAttribute(sim_fused_kernel<8, false, 2, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, FSmem<2>::bytes));
+    OVDET_CUDA_TRY(cudaFuncSetAttribute(sim_fused_kernel<0, false, 1, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, FSmem<1>::bytes));
   }
   if (cg == 2) {
     // one CTA per SM, launched as clusters of two (the pair shares a TPC)
@@ -897,11 +912,14 @@ int fused_launch(const float* const* obj_embeds, const int64_t* hw, const int64_
     cfg.attrs = attr;
     cfg.numAttrs = 1;
     if (proj) OVDET_CUDA_TRY(cudaLaunchKernelEx(&cfg, sim_fused_kernel<4, false, 2, true>, maps, bmaps, p));
+    else if (in_bf16) OVDET_CUDA_TRY(cudaLaunchKernelEx(&cfg, sim_fused_kernel<8, false, 2, false, true>, maps, bmaps, p));
     else OVDET_CUDA_TRY(cudaLaunchKernelEx(&cfg, sim_fused_kernel<8, false, 2, false>, maps, bmaps, p));
     return OVDET_OK;
   }
   const int grid = (int)(tiles < sm_count() ? tiles : sm_count());
-  if (proj)
+  if (in_bf16)
+    sim_fused_kernel<0, false, 1, false, true><<<grid, F_THREADS, FSmem<1>::bytes, as_stream(stream)>>>(maps, bmaps, p);
+  else if (proj)
     sim_fused_kernel<0, false, 1, true><<<grid, F_THREADS, FSmem<1>::bytes, as_stream(stream)>>>(maps, bmaps, p);
   else if (split3)
     sim_fused_kernel<0, true, 1, false><<<grid, F_THREADS, FSmem<1>::bytes, as_stream(stream)>>>(maps, bmaps, p);
@@ -925,7 +943,20 @@ extern "C" int ovdet_similarity_fused(const float* const* obj_embeds, const int6
   if (dim % 64 != 0) return OVDET_ERR_UNSUPPORTED_SHAPE;   // the text operand has exactly `dim` columns
   return ovdet::fused_launch(obj_embeds, hw, stride_b, stride_d, num_levels, batch, dim, text_op, nullptr,
                              classes, text_batched, /*normalize=*/1, /*split3=*/0, alpha, beta, logits,
-                             logits_dtype, ldc, row_max, row_arg, inv_norm, stream);
+                             logits_dtype, ldc, row_max, row_arg, inv_norm, stream, 0);
+}
+
+extern "C" int ovdet_similarity_fused_bf16in(const void* const* obj_embeds, const int64_t* hw,
+                                             const int64_t* stride_b, const int64_t* stride_d,
+                                             int num_levels, int64_t batch, int64_t dim,
+                                             const void* text_op, int64_t classes, int text_batched,
+                                             float alpha, float beta, void* logits, int logits_dtype,
+                                             int64_t ldc, float* row_max, int32_t* row_arg,
+                                             float* inv_norm, void* stream) {
+  if (dim % 64 != 0) return OVDET_ERR_UNSUPPORTED_SHAPE;
+  return ovdet::fused_launch(reinterpret_cast<const float* const*>(obj_embeds), hw, stride_b, stride_d,
+                             num_levels, batch, dim, text_op, nullptr, classes, text_batched, 1, 0, alpha,
+                             beta, logits, logits_dtype, ldc, row_max, row_arg, inv_norm, stream, 1);
 }
 
 extern "C" int ovdet_similarity_fused_fp32(const float* const* obj_embeds, const int64_t* hw,
@@ -938,7 +969,7 @@ extern "C" int ovdet_similarity_fused_fp32(const float* const* obj_embeds, const
   if (dim % 64 != 0) return OVDET_ERR_UNSUPPORTED_SHAPE;
   return ovdet::fused_launch(obj_embeds, hw, stride_b, stride_d, num_levels, batch, dim, text_op3, nullptr,
                              classes, text_batched, /*normalize=*/1, /*split3=*/1, alpha, beta, logits,
-                             logits_dtype, ldc, row_max, row_arg, inv_norm, stream);
+                             logits_dtype, ldc, row_max, row_arg, inv_norm, stream, 0);
 }
 
 extern "C" int ovdet_similarity_projected(const float* const* hidden, const int64_t* hw,
@@ -950,5 +981,5 @@ extern "C" int ovdet_similarity_projected(const float* const* hidden, const int6
   if (!level_ops) return OVDET_ERR_INVALID_ARG;
   return ovdet::fused_launch(hidden, hw, stride_b, stride_d, num_levels, batch, hidden_dim, nullptr, level_ops,
                              classes, text_batched, /*normalize=*/1, /*split3=*/0, alpha, beta, nullptr,
-                             OVDET_F32, classes, row_max, row_arg, inv_norm, stream);
+                             OVDET_F32, classes, row_max, row_arg, inv_norm, stream, 0);
 }

@@ -184,7 +184,7 @@ class Detector:
         chunk = min(chunk, batch)
         if batch % chunk:
             raise ValueError("ovdet: batch must be a multiple of the chunk size")
-        key = (batch, chunk, tuple(tuple(e.shape[1:]) for e in obj_embeds),
+        key = (batch, chunk, tuple(tuple(e.shape[1:]) for e in obj_embeds), obj_embeds[0].dtype,
                None if projections is None else tuple(w.data_ptr() for w, _ in projections))
         st = self._host_state
         if st is None or st["key"] != key:
@@ -197,8 +197,8 @@ class Detector:
             st = {
                 "key": key, "pipe": pipe,
                 "copy": torch.cuda.Stream(dev), "compute": torch.cuda.Stream(dev),
-                "stage": [([torch.empty((chunk,) + tuple(e.shape[1:]), device=dev) for e in obj_embeds],
-                           [torch.empty((chunk,) + tuple(p.shape[1:]), device=dev) for p in box_preds])
+                "stage": [([torch.empty((chunk,) + tuple(e.shape[1:]), device=dev, dtype=e.dtype) for e in obj_embeds],
+                           [torch.empty((chunk,) + tuple(p.shape[1:]), device=dev, dtype=p.dtype) for p in box_preds])
                           for _ in range(2)],
                 "out": {"boxes": torch.empty(batch, md, 4).pin_memory(),
                         "scores": torch.empty(batch, md).pin_memory(),

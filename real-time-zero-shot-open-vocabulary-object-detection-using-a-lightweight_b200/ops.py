@@ -142,16 +142,21 @@ def similarity(regions_op: torch.Tensor, text_op: torch.Tensor, inv_norm: Option
 
 
 def fused_supported(obj_embeds: Sequence[torch.Tensor]) -> bool:
-    """Shapes the fused K1+K2 kernel takes (TMA alignment, <= 4 levels, dim <= 512)."""
+    """Shapes the fused K1+K2 kernel takes (TMA alignment, <= 4 levels, dim <= 512); fp32 levels,
+    or bf16 levels (all of them) for the bf16-activation variant."""
     if len(obj_embeds) > 4:
         return False
+    dt = obj_embeds[0].dtype
+    if dt not in (torch.float32, torch.bfloat16):
+        return False
+    per16 = 16 // obj_embeds[0].element_size()
     for e in obj_embeds:
         b, d, h, w = e.shape
-        if e.dtype != torch.float32 or d % 64 or d > 512:
+        if e.dtype != dt or d % 64 or d > 512:
             return False
         if e.stride(3) != 1 or e.stride(2) != w:
             return False
-        if e.stride(1) % 4 or e.stride(0) % 4 or e.data_ptr() % 16 or e.stride(1) < h * w:
+        if e.stride(1) % per16 or e.stride(0) % per16 or e.data_ptr() % 16 or e.stride(1) < h * w:
             return False
     return True
 
@@ -180,8 +185,11 @@ def similarity_fused(obj_embeds: Sequence[torch.Tensor], text_op: torch.Tensor, 
     Returns ``(logits [B, A, C] or None, row_max, row_arg)``; ``want_arg=False`` skips the
     argmax (scores only)."""
     first = obj_embeds[0]
-    _require_cuda(first, "obj_embed", torch.float32)
+    _require_cuda(first, "obj_embed")
     _require_cuda(text_op, "text_op", torch.bfloat16)
+    in16 = first.dtype == torch.bfloat16
+    if in16 and fp32:
+        raise ValueError("ovdet: the fp32-accurate mode takes fp32 activations")
     if not fused_supported(obj_embeds):
         raise ValueError("ovdet: shapes/strides not supported by the fused kernel "
                          "(use l2norm_regions + similarity)")
@@ -209,7 +217,8 @@ def similarity_fused(obj_embeds: Sequence[torch.Tensor], text_op: torch.Tensor, 
     hw = (ctypes.c_int64 * n)(*[e.shape[2] * e.shape[3] for e in obj_embeds])
     sb = (ctypes.c_int64 * n)(*[e.stride(0) for e in obj_embeds])
     sd = (ctypes.c_int64 * n)(*[e.stride(1) for e in obj_embeds])
-    entry = lib().ovdet_similarity_fused_fp32 if fp32 else lib().ovdet_similarity_fused
+    entry = (lib().ovdet_similarity_fused_fp32 if fp32 else
+             lib().ovdet_similarity_fused_bf16in if in16 else lib().ovdet_similarity_fused)
     with torch.cuda.device(dev):
         check(entry(ptrs, hw, sb, sd, n, batch, dim, text_op.data_ptr(),
                     classes, int(bt == batch and batch > 1), float(alpha),

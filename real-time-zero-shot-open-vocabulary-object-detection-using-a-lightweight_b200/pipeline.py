@@ -250,6 +250,7 @@ class HeadPipeline:
         for l, (e, p) in enumerate(zip(obj_embeds, box_preds)):
             a.obj_embeds[l], a.box_preds[l] = e.data_ptr(), p.data_ptr()
             a.emb_stride_b[l], a.emb_stride_d[l], a.box_stride_b[l] = e.stride(0), e.stride(1), p.stride(0)
+        a.embed_dtype = _cabi.OVDET_BF16 if obj_embeds[0].dtype == torch.bfloat16 else _cabi.OVDET_F32
         a.scale = self.scale.data_ptr() if self.use_geometry else None
         a.clip_wh = self.clip_wh.data_ptr() if self.use_geometry else None
         self.last_path = "fused"

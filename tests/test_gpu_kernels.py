@@ -951,3 +951,29 @@ def test_predict_host_streams_equal_predict(ov, cuda_device):
             k = int(want["count"][i])
             for key in ("boxes", "scores", "classes"):
                 assert torch.equal(got[key][i, :k], want[key][i, :k]), key
+
+
+@pytest.mark.parametrize("classes,batched,dim", [(1203, False, 512), (80, True, 512), (33, False, 128)])
+def test_similarity_fused_bf16_activations(ov, cuda_device, classes, batched, dim):
+    """bf16 conv outputs (autocast) straight into the fused kernel: same bar as the bf16 path,
+    against the oracle fed with the same (exactly representable) values in fp32."""
+    from ovdet import ops
+    torch.manual_seed(classes)
+    b = 2
+    shapes = [(24, 24), (16, 8), (4, 4)]                    # 576 | 128 | 16 anchors, H*W multiples of 8
+    embs16 = [(torch.randn(b, dim, h, w) * (0.5 + l)).to(torch.bfloat16) for l, (h, w) in enumerate(shapes)]
+    text = torch.randn(b, classes, dim) if batched else torch.randn(classes, dim).unsqueeze(0).expand(b, -1, -1)
+    ref = torch.cat([ref_port.compute_similarity(e.float(), text, 1.2, 0.1).flatten(2).transpose(1, 2)
+                     for e in embs16], dim=1)
+    dev = [e.to(cuda_device) for e in embs16]
+    assert ops.fused_supported(dev)
+    top = ops.l2norm_text(text.to(cuda_device) if batched else text[0].to(cuda_device))
+    logits, rmax, rarg = ops.similarity_fused(dev, top, 1.2, 0.1, logits_dtype=torch.float32, want_max=True)
+    torch.cuda.synchronize()
+    assert_logits_close(logits, ref, "bf16", 1.2)
+    m, a = logits.max(dim=-1)
+    assert torch.equal(rmax, m) and torch.equal(rarg.long(), a)
+    # the activations are already bf16, so the only rounding left is the text operand's: the fp32-input
+    # kernel fed with the widened values multiplies the same bf16 products
+    l32, _, _ = ops.similarity_fused([e.float() for e in dev], top, 1.2, 0.1, logits_dtype=torch.float32)
+    assert (logits - l32).abs().max().item() <= 2e-6
