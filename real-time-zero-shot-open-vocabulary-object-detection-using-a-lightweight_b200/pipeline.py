@@ -11,8 +11,8 @@ model/yolo_clip.py:173-214 followed by inference/detector.py:163-223 for every i
 """
 from __future__ import annotations
 
-from dataclasses import dataclass, field
-from typing import Dict, List, Optional, Sequence, Tuple
+from dataclasses import dataclass
+from typing import Dict, Optional, Sequence, Tuple
 
 import torch
 
@@ -114,8 +114,6 @@ class HeadPipeline:
         self._parallel_decode = False      # set by capture(): decode forked beside the similarity kernel
         self._side = None
         self._fork = None
-        self.launches_per_step = ((3 if self.want_fused else len(self.level_shapes) + 3)
-                                  + (1 if per_image_text else 0))
 
     # -- one-off / per-call host parameters -------------------------------------------------
     def set_vocabulary(self, text: torch.Tensor) -> None:
