@@ -135,6 +135,22 @@ OVDET_API int ovdet_similarity_fused(const float* const* obj_embeds, const int64
                                      int64_t ldc, float* row_max, int32_t* row_arg,
                                      float* inv_norm, void* stream);
 
+/* K1+K2 fused with a scratch buffer for SMALL launches (scores / argmax only).  When the launch has
+ * fewer anchor tiles than half the CTA pairs of the GPU (batch 1 at 640^2: 67 tiles on 74 pairs), the
+ * class tiles of every anchor tile are split over up to 4 work items; each writes its partial
+ * (max, argmax) to the workspace and the last one to arrive - counted with an atomic per 32-row
+ * group - merges them (lower class index wins ties, as in the unsplit kernel).  The workspace
+ * (ovdet_similarity_split_workspace_bytes; 0 = this shape never splits) must be ZERO before its first
+ * use and is left zero.  embed_dtype: OVDET_F32 or OVDET_BF16 activations. */
+OVDET_API size_t ovdet_similarity_split_workspace_bytes(int64_t batch, int64_t anchors);
+OVDET_API int ovdet_similarity_fused_ws(const float* const* obj_embeds, const int64_t* hw,
+                                        const int64_t* stride_b, const int64_t* stride_d,
+                                        int num_levels, int64_t batch, int64_t dim,
+                                        const void* text_op, int64_t classes, int text_batched,
+                                        float alpha, float beta, float* row_max, int32_t* row_arg,
+                                        float* inv_norm, void* workspace, size_t workspace_bytes,
+                                        int embed_dtype, void* stream);
+
 /* K1+K2 fused, bf16 activations: as ovdet_similarity_fused, but obj_embeds[l] is bf16
  * [batch, dim, hw[l]] (the head convolutions ran under autocast; the reference's
  * compute_similarity accepts any float dtype).  The sum of squares is accumulated in fp32; the
@@ -348,7 +364,9 @@ typedef struct ovdet_head_step_args {
   const float* clip_wh;            /* optional [batch, 2] */
   float* out_boxes; float* out_scores; int32_t* out_classes; int32_t* out_anchor; int32_t* out_keep;
   int32_t* out_count; int32_t* out_candidates;
-  void* workspace; size_t workspace_bytes;
+  void* workspace; size_t workspace_bytes;           /* K4: ovdet_nms_workspace_bytes */
+  void* sim_workspace; size_t sim_workspace_bytes;   /* optional, ZEROED once by the caller:
+                                                        ovdet_similarity_split_workspace_bytes */
 } ovdet_head_step_args;
 
 OVDET_API int ovdet_head_step(const ovdet_head_step_args* args, void* stream);

@@ -34,6 +34,7 @@ class HeadStepArgs(ctypes.Structure):
         ("out_boxes", c_void_p), ("out_scores", c_void_p), ("out_classes", c_void_p),
         ("out_anchor", c_void_p), ("out_keep", c_void_p), ("out_count", c_void_p),
         ("out_candidates", c_void_p), ("workspace", c_void_p), ("workspace_bytes", c_size_t),
+        ("sim_workspace", c_void_p), ("sim_workspace_bytes", c_size_t),
     ]
 
 
@@ -54,6 +55,11 @@ PROTOTYPES = {
                                        POINTER(c_int64), c_int, c_int64, c_int64, c_void_p, c_int64,
                                        c_int, c_float, c_float, c_void_p, c_int, c_int64,
                                        c_void_p, c_void_p, c_void_p, c_void_p]),
+    "ovdet_similarity_split_workspace_bytes": (c_size_t, [c_int64, c_int64]),
+    "ovdet_similarity_fused_ws": (c_int, [POINTER(c_void_p), POINTER(c_int64), POINTER(c_int64),
+                                          POINTER(c_int64), c_int, c_int64, c_int64, c_void_p, c_int64,
+                                          c_int, c_float, c_float, c_void_p, c_void_p, c_void_p,
+                                          c_void_p, c_size_t, c_int, c_void_p]),
     "ovdet_similarity_fused_bf16in": (c_int, [POINTER(c_void_p), POINTER(c_int64), POINTER(c_int64),
                                               POINTER(c_int64), c_int, c_int64, c_int64, c_void_p, c_int64,
                                               c_int, c_float, c_float, c_void_p, c_int, c_int64,

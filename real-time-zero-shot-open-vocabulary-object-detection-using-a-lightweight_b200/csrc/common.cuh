@@ -40,7 +40,7 @@ int fused_launch(const float* const* obj_embeds, const int64_t* hw, const int64_
                  const void* text_op, const void* const* level_ops, int64_t classes, int text_batched,
                  int normalize, int split3, float alpha, float beta, void* logits, int logits_dtype,
                  int64_t ldc, float* row_max, int32_t* row_arg, float* inv_norm, void* stream,
-                 int in_bf16 = 0);
+                 int in_bf16 = 0, void* split_ws = nullptr, size_t split_ws_bytes = 0);
 
 inline cudaStream_t as_stream(void* s) { return reinterpret_cast<cudaStream_t>(s); }
 

@@ -121,6 +121,13 @@ struct FusedParams {
   float* row_max;
   int* row_arg;
   float* inv_norm;
+  // Small launches (fewer anchor tiles than CTA pairs): the class tiles of an anchor tile are split
+  // over `nsplit` work items; each writes its partial (max, argmax) and the last one to arrive
+  // (per 32-row group, counted with an atomic) merges them.  Scratch is caller memory.
+  int nsplit;
+  float* part_max;                 // [nsplit, batch * anchors]
+  int* part_arg;                   // [nsplit, batch * anchors]
+  int* part_count;                 // [tiles * 4], zero on entry, left zero
   int dbg;
 };
 
@@ -231,6 +238,8 @@ sim_fused_kernel(const __grid_constant__ LevelMaps amaps, const __grid_constant_
   const unsigned lazy_ns = (p.dbg & 16) ? 0u : ((p.dbg & 32) ? 256u : 64u);   // back-off of the non-critical waits
   const int total_tiles = p.tile_start[p.levels];
   const int total_pairs = (total_tiles + CG - 1) / CG;
+  const int NSPLIT = p.nsplit;                                   // >= 1
+  const int total_work = total_pairs * NSPLIT;
   // barriers of the leader CTA that both CTAs arrive on (shared::cluster addresses)
   const uint32_t lead_b_full0 = CG == 2 ? ptx::map_to_cta(b_full0, 0) : b_full0;
   const uint32_t lead_a_ready0 = CG == 2 ? ptx::map_to_cta(a_ready0, 0) : a_ready0;
@@ -265,12 +274,14 @@ sim_fused_kernel(const __grid_constant__ LevelMaps amaps, const __grid_constant_
     // ================================ text (B) producer ======================================
     const uint32_t issue = ptx::elect_one();
     uint32_t g = 0;                                    // N tiles produced so far
-    for (int pair = pair0; pair < total_pairs; pair += pair_stride) {
-      const int tile = pair * CG + (int)rank;
+    for (int w = pair0; w < total_work; w += pair_stride) {
+      const int tile = (w / NSPLIT) * CG + (int)rank;
+      const int nt_b = (w % NSPLIT) * NT / NSPLIT, nt_e = (w % NSPLIT + 1) * NT / NSPLIT;
+      (void)nt_b; (void)nt_e;
       const TileCoord tc = decode_tile(p, tile);
       const int tb = p.text_batched ? tc.b : 0;
       const CUtensorMap* bmap = &bmaps.m[PROJ ? tc.level : 0];
-      for (int nt = 0; nt < NT; ++nt, ++g) {
+      for (int nt = nt_b; nt < nt_e; ++nt, ++g) {
         const int row0 = ntile_row0(nt);
         const int n_half = ntile_nsize(nt) >> 1;
         (void)n_half;
@@ -304,12 +315,13 @@ sim_fused_kernel(const __grid_constant__ LevelMaps amaps, const __grid_constant_
     const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem_base, 0);
     const uint32_t smem_b_u = __shfl_sync(0xffffffffu, smem_b, 0);
     uint32_t g = 0, lt = 0;
-    for (int pair = pair0; pair < total_pairs; pair += pair_stride, ++lt) {
-      for (int nt = 0; nt < NT; ++nt, ++g) {
+    for (int w = pair0; w < total_work; w += pair_stride, ++lt) {
+      const int nt_b = (w % NSPLIT) * NT / NSPLIT, nt_e = (w % NSPLIT + 1) * NT / NSPLIT;
+      for (int nt = nt_b; nt < nt_e; ++nt, ++g) {
         const int n_size = ntile_nsize(nt);
         const uint32_t idesc = ptx::umma_idesc_bf16_f32(F_BLOCK_M * CG, (uint32_t)n_size);
         const uint32_t as = g & 1u;
-        const bool first_nt = nt == 0, last_nt = nt == NT - 1;
+        const bool first_nt = nt == nt_b, last_nt = nt == nt_e - 1;
         const uint32_t it0 = g * (uint32_t)NSTAGE;
         // peek at the first text stage while waiting for the accumulator to drain
         bool ready = ptx::mbar_try_wait(b_full0 + 8u * (it0 % F_B_STAGES), (it0 / F_B_STAGES) & 1u);
@@ -361,8 +373,10 @@ sim_fused_kernel(const __grid_constant__ LevelMaps amaps, const __grid_constant_
     // ================================ activation (A) producer ================================
     const uint32_t issue = ptx::elect_one();
     uint32_t ia = 0;
-    for (int pair = pair0; pair < total_pairs; pair += pair_stride) {
-      const int tile = pair * CG + (int)rank;
+    for (int w = pair0; w < total_work; w += pair_stride) {
+      const int tile = (w / NSPLIT) * CG + (int)rank;
+      const int nt_b = (w % NSPLIT) * NT / NSPLIT, nt_e = (w % NSPLIT + 1) * NT / NSPLIT;
+      (void)nt_b; (void)nt_e;
       const TileCoord tc = decode_tile(p, tile);
       const CUtensorMap* map = &amaps.m[tc.level];
 #pragma unroll
@@ -383,14 +397,16 @@ sim_fused_kernel(const __grid_constant__ LevelMaps amaps, const __grid_constant_
     // SM's TMA path (measured 2.25 ms with it vs 2.14 ms without, single-CTA kernel), so it is off.
     const uint32_t issue = ptx::elect_one();
     uint32_t lt = 0;
-    for (int pair = pair0; pair < total_pairs; pair += pair_stride, ++lt) {
-      const int tile = pair * CG + (int)rank;
+    for (int w = pair0; w < total_work; w += pair_stride, ++lt) {
+      const int tile = (w / NSPLIT) * CG + (int)rank;
+      const int nt_b = (w % NSPLIT) * NT / NSPLIT, nt_e = (w % NSPLIT + 1) * NT / NSPLIT;
+      (void)nt_b; (void)nt_e;
       const int next = tile + pair_stride * CG;
       if (next >= total_tiles || !(p.dbg & 1)) break;       // off unless OVDET_DBG bit 0 is set
       if (CG == 1 && (p.dbg & 4)) {
         ptx::mbar_wait(a_ready0, lt & 1u);
       } else {                                         // the current tile's first N tile is done
-        const uint32_t g0 = lt * (uint32_t)NT;
+        const uint32_t g0 = lt * (uint32_t)NT;     // (prefetch experiment: only meaningful with nsplit == 1)
         ptx::mbar_wait(t_full0 + 8u * (g0 & 1u), (g0 >> 1) & 1u);
       }
       const TileCoord tc = decode_tile(p, next);
@@ -414,8 +430,10 @@ sim_fused_kernel(const __grid_constant__ LevelMaps amaps, const __grid_constant_
       ptx::tc_fence_before();
     }
     uint32_t ia = 0, lt = 0;
-    for (int pair = pair0; pair < total_pairs; pair += pair_stride, ++lt) {
-      const int tile = pair * CG + (int)rank;
+    for (int w = pair0; w < total_work; w += pair_stride, ++lt) {
+      const int tile = (w / NSPLIT) * CG + (int)rank;
+      const int nt_b = (w % NSPLIT) * NT / NSPLIT, nt_e = (w % NSPLIT + 1) * NT / NSPLIT;
+      (void)nt_b; (void)nt_e;
       const TileCoord tc = decode_tile(p, tile);
       float ss0 = 0.f, ss1 = 0.f, ss2 = 0.f, ss3 = 0.f;
       // block `t` of the A region: wait until the previous tile's MMAs have read it, store, publish
@@ -483,8 +501,10 @@ sim_fused_kernel(const __grid_constant__ LevelMaps amaps, const __grid_constant_
     float* stage = epi_stage + lg * 32 * F_VPITCH;
     const bool want_max = p.row_max != nullptr;
     uint32_t acc_it = 0, lt = 0;
-    for (int pair = pair0; pair < total_pairs; pair += pair_stride, ++lt) {
-      const int tile = pair * CG + (int)rank;
+    for (int w = pair0; w < total_work; w += pair_stride, ++lt) {
+      const int tile = (w / NSPLIT) * CG + (int)rank;
+      const int nt_b = (w % NSPLIT) * NT / NSPLIT, nt_e = (w % NSPLIT + 1) * NT / NSPLIT;
+      (void)nt_b; (void)nt_e;
       const TileCoord tc = decode_tile(p, tile);
       const int r_in_tile = lg * 32 + lane;
       const bool row_ok = r_in_tile < tc.rows;
@@ -508,7 +528,7 @@ sim_fused_kernel(const __grid_constant__ LevelMaps amaps, const __grid_constant_
       const bool raw_mode = PROJ || (want_max && p.logits == nullptr && p.alpha >= 0.f && !(p.dbg & 2));
       const bool max_only = raw_mode && p.row_arg == nullptr;
       float raw_best = -INFINITY;
-      for (int nt = 0; nt < NT; ++nt, ++acc_it) {
+      for (int nt = nt_b; nt < nt_e; ++nt, ++acc_it) {
         const int n0 = (nt - NG) * F_BLOCK_N;          // first class of a class tile
         const int n_valid = ntile_valid(nt);
         const int nchunks = (n_valid + 31) >> 5;
@@ -714,7 +734,42 @@ sim_fused_kernel(const __grid_constant__ LevelMaps amaps, const __grid_constant_
           else ptx::mbar_arrive(t_empty0 + 8u * as);
         }
       }
-      if (PROJ) {
+      if (!PROJ && NSPLIT > 1) {
+        // partial result of this class range -> scratch; the last part to arrive merges
+        float best = bv[0];
+        int best_idx = bi[0];
+#pragma unroll
+        for (int qd = 1; qd < 4; ++qd)
+          if (bv[qd] > best || (bv[qd] == best && bi[qd] < best_idx)) { best = bv[qd]; best_idx = bi[qd]; }
+        if (max_only) best = raw_best;
+        if (raw_mode) best = fmaf(scale, best, beta);
+        const int part = w % NSPLIT;
+        const long long rows_total = (long long)p.batch * p.anchors;
+        if (row_ok) {
+          p.part_max[part * rows_total + grow] = best;
+          p.part_arg[part * rows_total + grow] = best_idx;
+        }
+        __threadfence();
+        __syncwarp();
+        int last = 0;
+        if (lane == 0) last = atomicAdd(p.part_count + tile * 4 + lg, 1) == NSPLIT - 1;
+        last = __shfl_sync(0xffffffffu, last, 0);
+        if (last) {
+          __threadfence();
+          if (row_ok) {
+            float m = -INFINITY;
+            int mi = 0;
+            for (int q2 = 0; q2 < NSPLIT; ++q2) {             // class ranges ascend with the part index
+              const float v = __ldcg(p.part_max + q2 * rows_total + grow);
+              const int vi = __ldcg(p.part_arg + q2 * rows_total + grow);
+              if (v > m) { m = v; mi = vi; }
+            }
+            p.row_max[grow] = m;
+            if (p.row_arg != nullptr) p.row_arg[grow] = mi;
+          }
+          if (lane == 0) p.part_count[tile * 4 + lg] = 0;      // ready for the next launch
+        }
+      } else if (PROJ) {
         float best = bv[0];
         int best_idx = bi[0];
 #pragma unroll
@@ -780,7 +835,7 @@ int fused_launch(const float* const* obj_embeds, const int64_t* hw, const int64_
                  const void* text_op, const void* const* level_ops, int64_t classes, int text_batched,
                  int normalize, int split3, float alpha, float beta, void* logits, int logits_dtype,
                  int64_t ldc, float* row_max, int32_t* row_arg, float* inv_norm, void* stream,
-                 int in_bf16) {
+                 int in_bf16, void* split_ws, size_t split_ws_bytes) {
   const int proj = level_ops != nullptr;
   if (in_bf16 && (proj || split3)) return OVDET_ERR_UNSUPPORTED_SHAPE;   // bf16 activations: cosine mode only
   if (batch == 0) return check_device();            // an empty batch is a no-op (its pointers may be null)
@@ -882,6 +937,23 @@ int fused_launch(const float* const* obj_embeds, const int64_t* hw, const int64_
   p.row_max = row_max;
   p.row_arg = row_arg;
   p.inv_norm = inv_norm;
+  // small launch: split the class tiles of every anchor tile over the idle CTA pairs
+  p.nsplit = 1;
+  if (cg == 2 && !proj && !split3 && !logits && row_max && split_ws && !((uintptr_t)split_ws & 15)) {
+    const long long pairs = (tiles + 1) / 2;
+    const long long max_pairs = sm_count() / 2;
+    long long ns = pairs > 0 ? max_pairs / pairs : 1;
+    if (ns > 4) ns = 4;
+    if (ns > p.n_tiles) ns = p.n_tiles;
+    const long long rows = (long long)batch * anchors;
+    const size_t need = (size_t)ns * rows * 8 + (size_t)(tiles + 2) * 16;
+    if (ns >= 2 && split_ws_bytes >= need) {
+      p.nsplit = (int)ns;
+      p.part_count = static_cast<int*>(split_ws);                       // zero on entry, left zero
+      p.part_max = reinterpret_cast<float*>(static_cast<char*>(split_ws) + (size_t)(tiles + 2) * 16);
+      p.part_arg = reinterpret_cast<int*>(p.part_max + ns * rows);
+    }
+  }
   // experiment switches: 1 L2 prefetch warp on, 2 no raw-accumulator
   // epilogue, 16 / 32 back-off of the non-critical waits off / 256 ns
   static const int dbg_env = []() { const char* e = getenv("OVDET_DBG"); return e ? atoi(e) : 0; }();
@@ -899,7 +971,7 @@ int fused_launch(const float* const* obj_embeds, const int64_t* hw, const int64_
   }
   if (cg == 2) {
     // one CTA per SM, launched as clusters of two (the pair shares a TPC)
-    const long long pairs = (tiles + 1) / 2;
+    const long long pairs = (tiles + 1) / 2 * p.nsplit;                // work items
     const int max_pairs = sm_count() / 2;
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3((unsigned)(2 * (pairs < max_pairs ? pairs : max_pairs)));
@@ -943,7 +1015,29 @@ extern "C" int ovdet_similarity_fused(const float* const* obj_embeds, const int6
   if (dim % 64 != 0) return OVDET_ERR_UNSUPPORTED_SHAPE;   // the text operand has exactly `dim` columns
   return ovdet::fused_launch(obj_embeds, hw, stride_b, stride_d, num_levels, batch, dim, text_op, nullptr,
                              classes, text_batched, /*normalize=*/1, /*split3=*/0, alpha, beta, logits,
-                             logits_dtype, ldc, row_max, row_arg, inv_norm, stream, 0);
+                             logits_dtype, ldc, row_max, row_arg, inv_norm, stream, 0, nullptr, 0);
+}
+
+extern "C" size_t ovdet_similarity_split_workspace_bytes(int64_t batch, int64_t anchors) {
+  // scratch of the small-launch class split: worth having when batch * anchors fits half the CTA pairs
+  if (batch <= 0 || anchors <= 0) return 0;
+  const long long rows = (long long)batch * anchors;
+  const long long tiles = batch * ((anchors + 127) / 128 + 8);
+  if (tiles / 2 > 74 / 2) return 0;
+  return (size_t)4 * rows * 8 + (size_t)(tiles + 2) * 16 + 16;
+}
+
+extern "C" int ovdet_similarity_fused_ws(const float* const* obj_embeds, const int64_t* hw,
+                                         const int64_t* stride_b, const int64_t* stride_d,
+                                         int num_levels, int64_t batch, int64_t dim,
+                                         const void* text_op, int64_t classes, int text_batched,
+                                         float alpha, float beta, float* row_max, int32_t* row_arg,
+                                         float* inv_norm, void* workspace, size_t workspace_bytes,
+                                         int embed_dtype, void* stream) {
+  if (dim % 64 != 0) return OVDET_ERR_UNSUPPORTED_SHAPE;
+  return ovdet::fused_launch(obj_embeds, hw, stride_b, stride_d, num_levels, batch, dim, text_op, nullptr,
+                             classes, text_batched, 1, 0, alpha, beta, nullptr, OVDET_F32, classes, row_max,
+                             row_arg, inv_norm, stream, embed_dtype == OVDET_BF16, workspace, workspace_bytes);
 }
 
 extern "C" int ovdet_similarity_fused_bf16in(const void* const* obj_embeds, const int64_t* hw,
@@ -956,7 +1050,7 @@ extern "C" int ovdet_similarity_fused_bf16in(const void* const* obj_embeds, cons
   if (dim % 64 != 0) return OVDET_ERR_UNSUPPORTED_SHAPE;
   return ovdet::fused_launch(reinterpret_cast<const float* const*>(obj_embeds), hw, stride_b, stride_d,
                              num_levels, batch, dim, text_op, nullptr, classes, text_batched, 1, 0, alpha,
-                             beta, logits, logits_dtype, ldc, row_max, row_arg, inv_norm, stream, 1);
+                             beta, logits, logits_dtype, ldc, row_max, row_arg, inv_norm, stream, 1, nullptr, 0);
 }
 
 extern "C" int ovdet_similarity_fused_fp32(const float* const* obj_embeds, const int64_t* hw,
@@ -969,7 +1063,7 @@ extern "C" int ovdet_similarity_fused_fp32(const float* const* obj_embeds, const
   if (dim % 64 != 0) return OVDET_ERR_UNSUPPORTED_SHAPE;
   return ovdet::fused_launch(obj_embeds, hw, stride_b, stride_d, num_levels, batch, dim, text_op3, nullptr,
                              classes, text_batched, /*normalize=*/1, /*split3=*/1, alpha, beta, logits,
-                             logits_dtype, ldc, row_max, row_arg, inv_norm, stream, 0);
+                             logits_dtype, ldc, row_max, row_arg, inv_norm, stream, 0, nullptr, 0);
 }
 
 extern "C" int ovdet_similarity_projected(const float* const* hidden, const int64_t* hw,
@@ -981,5 +1075,5 @@ extern "C" int ovdet_similarity_projected(const float* const* hidden, const int6
   if (!level_ops) return OVDET_ERR_INVALID_ARG;
   return ovdet::fused_launch(hidden, hw, stride_b, stride_d, num_levels, batch, hidden_dim, nullptr, level_ops,
                              classes, text_batched, /*normalize=*/1, /*split3=*/0, alpha, beta, nullptr,
-                             OVDET_F32, classes, row_max, row_arg, inv_norm, stream, 0);
+                             OVDET_F32, classes, row_max, row_arg, inv_norm, stream, 0, nullptr, 0);
 }

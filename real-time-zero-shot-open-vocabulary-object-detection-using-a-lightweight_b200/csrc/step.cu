@@ -14,17 +14,10 @@ extern "C" int ovdet_head_step(const ovdet_head_step_args* a, void* stream) {
     hw[l] = (int64_t)a->heights[l] * a->widths[l];
     anchors += hw[l];
   }
-  int rc;
-  if (a->embed_dtype == OVDET_BF16)
-    rc = ovdet_similarity_fused_bf16in(a->obj_embeds, hw, a->emb_stride_b, a->emb_stride_d, a->num_levels,
-                                       a->batch, a->dim, a->text_op, a->classes, a->text_batched, a->alpha,
-                                       a->beta, nullptr, OVDET_F32, a->classes, a->scores, a->class_ids,
-                                       a->inv_norm, stream);
-  else
-    rc = ovdet_similarity_fused(reinterpret_cast<const float* const*>(a->obj_embeds), hw, a->emb_stride_b,
-                                a->emb_stride_d, a->num_levels, a->batch, a->dim, a->text_op, a->classes,
-                                a->text_batched, a->alpha, a->beta, nullptr, OVDET_F32, a->classes,
-                                a->scores, a->class_ids, a->inv_norm, stream);
+  int rc = ovdet_similarity_fused_ws(reinterpret_cast<const float* const*>(a->obj_embeds), hw, a->emb_stride_b,
+                                     a->emb_stride_d, a->num_levels, a->batch, a->dim, a->text_op, a->classes,
+                                     a->text_batched, a->alpha, a->beta, a->scores, a->class_ids, a->inv_norm,
+                                     a->sim_workspace, a->sim_workspace_bytes, a->embed_dtype, stream);
   if (rc != OVDET_OK) return rc;
   rc = ovdet_decode_filter(a->box_preds, a->heights, a->widths, a->strides, a->box_stride_b,
                            a->num_levels, a->bins, a->batch, 1.0f, 1.0f, a->scores, a->conf,

@@ -244,6 +244,11 @@ class HeadPipeline:
             a.out_anchor, a.out_keep = r.anchor.data_ptr(), r.keep.data_ptr()
             a.out_count, a.out_candidates = r.count.data_ptr(), r.candidates.data_ptr()
             a.workspace, a.workspace_bytes = self.workspace.data_ptr(), self.workspace.numel()
+            # small launches (batch 1): zeroed scratch for the class split of the similarity kernel
+            need = _cabi.lib().ovdet_similarity_split_workspace_bytes(self.batch, self.anchors)
+            if need:
+                self._sim_ws = torch.zeros(need, device=self.device, dtype=torch.uint8)
+                a.sim_workspace, a.sim_workspace_bytes = self._sim_ws.data_ptr(), need
             self._step_args = a
         for l, (e, p) in enumerate(zip(obj_embeds, box_preds)):
             a.obj_embeds[l], a.box_preds[l] = e.data_ptr(), p.data_ptr()

