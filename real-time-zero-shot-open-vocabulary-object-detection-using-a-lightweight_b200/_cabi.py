@@ -106,12 +106,17 @@ def lib() -> ctypes.CDLL:
     """Load (once) and return the library; raise loudly when it has not been built."""
     global _lib
     if _lib is None:
-        if not os.path.exists(LIB_PATH):
+        if not os.path.exists(LIB_PATH) and not os.environ.get("OVDET_LIB_PATH"):
             raise RuntimeError(
                 f"{LIB_PATH} is missing: build it with `python -m ovdet.build` (nvcc, sm_100a). "
                 "ovdet has no CPU/PyTorch fallback.")
-        handle = ctypes.CDLL(LIB_PATH)
+        # OVDET_LIB_PATH: A/B tooling only (tools/ab): load another build of the same library; symbols
+        # it does not have yet are skipped
+        override = os.environ.get("OVDET_LIB_PATH")
+        handle = ctypes.CDLL(override or LIB_PATH)
         for name, (restype, argtypes) in PROTOTYPES.items():
+            if override and not hasattr(handle, name):
+                continue
             fn = getattr(handle, name)        # AttributeError if the ABI drifted
             fn.restype = restype
             fn.argtypes = argtypes
