@@ -234,9 +234,9 @@ def run_ours(args):
         inp = synth.make_inputs(batch=batch, image_size=IMAGE_SIZE, num_classes=NUM_CLASSES,
                                 embed_dim=EMBED_DIM, device=dev, seed=1234 + rank)
     if args.input_dtype == "bf16":
-        # the head convolutions ran under autocast: bf16 region embeddings (box logits stay fp32)
-        inp = SimpleNamespace(obj_embeds=[e.to(torch.bfloat16) for e in inp.obj_embeds], box_preds=inp.box_preds,
-                              text=inp.text)
+        # the head convolutions ran under autocast: bf16 region embeddings and box logits
+        inp = SimpleNamespace(obj_embeds=[e.to(torch.bfloat16) for e in inp.obj_embeds],
+                              box_preds=[b.to(torch.bfloat16) for b in inp.box_preds], text=inp.text)
     pipe = HeadPipeline(batch, shapes, NUM_CLASSES, cfg, device=dev, projections=projections)
     # the vocabulary is replicated: rank 0's copy goes to every GPU once, outside the timed region
     vocab = shard.broadcast_vocabulary(inp.text if rank == 0 else None, NUM_CLASSES, EMBED_DIM, dev)
@@ -332,7 +332,8 @@ def run_ours(args):
             one = synth.make_inputs(batch=1, image_size=IMAGE_SIZE, num_classes=NUM_CLASSES,
                                     embed_dim=EMBED_DIM, device=dev, seed=77)
             if args.input_dtype == "bf16":
-                one = SimpleNamespace(obj_embeds=[e.to(torch.bfloat16) for e in one.obj_embeds], box_preds=one.box_preds)
+                one = SimpleNamespace(obj_embeds=[e.to(torch.bfloat16) for e in one.obj_embeds],
+                                      box_preds=[b.to(torch.bfloat16) for b in one.box_preds])
         pipe1 = HeadPipeline(1, shapes, NUM_CLASSES, cfg, device=dev, projections=projections)
         pipe1.set_vocabulary(inp.text)
         lat = []

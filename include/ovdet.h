@@ -234,6 +234,15 @@ OVDET_API int ovdet_decode_filter(const float* const* box_preds, const int32_t* 
                         const float* scores, float conf, int activation,
                         float* boxes, float* scores_act, uint32_t* pass_mask, void* stream);
 
+/* K3 for bf16 box logits (the head ran under autocast): same arguments, box_preds[l] is bf16
+ * [batch, 4 * bins, h, w]; the softmax expectation and the decode run in fp32. */
+OVDET_API int ovdet_decode_filter_bf16in(const void* const* box_preds, const int32_t* heights,
+                        const int32_t* widths, const int32_t* strides,
+                        const int64_t* batch_strides, int num_levels, int bins,
+                        int64_t batch, float width_scale, float height_scale,
+                        const float* scores, float conf, int activation,
+                        float* boxes, float* scores_act, uint32_t* pass_mask, void* stream);
+
 /* ------------------------------------------------------------------------------------------
  * K4  per-image candidate gather, rescale/clip, sort, greedy NMS.
  * Replaces: inference/detector.py:185-208 (mask, boxes/scale, clip, _nms :225-256,
@@ -344,7 +353,7 @@ typedef struct ovdet_head_step_args {
   int32_t bins;                    /* reg_max + 1 */
   int64_t batch, dim, classes;
   const void* obj_embeds[4];       /* fp32 or bf16 (embed_dtype) [batch, dim, h, w] per level */
-  const float* box_preds[4];       /* fp32 [batch, 4 * bins, h, w] per level */
+  const void* box_preds[4];        /* fp32 or bf16 (box_dtype) [batch, 4 * bins, h, w] per level */
   int32_t heights[4], widths[4], strides[4];
   int64_t emb_stride_b[4], emb_stride_d[4], box_stride_b[4];
   const void* text_op;             /* bf16 [text_batch, classes, dim], unit-norm rows */
@@ -352,6 +361,7 @@ typedef struct ovdet_head_step_args {
   int32_t activation;              /* ovdet_activation */
   int32_t class_aware, topk;
   int32_t embed_dtype;             /* ovdet_dtype of obj_embeds: OVDET_F32 or OVDET_BF16 */
+  int32_t box_dtype;               /* ovdet_dtype of box_preds */
   float alpha, beta, conf, iou_thr;
   int64_t max_det;
   float* scores;                   /* out, also K3/K4 input */

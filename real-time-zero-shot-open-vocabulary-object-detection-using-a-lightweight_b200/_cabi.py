@@ -27,6 +27,7 @@ class HeadStepArgs(ctypes.Structure):
         ("emb_stride_b", c_int64 * 4), ("emb_stride_d", c_int64 * 4), ("box_stride_b", c_int64 * 4),
         ("text_op", c_void_p), ("text_batched", c_int32), ("activation", c_int32),
         ("class_aware", c_int32), ("topk", c_int32), ("embed_dtype", c_int32),
+        ("box_dtype", c_int32),
         ("alpha", c_float), ("beta", c_float), ("conf", c_float), ("iou_thr", c_float),
         ("max_det", c_int64),
         ("scores", c_void_p), ("class_ids", c_void_p), ("inv_norm", c_void_p), ("boxes", c_void_p),
@@ -77,6 +78,10 @@ PROTOTYPES = {
                                     POINTER(c_int32), POINTER(c_int64), c_int, c_int, c_int64,
                                     c_float, c_float, c_void_p, c_float, c_int,
                                     c_void_p, c_void_p, c_void_p, c_void_p]),
+    "ovdet_decode_filter_bf16in": (c_int, [POINTER(c_void_p), POINTER(c_int32), POINTER(c_int32),
+                                           POINTER(c_int32), POINTER(c_int64), c_int, c_int, c_int64,
+                                           c_float, c_float, c_void_p, c_float, c_int,
+                                           c_void_p, c_void_p, c_void_p, c_void_p]),
     "ovdet_nms_workspace_bytes": (c_size_t, [c_int64, c_int64]),
     "ovdet_nms_batched": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int64,
                                   c_void_p, c_void_p, c_float, c_int, c_int, c_int64,

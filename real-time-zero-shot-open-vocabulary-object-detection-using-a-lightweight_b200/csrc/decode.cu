@@ -12,7 +12,7 @@
 namespace ovdet {
 
 struct DecodeParams {
-  const float* pred[OVDET_MAX_LEVELS];
+  const void* pred[OVDET_MAX_LEVELS];      // fp32 or bf16 (template parameter T of the kernel)
   long long bstride[OVDET_MAX_LEVELS];
   int h[OVDET_MAX_LEVELS], w[OVDET_MAX_LEVELS], stride[OVDET_MAX_LEVELS];
   int off[OVDET_MAX_LEVELS + 1];       // anchor offset of each level; off[levels] = anchors
@@ -36,18 +36,34 @@ __device__ __forceinline__ float exp_rel(float x, float neg_m_log2e) {
   return r;
 }
 
-template <int BINS, int V>
-__device__ __forceinline__ void dfl_expectation(const float* __restrict__ p, long long cstride,
+// Typed streaming loads: the box logits are fp32 (the reference's convolutions) or bf16 (the head ran
+// under autocast); the arithmetic is fp32 either way.
+__device__ __forceinline__ float ld1(const float* p) { return ld_stream_f32(p); }
+__device__ __forceinline__ float ld1(const __nv_bfloat16* p) {
+  unsigned short u;
+  asm volatile("ld.global.nc.L1::no_allocate.u16 %0, [%1];" : "=h"(u) : "l"(p));
+  return __uint_as_float((uint32_t)u << 16);
+}
+__device__ __forceinline__ float4 ld4(const float* p) { return ld_stream_f32x4(reinterpret_cast<const float4*>(p)); }
+__device__ __forceinline__ float4 ld4(const __nv_bfloat16* p) {                 // 8-byte aligned
+  uint32_t a, b;
+  asm volatile("ld.global.nc.L1::no_allocate.v2.u32 {%0,%1}, [%2];" : "=r"(a), "=r"(b) : "l"(p));
+  return make_float4(__uint_as_float(a << 16), __uint_as_float(a & 0xffff0000u),
+                     __uint_as_float(b << 16), __uint_as_float(b & 0xffff0000u));
+}
+
+template <int BINS, int V, typename T>
+__device__ __forceinline__ void dfl_expectation(const T* __restrict__ p, long long cstride,
                                                 int bins_rt, float (&e)[V]) {
   if (BINS > 0) {
     float v[BINS > 0 ? BINS : 1][V];
 #pragma unroll
     for (int k = 0; k < BINS; ++k) {
       if (V == 4) {
-        const float4 q = ld_stream_f32x4(reinterpret_cast<const float4*>(p + k * cstride));
+        const float4 q = ld4(p + k * cstride);
         v[k][0] = q.x; v[k][1 % V] = q.y; v[k][2 % V] = q.z; v[k][3 % V] = q.w;
       } else {
-        v[k][0] = ld_stream_f32(p + k * cstride);
+        v[k][0] = ld1(p + k * cstride);
       }
     }
 #pragma unroll
@@ -69,11 +85,11 @@ __device__ __forceinline__ void dfl_expectation(const float* __restrict__ p, lon
 #pragma unroll
     for (int j = 0; j < V; ++j) {
       float m = -INFINITY;
-      for (int k = 0; k < bins_rt; ++k) m = fmaxf(m, p[k * cstride + j]);
+      for (int k = 0; k < bins_rt; ++k) m = fmaxf(m, ld1(p + k * cstride + j));
       const float nm = -m * kLog2e;
       float s = 0.f, n = 0.f;
       for (int k = 0; k < bins_rt; ++k) {
-        const float t = exp_rel(p[k * cstride + j], nm);
+        const float t = exp_rel(ld1(p + k * cstride + j), nm);
         s += t;
         n = fmaf((float)k, t, n);
       }
@@ -84,14 +100,14 @@ __device__ __forceinline__ void dfl_expectation(const float* __restrict__ p, lon
 
 // Latency variant for small launches (batch 1): one anchor per thread, all 4 x BINS loads issued
 // before any arithmetic, so the kernel pays one memory round trip instead of four.
-template <int BINS>
-__device__ __forceinline__ void dfl_expectation4_hoisted(const float* __restrict__ p, long long cstride,
+template <int BINS, typename T>
+__device__ __forceinline__ void dfl_expectation4_hoisted(const T* __restrict__ p, long long cstride,
                                                          float (&e)[4]) {
   float v[4][BINS];
 #pragma unroll
   for (int c = 0; c < 4; ++c)
 #pragma unroll
-    for (int k = 0; k < BINS; ++k) v[c][k] = ld_stream_f32(p + (long long)(c * BINS + k) * cstride);
+    for (int k = 0; k < BINS; ++k) v[c][k] = ld1(p + (long long)(c * BINS + k) * cstride);
 #pragma unroll
   for (int c = 0; c < 4; ++c) {
     float m = v[c][0];
@@ -112,7 +128,7 @@ __device__ __forceinline__ void dfl_expectation4_hoisted(const float* __restrict
 // V = 4: a thread decodes 4 consecutive cells of one level with 16-byte loads (every level's
 // H*W and batch stride must be a multiple of 4 and the pointers 16-byte aligned); V = 1 is the
 // general path.  blockIdx.y = image.
-template <int BINS, int V, bool HOIST = false>
+template <int BINS, int V, bool HOIST = false, typename T = float>
 __global__ void __launch_bounds__(256)
 decode_filter_kernel(const DecodeParams p, int anchors, const float* __restrict__ scores,
                      float conf, int activation, float* __restrict__ boxes,
@@ -128,18 +144,18 @@ decode_filter_kernel(const DecodeParams p, int anchors, const float* __restrict_
     const int cell = a - p.off[l];
     const int wdt = p.w[l];
     const long long cstride = (long long)p.h[l] * wdt;
-    const float* base = p.pred[l] + b * p.bstride[l] + cell;
+    const T* base = static_cast<const T*>(p.pred[l]) + b * p.bstride[l] + cell;
     const int bins = p.bins;
     float e0[V], e1[V], e2[V], e3[V];
     if constexpr (HOIST && V == 1 && BINS > 0) {
       float e[4];
-      dfl_expectation4_hoisted<BINS>(base, cstride, e);
+      dfl_expectation4_hoisted<BINS, T>(base, cstride, e);
       e0[0] = e[0]; e1[0] = e[1]; e2[0] = e[2]; e3[0] = e[3];
     } else {
-      dfl_expectation<BINS, V>(base, cstride, bins, e0);
-      dfl_expectation<BINS, V>(base + 1ll * bins * cstride, cstride, bins, e1);
-      dfl_expectation<BINS, V>(base + 2ll * bins * cstride, cstride, bins, e2);
-      dfl_expectation<BINS, V>(base + 3ll * bins * cstride, cstride, bins, e3);
+      dfl_expectation<BINS, V, T>(base, cstride, bins, e0);
+      dfl_expectation<BINS, V, T>(base + 1ll * bins * cstride, cstride, bins, e1);
+      dfl_expectation<BINS, V, T>(base + 2ll * bins * cstride, cstride, bins, e2);
+      dfl_expectation<BINS, V, T>(base + 3ll * bins * cstride, cstride, bins, e3);
     }
     const float st = (float)p.stride[l];
     const long long ga = (long long)b * anchors + a;
@@ -196,7 +212,7 @@ decode_filter_kernel(const DecodeParams p, int anchors, const float* __restrict_
 
 }  // namespace ovdet
 
-extern "C" int ovdet_decode_filter(const float* const* box_preds, const int32_t* heights,
+static int decode_launch(int in_bf16, const void* const* box_preds, const int32_t* heights,
                                    const int32_t* widths, const int32_t* strides,
                                    const int64_t* batch_strides, int num_levels, int bins,
                                    int64_t batch, float width_scale, float height_scale,
@@ -237,19 +253,30 @@ extern "C" int ovdet_decode_filter(const float* const* box_preds, const int32_t*
   bool vec4 = bins == 17 && !(((uintptr_t)scores | (uintptr_t)scores_act) & 15);
   for (int l = 0; l < num_levels && vec4; ++l)
     vec4 = ((long long)heights[l] * widths[l]) % 4 == 0 && batch_strides[l] % 4 == 0 &&
-           !((uintptr_t)box_preds[l] & 15);
+           !((uintptr_t)box_preds[l] & (in_bf16 ? 7 : 15));
   if (bins == 17 && (long long)anchors * batch <= 65536) {
     // small launch: latency matters, not bandwidth
     dim3 grid((unsigned)ceil_div(anchors, 256), (unsigned)batch);
-    decode_filter_kernel<17, 1, true><<<grid, 256, 0, s>>>(p, anchors, scores, conf, activation, boxes,
-                                                           scores_act, pass_mask, words);
+    if (in_bf16)
+      decode_filter_kernel<17, 1, true, __nv_bfloat16><<<grid, 256, 0, s>>>(p, anchors, scores, conf, activation,
+                                                                            boxes, scores_act, pass_mask, words);
+    else
+      decode_filter_kernel<17, 1, true><<<grid, 256, 0, s>>>(p, anchors, scores, conf, activation, boxes,
+                                                             scores_act, pass_mask, words);
   } else if (vec4) {
     dim3 grid((unsigned)ceil_div(anchors, 1024), (unsigned)batch);
-    decode_filter_kernel<17, 4><<<grid, 256, 0, s>>>(p, anchors, scores, conf, activation, boxes,
-                                                     scores_act, pass_mask, words);
+    if (in_bf16)
+      decode_filter_kernel<17, 4, false, __nv_bfloat16><<<grid, 256, 0, s>>>(p, anchors, scores, conf, activation,
+                                                                             boxes, scores_act, pass_mask, words);
+    else
+      decode_filter_kernel<17, 4><<<grid, 256, 0, s>>>(p, anchors, scores, conf, activation, boxes,
+                                                       scores_act, pass_mask, words);
   } else {
     dim3 grid((unsigned)ceil_div(anchors, 256), (unsigned)batch);
-    if (bins == 17)
+    if (in_bf16)
+      decode_filter_kernel<0, 1, false, __nv_bfloat16><<<grid, 256, 0, s>>>(p, anchors, scores, conf, activation,
+                                                                            boxes, scores_act, pass_mask, words);
+    else if (bins == 17)
       decode_filter_kernel<17, 1><<<grid, 256, 0, s>>>(p, anchors, scores, conf, activation, boxes,
                                                        scores_act, pass_mask, words);
     else
@@ -258,4 +285,28 @@ extern "C" int ovdet_decode_filter(const float* const* box_preds, const int32_t*
   }
   OVDET_LAUNCH_CHECK();
   return OVDET_OK;
+}
+
+extern "C" int ovdet_decode_filter(const float* const* box_preds, const int32_t* heights,
+                                   const int32_t* widths, const int32_t* strides,
+                                   const int64_t* batch_strides, int num_levels, int bins,
+                                   int64_t batch, float width_scale, float height_scale,
+                                   const float* scores, float conf, int activation,
+                                   float* boxes, float* scores_act, uint32_t* pass_mask,
+                                   void* stream) {
+  return decode_launch(0, reinterpret_cast<const void* const*>(box_preds), heights, widths, strides,
+                       batch_strides, num_levels, bins, batch, width_scale, height_scale, scores, conf,
+                       activation, boxes, scores_act, pass_mask, stream);
+}
+
+extern "C" int ovdet_decode_filter_bf16in(const void* const* box_preds, const int32_t* heights,
+                                          const int32_t* widths, const int32_t* strides,
+                                          const int64_t* batch_strides, int num_levels, int bins,
+                                          int64_t batch, float width_scale, float height_scale,
+                                          const float* scores, float conf, int activation,
+                                          float* boxes, float* scores_act, uint32_t* pass_mask,
+                                          void* stream) {
+  return decode_launch(1, box_preds, heights, widths, strides, batch_strides, num_levels, bins, batch,
+                       width_scale, height_scale, scores, conf, activation, boxes, scores_act, pass_mask,
+                       stream);
 }

@@ -19,9 +19,14 @@ extern "C" int ovdet_head_step(const ovdet_head_step_args* a, void* stream) {
                                      a->text_batched, a->alpha, a->beta, a->scores, a->class_ids, a->inv_norm,
                                      a->sim_workspace, a->sim_workspace_bytes, a->embed_dtype, stream);
   if (rc != OVDET_OK) return rc;
-  rc = ovdet_decode_filter(a->box_preds, a->heights, a->widths, a->strides, a->box_stride_b,
-                           a->num_levels, a->bins, a->batch, 1.0f, 1.0f, a->scores, a->conf,
-                           a->activation, a->boxes, a->scores_act, a->pass_mask, stream);
+  if (a->box_dtype == OVDET_BF16)
+    rc = ovdet_decode_filter_bf16in(a->box_preds, a->heights, a->widths, a->strides, a->box_stride_b,
+                                    a->num_levels, a->bins, a->batch, 1.0f, 1.0f, a->scores, a->conf,
+                                    a->activation, a->boxes, a->scores_act, a->pass_mask, stream);
+  else
+    rc = ovdet_decode_filter(reinterpret_cast<const float* const*>(a->box_preds), a->heights, a->widths,
+                             a->strides, a->box_stride_b, a->num_levels, a->bins, a->batch, 1.0f, 1.0f,
+                             a->scores, a->conf, a->activation, a->boxes, a->scores_act, a->pass_mask, stream);
   if (rc != OVDET_OK) return rc;
   const float* nms_scores = (a->activation == OVDET_ACT_SIGMOID && a->scores_act) ? a->scores_act : a->scores;
   return ovdet_nms_batched(a->boxes, nms_scores, a->class_ids, a->pass_mask, a->batch, anchors, a->scale,

@@ -255,8 +255,11 @@ class LevelTable:
         if n > _cabi.MAX_LEVELS or n != len(strides):
             raise ValueError("ovdet: unsupported number of levels")
         self.keep = []
+        self.dtype = box_preds[0].dtype
+        if self.dtype not in (torch.float32, torch.bfloat16):
+            raise TypeError("ovdet: box_preds must be float32 or bfloat16")
         for p in box_preds:
-            _require_cuda(p, "box_preds", torch.float32)
+            _require_cuda(p, "box_preds", self.dtype)
             b, ch, h, w = p.shape
             if p.stride(3) != 1 or p.stride(2) != w or p.stride(1) != h * w:
                 p = p.contiguous()
@@ -297,8 +300,9 @@ def decode_filter(box_preds: Sequence[torch.Tensor], strides: Sequence[int],
             pass_mask = torch.empty(batch, (anchors + 31) // 32, device=dev, dtype=torch.int32)
         if act == _cabi.ACT_SIGMOID and scores_act is None:
             scores_act = torch.empty_like(scores)
+    entry = lib().ovdet_decode_filter_bf16in if table.dtype == torch.bfloat16 else lib().ovdet_decode_filter
     with torch.cuda.device(dev):
-        check(lib().ovdet_decode_filter(table.ptrs, table.heights, table.widths, table.strides,
+        check(entry(table.ptrs, table.heights, table.widths, table.strides,
                                         table.bstrides, table.n, bins, batch, float(width_scale),
                                         float(height_scale), _ptr(scores), float(conf), act,
                                         _ptr(boxes), _ptr(scores_act), _ptr(pass_mask),

@@ -207,7 +207,7 @@ class HeadPipeline:
     # -- the bf16 step as ONE C call (ovdet_head_step): same kernels, one host round trip ----------
     def _single_call_ok(self, box_preds) -> bool:
         for p in box_preds:
-            if p.dtype != torch.float32 or p.stride(3) != 1 or p.stride(2) != p.shape[3] or \
+            if p.dtype not in (torch.float32, torch.bfloat16) or p.stride(3) != 1 or p.stride(2) != p.shape[3] or \
                     p.stride(1) != p.shape[2] * p.shape[3]:
                 return False
         return len(box_preds) <= 4
@@ -254,6 +254,7 @@ class HeadPipeline:
             a.obj_embeds[l], a.box_preds[l] = e.data_ptr(), p.data_ptr()
             a.emb_stride_b[l], a.emb_stride_d[l], a.box_stride_b[l] = e.stride(0), e.stride(1), p.stride(0)
         a.embed_dtype = _cabi.OVDET_BF16 if obj_embeds[0].dtype == torch.bfloat16 else _cabi.OVDET_F32
+        a.box_dtype = _cabi.OVDET_BF16 if box_preds[0].dtype == torch.bfloat16 else _cabi.OVDET_F32
         a.scale = self.scale.data_ptr() if self.use_geometry else None
         a.clip_wh = self.clip_wh.data_ptr() if self.use_geometry else None
         self.last_path = "fused"

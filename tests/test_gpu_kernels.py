@@ -1003,3 +1003,20 @@ def test_small_launch_class_split(ov, cuda_device, batch, classes):
         assert torch.equal(pipe.result.count, want_n)
     if getattr(pipe, "_sim_ws", None) is not None:
         assert int(pipe._sim_ws.sum()) == 0 or True                     # counters are reset by the merging warp
+
+
+def test_decode_bf16_box_logits(ov, cuda_device):
+    """bf16 box logits (head under autocast): decode == the oracle on the same values widened to
+    fp32, for the 16-byte-load path, the hoisted small-launch path and the generic path."""
+    from ovdet import ops, synth
+    for batch, size, strides in ((40, 640, (8, 16, 32)), (2, 320, (8, 16, 32)), (2, 160, (8, 16, 32))):
+        inp = synth.make_inputs(batch=batch, image_size=size, num_classes=10, embed_dim=64, seed=3)
+        preds16 = [p.to(torch.bfloat16) for p in inp.box_preds]
+        grids = [ref_port.create_grid(batch, p.shape[2], p.shape[3], s) for p, s in zip(preds16, strides)]
+        ref = ref_port.decode_boxes([p.float() for p in preds16], grids)
+        scores = torch.rand(batch, ref.shape[1]) - 0.3
+        boxes, _, mask = ops.decode_filter([p.to(cuda_device) for p in preds16], strides,
+                                           scores=scores.to(cuda_device), conf=0.25)
+        torch.cuda.synchronize()
+        torch.testing.assert_close(boxes.cpu(), ref, rtol=1e-4, atol=1e-3)
+        assert torch.equal(_unpack(mask.cpu(), ref.shape[1]), scores > 0.25)
