@@ -68,7 +68,7 @@ class ClockSampler:
         try:
             self.proc = subprocess.Popen(
                 ["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.QUERY}",
-                 "--format=csv,noheader,nounits", "-lms", "50"],
+                 "--format=csv,noheader,nounits", "-lms", "20"],
                 stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             threading.Thread(target=self._pump, daemon=True).start()
         except OSError:
@@ -76,16 +76,24 @@ class ClockSampler:
 
     def _pump(self):
         for line in self.proc.stdout:
-            self.rows.append(line.strip())
+            self.rows.append((time.perf_counter(), line.strip()))
 
-    def stop(self):
+    def mark(self):
+        """Host time stamp; rows are kept only between the two marks given to stop()."""
+        return time.perf_counter()
+
+    def in_window(self, t0, t1=None):
+        return sum(1 for t, _ in self.rows if t >= t0 and (t1 is None or t <= t1))
+
+    def stop(self, t0=None, t1=None, window="timed region"):
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
         self.proc.terminate()
         sm, smax, reasons = [], None, set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for row in self.rows:
+        for t, row in self.rows:
+            if (t0 is not None and t < t0) or (t1 is not None and t > t1):
+                continue
             parts = [p.strip() for p in row.split(",")]
             if len(parts) < 7:
                 continue
@@ -98,7 +106,7 @@ class ClockSampler:
                 if val.lower().startswith("active"):
                     reasons.add(name)
         return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": smax,
-                "samples": len(sm), "reasons": sorted(reasons)}
+                "samples": len(sm), "window": window, "reasons": sorted(reasons)}
 
 
 def measured_peaks():
@@ -254,6 +262,11 @@ def run_ours(args):
         torch.cuda.synchronize()
 
     # ---- device-resident throughput ("value") with per-kernel events for the roofline --------
+    # nvidia-smi needs ~0.1-0.3 s to print its first row: start it before the warm-up, keep only
+    # the rows that arrive between the marks around the timed region
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
     for _ in range(args.warmup):
         pipe.run(inp.obj_embeds, inp.box_preds, text=step_text)
     barrier()
@@ -262,12 +275,10 @@ def run_ours(args):
     cand = res.candidates.float().mean().item()
     overflow = int((res.count >= MAX_DET).sum().item())
 
-    sampler = ClockSampler(local)
-    if rank == 0:
-        sampler.start()
     stage_events = []
     start, stop = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
+    t_mark0 = sampler.mark()
     start.record()
     for _ in range(args.steps):
         ev = {}
@@ -276,7 +287,20 @@ def run_ours(args):
     stop.record()
     barrier()
     elapsed_ms = start.elapsed_time(stop)
-    clocks = sampler.stop() if rank == 0 else None
+    clocks = None
+    if rank == 0:
+        t_mark1 = sampler.mark()
+        window = "timed region"
+        if sampler.proc is not None and sampler.in_window(t_mark0, t_mark1) < 5:
+            # a timed region shorter than a few sampling periods: keep the same steps running
+            # (untimed) until there are 5 rows under this load, at most 3 s
+            window = "timed region + untimed continuation of the same steps"
+            t_end = time.perf_counter() + 3.0
+            while sampler.in_window(t_mark0) < 5 and time.perf_counter() < t_end:
+                pipe.run(inp.obj_embeds, inp.box_preds, text=step_text)
+                torch.cuda.synchronize()
+            t_mark1 = sampler.mark()
+        clocks = sampler.stop(t_mark0, t_mark1, window)
     elapsed_ms = shard.max_over_ranks(elapsed_ms, dev)
     value = n_gpus * batch * args.steps / (elapsed_ms / 1e3)
 

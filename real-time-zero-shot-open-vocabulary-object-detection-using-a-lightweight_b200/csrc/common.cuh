@@ -81,3 +81,17 @@ __device__ __forceinline__ float ordered_to_float(uint32_t u) {
 }
 
 }  // namespace ovdet
+
+// Internal launchers behind ovdet_decode_filter* / ovdet_nms_batched*; `pdl` = launch with programmatic
+// stream serialization (only ovdet_head_step, which knows what the preceding kernel is, sets it).
+int ovdet_decode_launch_internal(int pdl, int in_bf16, const void* const* box_preds, const int32_t* heights,
+                                 const int32_t* widths, const int32_t* strides, const int64_t* batch_strides,
+                                 int num_levels, int bins, int64_t batch, float width_scale, float height_scale,
+                                 const float* scores, float conf, int activation, float* boxes,
+                                 float* scores_act, uint32_t* pass_mask, void* stream);
+int ovdet_nms_launch_internal(int pdl, int use_conf, float conf, const float* boxes, const float* scores,
+                              const int32_t* classes, const uint32_t* pass_mask, int64_t batch, int64_t anchors,
+                              const float* scale, const float* clip_wh, float iou_thr, int class_aware, int topk,
+                              int64_t max_det, float* out_boxes, float* out_scores, int32_t* out_classes,
+                              int32_t* out_anchor, int32_t* out_keep, int32_t* out_count,
+                              int32_t* out_candidates, void* workspace, size_t workspace_bytes, void* stream);

@@ -19,6 +19,11 @@ struct DecodeParams {
   int levels;
   int bins;
   float wscale, hscale;
+  // programmatic dependent launch (ovdet_head_step only): the kernel was launched while the
+  // similarity kernel may still be running; that kernel produces `scores` and nothing else this
+  // one reads, so the grid dependency is awaited just before the scores are loaded and the box
+  // decode overlaps the similarity kernel's tail
+  int pdl;
 };
 
 // Expectation of the softmax over the bins of one coordinate, for V consecutive anchors at once:
@@ -130,9 +135,9 @@ __device__ __forceinline__ void dfl_expectation4_hoisted(const T* __restrict__ p
 // general path.  blockIdx.y = image.
 template <int BINS, int V, bool HOIST = false, typename T = float>
 __global__ void __launch_bounds__(256)
-decode_filter_kernel(const DecodeParams p, int anchors, const float* __restrict__ scores,
+decode_filter_kernel(const DecodeParams p, int anchors, const float* scores,
                      float conf, int activation, float* __restrict__ boxes,
-                     float* __restrict__ scores_act, uint32_t* __restrict__ pass_mask, int words) {
+                     float* scores_act, uint32_t* __restrict__ pass_mask, int words) {
   const int a = (blockIdx.x * 256 + threadIdx.x) * V;       // first anchor of this thread
   const int b = blockIdx.y;
   uint32_t pass = 0;                                         // bit j: anchor a + j passes
@@ -160,12 +165,17 @@ decode_filter_kernel(const DecodeParams p, int anchors, const float* __restrict_
     const float st = (float)p.stride[l];
     const long long ga = (long long)b * anchors + a;
     float sc[V];
+    if (p.pdl) cudaGridDependencySynchronize();
     if (scores != nullptr) {
+      // L2-coherent loads (ld.global.cg), never the read-only path: under PDL this kernel is already
+      // running while the similarity kernel writes the scores, so they are not read-only for its
+      // lifetime and an ld.global.nc may hit an L1 line left by the previous step (measured: stale
+      // pass masks in 299 of 300 steps with LDG.CONSTANT here)
       if (V == 4) {
-        const float4 q = *reinterpret_cast<const float4*>(scores + ga);
+        const float4 q = __ldcg(reinterpret_cast<const float4*>(scores + ga));
         sc[0] = q.x; sc[1 % V] = q.y; sc[2 % V] = q.z; sc[3 % V] = q.w;
       } else {
-        sc[0] = scores[ga];
+        sc[0] = __ldcg(scores + ga);
       }
     }
 #pragma unroll
@@ -212,7 +222,7 @@ decode_filter_kernel(const DecodeParams p, int anchors, const float* __restrict_
 
 }  // namespace ovdet
 
-static int decode_launch(int in_bf16, const void* const* box_preds, const int32_t* heights,
+int ovdet_decode_launch_internal(int pdl, int in_bf16, const void* const* box_preds, const int32_t* heights,
                                    const int32_t* widths, const int32_t* strides,
                                    const int64_t* batch_strides, int num_levels, int bins,
                                    int64_t batch, float width_scale, float height_scale,
@@ -246,10 +256,25 @@ static int decode_launch(int in_bf16, const void* const* box_preds, const int32_
   p.bins = bins;
   p.wscale = width_scale;
   p.hscale = height_scale;
+  p.pdl = pdl;
   if (batch == 0) return OVDET_OK;
   const int anchors = (int)total;
   const int words = (anchors + 31) / 32;
   cudaStream_t s = as_stream(stream);
+  // every variant goes through one launcher so that the PDL attribute can be attached
+  auto launch = [&](auto kern, dim3 grid) -> cudaError_t {
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = grid;
+    cfg.blockDim = dim3(256);
+    cfg.dynamicSmemBytes = 0;
+    cfg.stream = s;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = pdl ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kern, p, anchors, scores, conf, activation, boxes, scores_act, pass_mask, words);
+  };
   bool vec4 = bins == 17 && !(((uintptr_t)scores | (uintptr_t)scores_act) & 15);
   for (int l = 0; l < num_levels && vec4; ++l)
     vec4 = ((long long)heights[l] * widths[l]) % 4 == 0 && batch_strides[l] % 4 == 0 &&
@@ -258,30 +283,23 @@ static int decode_launch(int in_bf16, const void* const* box_preds, const int32_
     // small launch: latency matters, not bandwidth
     dim3 grid((unsigned)ceil_div(anchors, 256), (unsigned)batch);
     if (in_bf16)
-      decode_filter_kernel<17, 1, true, __nv_bfloat16><<<grid, 256, 0, s>>>(p, anchors, scores, conf, activation,
-                                                                            boxes, scores_act, pass_mask, words);
+      OVDET_CUDA_TRY(launch(decode_filter_kernel<17, 1, true, __nv_bfloat16>, grid));
     else
-      decode_filter_kernel<17, 1, true><<<grid, 256, 0, s>>>(p, anchors, scores, conf, activation, boxes,
-                                                             scores_act, pass_mask, words);
+      OVDET_CUDA_TRY(launch(decode_filter_kernel<17, 1, true>, grid));
   } else if (vec4) {
     dim3 grid((unsigned)ceil_div(anchors, 1024), (unsigned)batch);
     if (in_bf16)
-      decode_filter_kernel<17, 4, false, __nv_bfloat16><<<grid, 256, 0, s>>>(p, anchors, scores, conf, activation,
-                                                                             boxes, scores_act, pass_mask, words);
+      OVDET_CUDA_TRY(launch(decode_filter_kernel<17, 4, false, __nv_bfloat16>, grid));
     else
-      decode_filter_kernel<17, 4><<<grid, 256, 0, s>>>(p, anchors, scores, conf, activation, boxes,
-                                                       scores_act, pass_mask, words);
+      OVDET_CUDA_TRY(launch(decode_filter_kernel<17, 4>, grid));
   } else {
     dim3 grid((unsigned)ceil_div(anchors, 256), (unsigned)batch);
     if (in_bf16)
-      decode_filter_kernel<0, 1, false, __nv_bfloat16><<<grid, 256, 0, s>>>(p, anchors, scores, conf, activation,
-                                                                            boxes, scores_act, pass_mask, words);
+      OVDET_CUDA_TRY(launch(decode_filter_kernel<0, 1, false, __nv_bfloat16>, grid));
     else if (bins == 17)
-      decode_filter_kernel<17, 1><<<grid, 256, 0, s>>>(p, anchors, scores, conf, activation, boxes,
-                                                       scores_act, pass_mask, words);
+      OVDET_CUDA_TRY(launch(decode_filter_kernel<17, 1>, grid));
     else
-      decode_filter_kernel<0, 1><<<grid, 256, 0, s>>>(p, anchors, scores, conf, activation, boxes,
-                                                      scores_act, pass_mask, words);
+      OVDET_CUDA_TRY(launch(decode_filter_kernel<0, 1>, grid));
   }
   OVDET_LAUNCH_CHECK();
   return OVDET_OK;
@@ -294,7 +312,7 @@ extern "C" int ovdet_decode_filter(const float* const* box_preds, const int32_t*
                                    const float* scores, float conf, int activation,
                                    float* boxes, float* scores_act, uint32_t* pass_mask,
                                    void* stream) {
-  return decode_launch(0, reinterpret_cast<const void* const*>(box_preds), heights, widths, strides,
+  return ovdet_decode_launch_internal(0, 0, reinterpret_cast<const void* const*>(box_preds), heights, widths, strides,
                        batch_strides, num_levels, bins, batch, width_scale, height_scale, scores, conf,
                        activation, boxes, scores_act, pass_mask, stream);
 }
@@ -306,7 +324,7 @@ extern "C" int ovdet_decode_filter_bf16in(const void* const* box_preds, const in
                                           const float* scores, float conf, int activation,
                                           float* boxes, float* scores_act, uint32_t* pass_mask,
                                           void* stream) {
-  return decode_launch(1, box_preds, heights, widths, strides, batch_strides, num_levels, bins, batch,
+  return ovdet_decode_launch_internal(0, 1, box_preds, heights, widths, strides, batch_strides, num_levels, bins, batch,
                        width_scale, height_scale, scores, conf, activation, boxes, scores_act, pass_mask,
                        stream);
 }

@@ -44,6 +44,7 @@ struct NmsParams {
   const float* scores;
   const int* classes;
   const uint32_t* pass_mask;
+  int pdl;                                     // launched with programmatic stream serialization (ovdet_head_step)
   int use_conf;                                // 1: candidates = scores > conf (computed here, no pass mask)
   float conf;
   int anchors;
@@ -186,6 +187,7 @@ nms_batched_kernel(const NmsParams p) {
   __shared__ uint32_t s_removed[CHUNK_WORDS];
   __shared__ int s_count, s_kept_total, s_kept_chunk, s_carry;
 
+  if (p.pdl) cudaGridDependencySynchronize();   // the decode kernel (and, through it, the similarity kernel) is done
   const int b = blockIdx.x;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int A = p.anchors, W = p.words;
@@ -558,7 +560,7 @@ extern "C" size_t ovdet_nms_workspace_bytes(int64_t batch, int64_t anchors) {
   return (size_t)batch * L.total;
 }
 
-static int nms_launch(int use_conf, float conf, const float* boxes, const float* scores, const int32_t* classes,
+int ovdet_nms_launch_internal(int pdl, int use_conf, float conf, const float* boxes, const float* scores, const int32_t* classes,
                                  const uint32_t* pass_mask, int64_t batch, int64_t anchors,
                                  const float* scale, const float* clip_wh, float iou_thr,
                                  int class_aware, int topk, int64_t max_det, float* out_boxes,
@@ -583,7 +585,7 @@ static int nms_launch(int use_conf, float conf, const float* boxes, const float*
   if (!workspace || workspace_bytes < need || ((uintptr_t)workspace & 15)) return OVDET_ERR_WORKSPACE;
   NmsParams p{};
   p.boxes = boxes; p.scores = scores; p.classes = classes; p.pass_mask = pass_mask;
-  p.use_conf = use_conf; p.conf = conf;
+  p.use_conf = use_conf; p.conf = conf; p.pdl = pdl;
   if (use_conf && (pass_mask || (anchors + 31) / 32 > ovdet::FAST_WORDS)) return OVDET_ERR_UNSUPPORTED_SHAPE;
   p.anchors = (int)anchors; p.words = (int)((anchors + 31) / 32);
   p.scale = scale; p.clip_wh = clip_wh; p.iou_thr = iou_thr;
@@ -597,8 +599,17 @@ static int nms_launch(int use_conf, float conf, const float* boxes, const float*
   if (first_use_on_device(2)) {
     OVDET_CUDA_TRY(cudaFuncSetAttribute(nms_batched_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, NMS_SMEM_BYTES));
   }
-  nms_batched_kernel<<<(unsigned)batch, NMS_THREADS, NMS_SMEM_BYTES, as_stream(stream)>>>(p);
-  OVDET_LAUNCH_CHECK();
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3((unsigned)batch);
+  cfg.blockDim = dim3(NMS_THREADS);
+  cfg.dynamicSmemBytes = NMS_SMEM_BYTES;
+  cfg.stream = as_stream(stream);
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl ? 1 : 0;
+  OVDET_CUDA_TRY(cudaLaunchKernelEx(&cfg, nms_batched_kernel, p));
   return OVDET_OK;
 }
 
@@ -609,7 +620,7 @@ extern "C" int ovdet_nms_batched(const float* boxes, const float* scores, const 
                                  float* out_scores, int32_t* out_classes, int32_t* out_anchor,
                                  int32_t* out_keep, int32_t* out_count, int32_t* out_candidates,
                                  void* workspace, size_t workspace_bytes, void* stream) {
-  return nms_launch(0, 0.f, boxes, scores, classes, pass_mask, batch, anchors, scale, clip_wh, iou_thr,
+  return ovdet_nms_launch_internal(0, 0, 0.f, boxes, scores, classes, pass_mask, batch, anchors, scale, clip_wh, iou_thr,
                     class_aware, topk, max_det, out_boxes, out_scores, out_classes, out_anchor, out_keep,
                     out_count, out_candidates, workspace, workspace_bytes, stream);
 }
@@ -621,7 +632,7 @@ extern "C" int ovdet_nms_batched_conf(const float* boxes, const float* scores, c
                                       int32_t* out_classes, int32_t* out_anchor, int32_t* out_keep,
                                       int32_t* out_count, int32_t* out_candidates, void* workspace,
                                       size_t workspace_bytes, void* stream) {
-  return nms_launch(1, conf, boxes, scores, classes, nullptr, batch, anchors, scale, clip_wh, iou_thr,
+  return ovdet_nms_launch_internal(0, 1, conf, boxes, scores, classes, nullptr, batch, anchors, scale, clip_wh, iou_thr,
                     class_aware, topk, max_det, out_boxes, out_scores, out_classes, out_anchor, out_keep,
                     out_count, out_candidates, workspace, workspace_bytes, stream);
 }

@@ -234,6 +234,9 @@ sim_fused_kernel(const __grid_constant__ LevelMaps amaps, const __grid_constant_
   else __syncthreads();
   ptx::tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_smem;
+  // programmatic dependent launch: a dependent kernel (the decode of ovdet_head_step) may be
+  // scheduled from here on; it waits on this grid's completion itself before reading the scores
+  cudaTriggerProgrammaticLaunchCompletion();
 
   const unsigned lazy_ns = (p.dbg & 16) ? 0u : ((p.dbg & 32) ? 256u : 64u);   // back-off of the non-critical waits
   const int total_tiles = p.tile_start[p.levels];

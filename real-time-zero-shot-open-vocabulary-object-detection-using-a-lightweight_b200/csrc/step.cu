@@ -4,6 +4,7 @@
 // ~20 us, more than each kernel at batch 1).  Replaces model/yolo_clip.py:173-214 followed by
 // inference/detector.py:184-208 for every image of the batch.
 #include "common.cuh"
+#include <cstdlib>
 
 extern "C" int ovdet_head_step(const ovdet_head_step_args* a, void* stream) {
   if (!a) return OVDET_ERR_INVALID_ARG;
@@ -19,20 +20,20 @@ extern "C" int ovdet_head_step(const ovdet_head_step_args* a, void* stream) {
                                      a->text_batched, a->alpha, a->beta, a->scores, a->class_ids, a->inv_norm,
                                      a->sim_workspace, a->sim_workspace_bytes, a->embed_dtype, stream);
   if (rc != OVDET_OK) return rc;
-  if (a->box_dtype == OVDET_BF16)
-    rc = ovdet_decode_filter_bf16in(a->box_preds, a->heights, a->widths, a->strides, a->box_stride_b,
-                                    a->num_levels, a->bins, a->batch, 1.0f, 1.0f, a->scores, a->conf,
-                                    a->activation, a->boxes, a->scores_act, a->pass_mask, stream);
-  else
-    rc = ovdet_decode_filter(reinterpret_cast<const float* const*>(a->box_preds), a->heights, a->widths,
-                             a->strides, a->box_stride_b, a->num_levels, a->bins, a->batch, 1.0f, 1.0f,
-                             a->scores, a->conf, a->activation, a->boxes, a->scores_act, a->pass_mask, stream);
+  // K3 and K4 are launched with programmatic stream serialization: their CTAs may be scheduled while
+  // the preceding kernel drains (K3 decodes the boxes beside the similarity kernel's tail and waits
+  // for it only before it reads the scores; K4 waits at its first instruction).  OVDET_PDL=0 disables.
+  static const int pdl = []() { const char* e = getenv("OVDET_PDL"); return e ? atoi(e) : 1; }();
+  rc = ovdet_decode_launch_internal(pdl, a->box_dtype == OVDET_BF16, a->box_preds, a->heights, a->widths,
+                                    a->strides, a->box_stride_b, a->num_levels, a->bins, a->batch, 1.0f, 1.0f,
+                                    a->scores, a->conf, a->activation, a->boxes, a->scores_act, a->pass_mask,
+                                    stream);
   if (rc != OVDET_OK) return rc;
   const float* nms_scores = (a->activation == OVDET_ACT_SIGMOID && a->scores_act) ? a->scores_act : a->scores;
-  return ovdet_nms_batched(a->boxes, nms_scores, a->class_ids, a->pass_mask, a->batch, anchors, a->scale,
-                           a->clip_wh, a->iou_thr, a->class_aware, a->topk, a->max_det, a->out_boxes,
-                           a->out_scores, a->out_classes, a->out_anchor, a->out_keep, a->out_count,
-                           a->out_candidates, a->workspace, a->workspace_bytes, stream);
+  return ovdet_nms_launch_internal(pdl, 0, 0.f, a->boxes, nms_scores, a->class_ids, a->pass_mask, a->batch,
+                                   anchors, a->scale, a->clip_wh, a->iou_thr, a->class_aware, a->topk, a->max_det,
+                                   a->out_boxes, a->out_scores, a->out_classes, a->out_anchor, a->out_keep,
+                                   a->out_count, a->out_candidates, a->workspace, a->workspace_bytes, stream);
 }
 
 extern "C" size_t ovdet_head_step_args_size(void) { return sizeof(ovdet_head_step_args); }

@@ -656,6 +656,38 @@ def test_graph_replay_equals_eager(ov, cuda_device):
     same(snapshot(pipe.replay()), want_b)
 
 
+def test_single_call_step_with_changing_inputs(ov, cuda_device):
+    """ovdet_head_step launches K3 and K4 with programmatic dependent launch (they start while the
+    preceding kernel drains).  Every intermediate and every kept row must equal the per-stage
+    path when the inputs change from step to step - a K3 that read the scores through the
+    read-only cache path passed same-input tests and returned the PREVIOUS step's pass mask."""
+    from ovdet import synth
+    from ovdet.pipeline import HeadConfig, HeadPipeline
+    shapes = [(32, 32), (16, 16), (8, 8)]
+    ins = [synth.make_inputs(batch=2, image_size=256, num_classes=90, seed=s, device=cuda_device)
+           for s in (41, 42, 43)]
+    pipe = HeadPipeline(2, shapes, 90, HeadConfig(precision="bf16", max_det=64), device=cuda_device)
+    pipe.set_vocabulary(ins[0].text)
+    ref = []
+    for x in ins:
+        r = pipe.run(x.obj_embeds, x.box_preds, events={})           # one launch per stage, no PDL
+        torch.cuda.synchronize()
+        ref.append([t.clone() for t in (pipe.scores, pipe.pass_mask, pipe.boxes, r.count,
+                                        r.boxes, r.scores, r.classes, r.anchor)])
+    assert not torch.equal(ref[0][1], ref[1][1]) and not torch.equal(ref[1][1], ref[2][1])
+    for it in range(30):
+        i = it % 3
+        r = pipe.run(ins[i].obj_embeds, ins[i].box_preds)            # single C call
+        torch.cuda.synchronize()
+        assert pipe.last_path == "fused"
+        got = [pipe.scores, pipe.pass_mask, pipe.boxes, r.count, r.boxes, r.scores, r.classes, r.anchor]
+        for j in range(4):
+            assert torch.equal(got[j], ref[i][j]), (it, j)
+        for b, k in enumerate(ref[i][3].tolist()):
+            for j in range(4, 8):
+                assert torch.equal(got[j][b, :k], ref[i][j][b, :k]), (it, j, b)
+
+
 # ------------------------------------------------------------------------------------------
 # K4 properties (hypothesis): random box sets, duplicates, degenerate boxes, ties in IoU
 # ------------------------------------------------------------------------------------------
