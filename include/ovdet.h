@@ -48,6 +48,7 @@ typedef enum ovdet_dtype { OVDET_F32 = 0, OVDET_BF16 = 1 } ovdet_dtype;
 typedef enum ovdet_activation { OVDET_ACT_NONE = 0, OVDET_ACT_SIGMOID = 1 } ovdet_activation;
 
 #define OVDET_MAX_LEVELS 8
+#define OVDET_MAX_PEERS 8            /* GPUs of one NVSwitch box a vocabulary can be sharded over */
 
 OVDET_API int ovdet_version(void);
 OVDET_API const char* ovdet_strerror(int status);
@@ -382,6 +383,61 @@ typedef struct ovdet_head_step_args {
 OVDET_API int ovdet_head_step(const ovdet_head_step_args* args, void* stream);
 /* sizeof(ovdet_head_step_args) as compiled into the library (binding layers check their mirror). */
 OVDET_API size_t ovdet_head_step_args_size(void);
+
+/* ------------------------------------------------------------------------------------------
+ * Vocabulary-parallel similarity (SURVEY section 8 e "not built (optional later)" / f-4): the
+ * C prompts are sharded over the GPUs of one NVLink box, every rank sees the whole image batch
+ * and owns classes [class_offset, class_offset + classes).  The one exchange step of the path is
+ * the reduction of the per-anchor (max, argmax) pairs of model/yolo_clip.py:198-206 over the
+ * class shards.  It is fused into the similarity kernel: a finished row is packed into a 64-bit
+ * key (score ascending, class descending: the maximum is the best score, lowest class index on
+ * ties - torch.max's rule) and max-reduced with system-scope atomics straight into EVERY rank's
+ * key array through NVLink peer mappings, from the epilogue warp that produced it.  No NCCL call
+ * on the data path; ovdet_vp_signal / ovdet_vp_wait_unpack are the flag handshake that replaces
+ * the collective's synchronisation.
+ *
+ * Exchange buffer (one per rank, ovdet_vp_buffer_bytes(rows, world) bytes, rows = batch * anchors):
+ *   keys[2][rows] u64 (step parity p uses keys[p]; wait_unpack hands a row back as 0 after reading
+ *   it, which is ordered before any peer's step + 2 atomics by the step + 1 handshake) followed by
+ *   flags[world] u64 (flags[g] = last step rank g has finished contributing to).
+ * Peer buffers: ovdet_peer_buffer_create allocates device memory and exports a 64-byte IPC handle;
+ * the other ranks (one process per GPU) map it with ovdet_peer_buffer_open.  Within one process
+ * (tests: several virtual ranks on one GPU) the pointers are used directly.
+ * `step` starts at 1 and increases by 1 per exchange on every rank.
+ * ---------------------------------------------------------------------------------------- */
+OVDET_API int ovdet_peer_buffer_create(size_t bytes, void** ptr, void* handle64);
+OVDET_API int ovdet_peer_buffer_open(const void* handle64, void** ptr);
+OVDET_API int ovdet_peer_buffer_close(void* ptr);
+OVDET_API int ovdet_peer_buffer_destroy(void* ptr);
+OVDET_API size_t ovdet_vp_buffer_bytes(int64_t rows, int world);
+/* keys and flags to zero (once, before step 1; every rank, then a host-side barrier). */
+OVDET_API int ovdet_vp_buffer_init(void* buffer, int64_t rows, int world, void* stream);
+/* ovdet_similarity_fused_ws with the row results reduced into peer_buffers[0..world) instead of
+ * row_max / row_arg.  text_op holds only this rank's `classes` rows. */
+OVDET_API int ovdet_similarity_fused_vp(const void* const* obj_embeds, const int64_t* hw,
+                                        const int64_t* stride_b, const int64_t* stride_d,
+                                        int num_levels, int64_t batch, int64_t dim, const void* text_op,
+                                        int64_t classes, int text_batched, float alpha, float beta,
+                                        float* inv_norm, void* workspace, size_t workspace_bytes,
+                                        int embed_dtype, int64_t class_offset,
+                                        void* const* peer_buffers, int world, int64_t step, void* stream);
+/* after the similarity kernel on the same stream: tell every rank that this rank's keys of `step`
+ * have landed (system-scope release store of `step` into flags[rank] of every buffer). */
+OVDET_API int ovdet_vp_signal(void* const* peer_buffers, int world, int rank, int64_t rows, int64_t step,
+                              void* stream);
+/* wait until flags[g] >= step for every g, then keys[step & 1] -> scores fp32 / class_ids int32
+ * (global class indices) and hand the rows back.  The wait is bounded (timeout_ms, 0 = 2000): on
+ * expiry *status (device int32, optional) is set to 1 and the kernel continues with what it has. */
+OVDET_API int ovdet_vp_wait_unpack(void* local_buffer, int world, int64_t rows, int64_t step,
+                                   float* scores, int32_t* class_ids, int32_t* status, int timeout_ms,
+                                   void* stream);
+/* The same reduction as a library collective (the baseline the fused exchange is measured against):
+ * pack (score, class_offset + class) into int64 keys whose SIGNED order is the key order above, so
+ * that an all-reduce(MAX) over int64 (NCCL, or gloo in the CPU tests) merges the shards; unpack. */
+OVDET_API int ovdet_pack_score_keys(const float* scores, const int32_t* class_ids, int64_t n,
+                                    int64_t class_offset, int64_t* keys, void* stream);
+OVDET_API int ovdet_unpack_score_keys(const int64_t* keys, int64_t n, float* scores, int32_t* class_ids,
+                                      void* stream);
 
 #ifdef __cplusplus
 }

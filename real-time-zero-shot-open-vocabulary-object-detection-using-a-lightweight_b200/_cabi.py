@@ -102,6 +102,22 @@ PROTOTYPES = {
     "ovdet_head_step": (c_int, [POINTER(HeadStepArgs), c_void_p]),
     "ovdet_head_step_args_size": (c_size_t, []),
     "ovdet_pack_boxes_i32": (c_int, [c_void_p, c_void_p, c_int64, c_int64, c_void_p, c_void_p]),
+    # vocabulary-parallel exchange (vocab_parallel.cu)
+    "ovdet_peer_buffer_create": (c_int, [c_size_t, POINTER(c_void_p), c_void_p]),
+    "ovdet_peer_buffer_open": (c_int, [c_void_p, POINTER(c_void_p)]),
+    "ovdet_peer_buffer_close": (c_int, [c_void_p]),
+    "ovdet_peer_buffer_destroy": (c_int, [c_void_p]),
+    "ovdet_vp_buffer_bytes": (c_size_t, [c_int64, c_int]),
+    "ovdet_vp_buffer_init": (c_int, [c_void_p, c_int64, c_int, c_void_p]),
+    "ovdet_similarity_fused_vp": (c_int, [POINTER(c_void_p), POINTER(c_int64), POINTER(c_int64),
+                                          POINTER(c_int64), c_int, c_int64, c_int64, c_void_p, c_int64,
+                                          c_int, c_float, c_float, c_void_p, c_void_p, c_size_t, c_int,
+                                          c_int64, POINTER(c_void_p), c_int, c_int64, c_void_p]),
+    "ovdet_vp_signal": (c_int, [POINTER(c_void_p), c_int, c_int, c_int64, c_int64, c_void_p]),
+    "ovdet_vp_wait_unpack": (c_int, [c_void_p, c_int, c_int64, c_int64, c_void_p, c_void_p, c_void_p,
+                                     c_int, c_void_p]),
+    "ovdet_pack_score_keys": (c_int, [c_void_p, c_void_p, c_int64, c_int64, c_void_p, c_void_p]),
+    "ovdet_unpack_score_keys": (c_int, [c_void_p, c_int64, c_void_p, c_void_p, c_void_p]),
 }
 
 _lib = None

@@ -35,12 +35,19 @@ bool first_use_on_device(int slot);
 
 // sim_fused_sm100.cu: the fused normalise + GEMM + row max kernel behind ovdet_similarity_fused
 // and ovdet_max_sigmoid_attention.
+// `vp` (vocabulary-parallel launches only): where the packed (score, class) keys of every row go.
+struct VpTarget {
+  int world;
+  int class_offset;                              // global index of this launch's class 0
+  unsigned long long* keys[OVDET_MAX_PEERS];     // one [batch * anchors] key array per rank
+};
 int fused_launch(const float* const* obj_embeds, const int64_t* hw, const int64_t* stride_b,
                  const int64_t* stride_d, int num_levels, int64_t batch, int64_t dim,
                  const void* text_op, const void* const* level_ops, int64_t classes, int text_batched,
                  int normalize, int split3, float alpha, float beta, void* logits, int logits_dtype,
                  int64_t ldc, float* row_max, int32_t* row_arg, float* inv_norm, void* stream,
-                 int in_bf16 = 0, void* split_ws = nullptr, size_t split_ws_bytes = 0);
+                 int in_bf16 = 0, void* split_ws = nullptr, size_t split_ws_bytes = 0,
+                 const VpTarget* vp = nullptr);
 
 inline cudaStream_t as_stream(void* s) { return reinterpret_cast<cudaStream_t>(s); }
 
@@ -78,6 +85,17 @@ __device__ __forceinline__ uint32_t float_to_ordered(float f) {
 }
 __device__ __forceinline__ float ordered_to_float(uint32_t u) {
   return __uint_as_float((u & 0x80000000u) ? (u & 0x7fffffffu) : ~u);
+}
+
+// (score, class) -> one 64-bit key whose unsigned order is (score ascending, class DESCENDING): the
+// maximum over any set of keys is the highest score and, among equal scores, the lowest class index
+// (torch.max's CPU tie rule).  -0.0 is folded into +0.0 first (equal as floats).
+__device__ __forceinline__ unsigned long long vp_pack_key(float score, int cls) {
+  return ((unsigned long long)float_to_ordered(score + 0.0f) << 32) | (0xffffffffu - (uint32_t)cls);
+}
+__device__ __forceinline__ void vp_unpack_key(unsigned long long key, float& score, int& cls) {
+  score = ordered_to_float((uint32_t)(key >> 32));
+  cls = (int)(0xffffffffu - (uint32_t)key);
 }
 
 }  // namespace ovdet

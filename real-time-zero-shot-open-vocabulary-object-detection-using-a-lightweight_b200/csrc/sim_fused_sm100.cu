@@ -128,6 +128,14 @@ struct FusedParams {
   float* part_max;                 // [nsplit, batch * anchors]
   int* part_arg;                   // [nsplit, batch * anchors]
   int* part_count;                 // [tiles * 4], zero on entry, left zero
+  // Vocabulary-parallel exchange (vocab_parallel.cu): this launch holds classes
+  // [vp_class_offset, vp_class_offset + classes) of a vocabulary sharded over vp_world GPUs.  A row's
+  // (score, global class) is packed into one 64-bit key and max-reduced straight into EVERY rank's
+  // key array with system-scope atomics over NVLink peer mappings, from the epilogue warp that
+  // produced it - no local row_max / row_arg, no separate collective.
+  int vp_world;                    // 0: off
+  int vp_class_offset;
+  unsigned long long* vp_keys[OVDET_MAX_PEERS];   // [batch * anchors] on every rank (peer-mapped)
   int dbg;
 };
 
@@ -502,7 +510,18 @@ sim_fused_kernel(const __grid_constant__ LevelMaps amaps, const __grid_constant_
     // ================================ epilogue ===============================================
     const int lg = warp & 3;
     float* stage = epi_stage + lg * 32 * F_VPITCH;
-    const bool want_max = p.row_max != nullptr;
+    const bool vp = p.vp_world > 0;
+    const bool want_max = p.row_max != nullptr || vp;
+    // a finished row: local (score, class) or, vocabulary-parallel, one max-reduction per rank
+    auto emit_row = [&](long long row, float v, int idx) {
+      if (vp) {
+        const unsigned long long key = vp_pack_key(v, p.vp_class_offset + idx);
+        for (int g = 0; g < p.vp_world; ++g) atomicMax_system(p.vp_keys[g] + row, key);
+      } else {
+        p.row_max[row] = v;
+        if (p.row_arg != nullptr) p.row_arg[row] = idx;
+      }
+    };
     uint32_t acc_it = 0, lt = 0;
     for (int w = pair0; w < total_work; w += pair_stride, ++lt) {
       const int tile = (w / NSPLIT) * CG + (int)rank;
@@ -529,7 +548,7 @@ sim_fused_kernel(const __grid_constant__ LevelMaps amaps, const __grid_constant_
       const bool vec_logits = p.logits != nullptr && ((uintptr_t)p.logits & 15) == 0 &&
                               (p.ldc * (p.logits_bf16 ? 2 : 4)) % 16 == 0;
       const bool raw_mode = PROJ || (want_max && p.logits == nullptr && p.alpha >= 0.f && !(p.dbg & 2));
-      const bool max_only = raw_mode && p.row_arg == nullptr;
+      const bool max_only = raw_mode && p.row_arg == nullptr && !vp;
       float raw_best = -INFINITY;
       for (int nt = nt_b; nt < nt_e; ++nt, ++acc_it) {
         const int n0 = (nt - NG) * F_BLOCK_N;          // first class of a class tile
@@ -767,8 +786,7 @@ sim_fused_kernel(const __grid_constant__ LevelMaps amaps, const __grid_constant_
               const int vi = __ldcg(p.part_arg + q2 * rows_total + grow);
               if (v > m) { m = v; mi = vi; }
             }
-            p.row_max[grow] = m;
-            if (p.row_arg != nullptr) p.row_arg[grow] = mi;
+            emit_row(grow, m, mi);
           }
           if (lane == 0) p.part_count[tile * 4 + lg] = 0;      // ready for the next launch
         }
@@ -794,8 +812,7 @@ sim_fused_kernel(const __grid_constant__ LevelMaps amaps, const __grid_constant_
         for (int q = 1; q < 4; ++q)
           if (bv[q] > best || (bv[q] == best && bi[q] < best_idx)) { best = bv[q]; best_idx = bi[q]; }
         if (raw_mode) best = fmaf(scale, best, beta);
-        p.row_max[grow] = best;
-        if (p.row_arg != nullptr) p.row_arg[grow] = best_idx;
+        emit_row(grow, best, best_idx);
       }
     }
   }
@@ -838,14 +855,20 @@ int fused_launch(const float* const* obj_embeds, const int64_t* hw, const int64_
                  const void* text_op, const void* const* level_ops, int64_t classes, int text_batched,
                  int normalize, int split3, float alpha, float beta, void* logits, int logits_dtype,
                  int64_t ldc, float* row_max, int32_t* row_arg, float* inv_norm, void* stream,
-                 int in_bf16, void* split_ws, size_t split_ws_bytes) {
+                 int in_bf16, void* split_ws, size_t split_ws_bytes, const VpTarget* vp) {
   const int proj = level_ops != nullptr;
+  if (vp) {                                         // vocabulary-parallel: keys instead of row_max / row_arg
+    if (proj || split3 || logits || row_max || row_arg || alpha < 0.f) return OVDET_ERR_INVALID_ARG;
+    if (vp->world < 1 || vp->world > OVDET_MAX_PEERS || vp->class_offset < 0) return OVDET_ERR_INVALID_ARG;
+    for (int g = 0; g < vp->world; ++g)
+      if (!vp->keys[g] || ((uintptr_t)vp->keys[g] & 7)) return OVDET_ERR_INVALID_ARG;
+  }
   if (in_bf16 && (proj || split3)) return OVDET_ERR_UNSUPPORTED_SHAPE;   // bf16 activations: cosine mode only
   if (batch == 0) return check_device();            // an empty batch is a no-op (its pointers may be null)
   if (!obj_embeds || !hw || !stride_b || !stride_d || (!text_op && !proj) || batch < 0 || classes <= 0 || dim <= 0)
     return OVDET_ERR_INVALID_ARG;
   if (num_levels <= 0) return OVDET_ERR_INVALID_ARG;
-  if (!logits && !row_max) return OVDET_ERR_INVALID_ARG;
+  if (!logits && !row_max && !vp) return OVDET_ERR_INVALID_ARG;
   if (row_arg && !row_max) return OVDET_ERR_INVALID_ARG;
   if (logits && (ldc < classes || (logits_dtype != OVDET_F32 && logits_dtype != OVDET_BF16)))
     return OVDET_ERR_INVALID_ARG;
@@ -940,9 +963,14 @@ int fused_launch(const float* const* obj_embeds, const int64_t* hw, const int64_
   p.row_max = row_max;
   p.row_arg = row_arg;
   p.inv_norm = inv_norm;
+  if (vp) {
+    p.vp_world = vp->world;
+    p.vp_class_offset = vp->class_offset;
+    for (int g = 0; g < vp->world; ++g) p.vp_keys[g] = vp->keys[g];
+  }
   // small launch: split the class tiles of every anchor tile over the idle CTA pairs
   p.nsplit = 1;
-  if (cg == 2 && !proj && !split3 && !logits && row_max && split_ws && !((uintptr_t)split_ws & 15)) {
+  if (cg == 2 && !proj && !split3 && !logits && (row_max || vp) && split_ws && !((uintptr_t)split_ws & 15)) {
     const long long pairs = (tiles + 1) / 2;
     const long long max_pairs = sm_count() / 2;
     long long ns = pairs > 0 ? max_pairs / pairs : 1;

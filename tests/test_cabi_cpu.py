@@ -106,6 +106,16 @@ def test_new_entries_validate_arguments(handle):
                                              None, None, None, None) == -1
     assert handle.ovdet_similarity_fused(None, None, None, None, 1, 1, 512, None, 80, 0, 1.0, 0.0, None, 0,
                                          80, None, None, None, None) == -1
+    # vocabulary-parallel exchange
+    assert handle.ovdet_vp_buffer_bytes(0, 2) == 0 and handle.ovdet_vp_buffer_bytes(100, 9) == 0
+    assert handle.ovdet_vp_buffer_bytes(100, 2) == (100 * 16 + 127) // 128 * 128 + 128
+    assert handle.ovdet_peer_buffer_create(0, None, None) == -1
+    assert handle.ovdet_peer_buffer_open(None, None) == -1
+    assert handle.ovdet_vp_buffer_init(None, 10, 2, None) == -1
+    assert handle.ovdet_vp_signal(None, 2, 0, 10, 1, None) == -1
+    assert handle.ovdet_vp_wait_unpack(None, 2, 10, 1, None, None, None, 0, None) == -1
+    assert handle.ovdet_pack_score_keys(None, None, 1, 0, None, None) == -1
+    assert handle.ovdet_unpack_score_keys(None, 1, None, None, None) == -1
 
 
 def test_bench_reference_arm_contract():

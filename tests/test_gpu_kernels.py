@@ -689,6 +689,105 @@ def test_single_call_step_with_changing_inputs(ov, cuda_device):
 
 
 # ------------------------------------------------------------------------------------------
+# Vocabulary-parallel exchange (SURVEY 8 e / f-4) on ONE device: several virtual ranks share the
+# GPU, their "peer" buffers are plain local pointers - the kernels cannot tell the difference.
+# The multi-process path (CUDA IPC mappings over NVLink) is tools/vp_check.py under torchrun.
+# ------------------------------------------------------------------------------------------
+def _virtual_ranks(world, batch, shapes, classes, cfg, dev):
+    from ovdet import vocab_parallel as vp
+    heads = [vp.VocabParallelHead(batch, shapes, classes, cfg, device=dev, rank=r, world=world)
+             for r in range(world)]
+    ptrs = [h.buffer.ptr for h in heads]
+    for h in heads:
+        h.connect(ptrs)
+    return heads
+
+
+@pytest.mark.parametrize("world,classes", [(2, 1203), (3, 200), (8, 90)])
+def test_vocab_parallel_virtual_ranks_equal_full_vocabulary(ov, cuda_device, world, classes):
+    """Class shards reduced through the in-kernel key exchange == one launch over the whole
+    vocabulary: scores bit-exact, classes equal, and the detections after K3/K4 identical, over
+    several steps with changing inputs (the parity hand-back of the key arrays)."""
+    from ovdet import synth
+    from ovdet.pipeline import HeadConfig, HeadPipeline
+    shapes = [(32, 32), (16, 16), (8, 8)]
+    cfg = HeadConfig(precision="bf16", max_det=64)
+    ins = [synth.make_inputs(batch=2, image_size=256, num_classes=classes, seed=s, device=cuda_device)
+           for s in (51, 52, 53)]
+    text = ins[0].text
+    full = HeadPipeline(2, shapes, classes, cfg, device=cuda_device)
+    full.set_vocabulary(text)
+    heads = _virtual_ranks(world, 2, shapes, classes, cfg, cuda_device)
+    try:
+        for h in heads:
+            h.set_vocabulary(text)
+        for it in range(5):
+            x = ins[it % 3]
+            r = full.run(x.obj_embeds, x.box_preds, events={})
+            torch.cuda.synchronize()
+            want = [t.clone() for t in (full.scores, full.class_ids, r.count, r.boxes, r.scores, r.classes, r.anchor)]
+            for h in heads:
+                h.similarity(x.obj_embeds)
+            for h in heads:
+                h.signal()
+            for h in heads:
+                h.merge()
+                res = h.finish(x.box_preds)
+                torch.cuda.synchronize()
+                assert not h.timed_out()
+                assert torch.equal(h.scores, want[0]), (it, h.rank)
+                assert torch.equal(h.class_ids, want[1]), (it, h.rank)
+                assert torch.equal(res.count, want[2])
+                for b, k in enumerate(want[2].tolist()):
+                    for g, w in zip((res.boxes, res.scores, res.classes, res.anchor), want[3:]):
+                        assert torch.equal(g[b, :k], w[b, :k])
+        assert int(want[2].sum()) > 0
+    finally:
+        for h in heads:
+            h.close()
+
+
+def test_vocab_parallel_wait_is_bounded(ov, cuda_device):
+    """A rank whose peer never signals does not hang the GPU: the wait expires and is reported."""
+    from ovdet import synth
+    from ovdet.pipeline import HeadConfig
+    shapes = [(32, 32), (16, 16), (8, 8)]
+    x = synth.make_inputs(batch=1, image_size=256, num_classes=40, seed=5, device=cuda_device)
+    heads = _virtual_ranks(2, 1, shapes, 40, HeadConfig(precision="bf16", max_det=16), cuda_device)
+    try:
+        for h in heads:
+            h.set_vocabulary(x.text)
+            h.timeout_ms = 20
+        heads[0].similarity(x.obj_embeds)
+        heads[0].signal()                       # rank 1 never contributes
+        heads[0].merge()
+        torch.cuda.synchronize()
+        assert heads[0].timed_out()
+    finally:
+        for h in heads:
+            h.close()
+
+
+def test_score_keys_device_equals_host_twin(ov, cuda_device):
+    """ovdet_pack_score_keys / ovdet_unpack_score_keys (the all-reduce baseline's kernels) against
+    the numpy twin the gloo tests use."""
+    from ovdet import vocab_parallel as vp
+    g = torch.Generator(device="cpu").manual_seed(9)
+    scores = torch.randn(3, 1000, generator=g)
+    scores[0, :6] = torch.tensor([0.0, -0.0, float("inf"), float("-inf"), 1e-45, -1e-45])
+    classes = torch.randint(0, 100000, (3, 1000), generator=g, dtype=torch.int32)
+    keys = vp.pack_score_keys(scores.to(cuda_device), classes.to(cuda_device), 12345)
+    want = vp.pack_keys_host(scores.numpy(), classes.numpy(), 12345)
+    assert np.array_equal(keys.cpu().numpy(), want)
+    s2 = torch.empty_like(scores, device=cuda_device)
+    c2 = torch.empty_like(classes, device=cuda_device)
+    vp.unpack_score_keys(keys, s2, c2)
+    hs, hc = vp.unpack_keys_host(want)
+    assert np.array_equal(s2.cpu().numpy(), hs) and np.array_equal(c2.cpu().numpy(), hc)
+    assert np.array_equal(hc, classes.numpy() + 12345)
+
+
+# ------------------------------------------------------------------------------------------
 # K4 properties (hypothesis): random box sets, duplicates, degenerate boxes, ties in IoU
 # ------------------------------------------------------------------------------------------
 def test_nms_properties_hypothesis(ov, cuda_device):
