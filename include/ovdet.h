@@ -403,7 +403,10 @@ OVDET_API size_t ovdet_head_step_args_size(void);
  * Peer buffers: ovdet_peer_buffer_create allocates device memory and exports a 64-byte IPC handle;
  * the other ranks (one process per GPU) map it with ovdet_peer_buffer_open.  Within one process
  * (tests: several virtual ranks on one GPU) the pointers are used directly.
- * `step` starts at 1 and increases by 1 per exchange on every rank.
+ * The step counters live in the buffers themselves (ctr[2] u64 behind the flags, moved by
+ * ovdet_vp_signal), so no argument changes from step to step and the sequence
+ * similarity_fused_vp -> vp_signal -> vp_wait_unpack can be captured in a CUDA graph; every rank
+ * must issue the same number of steps.
  * ---------------------------------------------------------------------------------------- */
 OVDET_API int ovdet_peer_buffer_create(size_t bytes, void** ptr, void* handle64);
 OVDET_API int ovdet_peer_buffer_open(const void* handle64, void** ptr);
@@ -420,17 +423,23 @@ OVDET_API int ovdet_similarity_fused_vp(const void* const* obj_embeds, const int
                                         int64_t classes, int text_batched, float alpha, float beta,
                                         float* inv_norm, void* workspace, size_t workspace_bytes,
                                         int embed_dtype, int64_t class_offset,
-                                        void* const* peer_buffers, int world, int64_t step, void* stream);
-/* after the similarity kernel on the same stream: tell every rank that this rank's keys of `step`
- * have landed (system-scope release store of `step` into flags[rank] of every buffer). */
-OVDET_API int ovdet_vp_signal(void* const* peer_buffers, int world, int rank, int64_t rows, int64_t step,
-                              void* stream);
+                                        void* const* peer_buffers, int world, int rank, void* stream);
+/* after the similarity kernel on the same stream: tell every rank that this rank's keys of the
+ * current step have landed (system-scope release store of the step into flags[rank] of every
+ * buffer) and advance this rank's counters. */
+OVDET_API int ovdet_vp_signal(void* const* peer_buffers, int world, int rank, int64_t rows, void* stream);
 /* wait until flags[g] >= step for every g, then keys[step & 1] -> scores fp32 / class_ids int32
  * (global class indices) and hand the rows back.  The wait is bounded (timeout_ms, 0 = 2000): on
  * expiry *status (device int32, optional) is set to 1 and the kernel continues with what it has. */
-OVDET_API int ovdet_vp_wait_unpack(void* local_buffer, int world, int64_t rows, int64_t step,
+OVDET_API int ovdet_vp_wait_unpack(void* local_buffer, int world, int64_t rows,
                                    float* scores, int32_t* class_ids, int32_t* status, int timeout_ms,
                                    void* stream);
+/* The vocabulary-parallel step in ONE call (ovdet_head_step for a class shard): similarity with the
+ * in-kernel exchange -> signal -> wait + unpack -> K3 -> K4.  `args` describes this rank's shard
+ * (args->classes rows in args->text_op); args->scores / args->class_ids receive the merged result. */
+OVDET_API int ovdet_head_step_vp(const ovdet_head_step_args* args, int64_t class_offset,
+                                 void* const* peer_buffers, int world, int rank, int32_t* status,
+                                 int timeout_ms, void* stream);
 /* The same reduction as a library collective (the baseline the fused exchange is measured against):
  * pack (score, class_offset + class) into int64 keys whose SIGNED order is the key order above, so
  * that an all-reduce(MAX) over int64 (NCCL, or gloo in the CPU tests) merges the shards; unpack. */

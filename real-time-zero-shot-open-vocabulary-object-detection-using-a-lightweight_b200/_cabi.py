@@ -112,10 +112,12 @@ PROTOTYPES = {
     "ovdet_similarity_fused_vp": (c_int, [POINTER(c_void_p), POINTER(c_int64), POINTER(c_int64),
                                           POINTER(c_int64), c_int, c_int64, c_int64, c_void_p, c_int64,
                                           c_int, c_float, c_float, c_void_p, c_void_p, c_size_t, c_int,
-                                          c_int64, POINTER(c_void_p), c_int, c_int64, c_void_p]),
-    "ovdet_vp_signal": (c_int, [POINTER(c_void_p), c_int, c_int, c_int64, c_int64, c_void_p]),
-    "ovdet_vp_wait_unpack": (c_int, [c_void_p, c_int, c_int64, c_int64, c_void_p, c_void_p, c_void_p,
+                                          c_int64, POINTER(c_void_p), c_int, c_int, c_void_p]),
+    "ovdet_vp_signal": (c_int, [POINTER(c_void_p), c_int, c_int, c_int64, c_void_p]),
+    "ovdet_vp_wait_unpack": (c_int, [c_void_p, c_int, c_int64, c_void_p, c_void_p, c_void_p,
                                      c_int, c_void_p]),
+    "ovdet_head_step_vp": (c_int, [POINTER(HeadStepArgs), c_int64, POINTER(c_void_p), c_int, c_int,
+                                   c_void_p, c_int, c_void_p]),
     "ovdet_pack_score_keys": (c_int, [c_void_p, c_void_p, c_int64, c_int64, c_void_p, c_void_p]),
     "ovdet_unpack_score_keys": (c_int, [c_void_p, c_int64, c_void_p, c_void_p, c_void_p]),
 }

@@ -39,7 +39,9 @@ bool first_use_on_device(int slot);
 struct VpTarget {
   int world;
   int class_offset;                              // global index of this launch's class 0
-  unsigned long long* keys[OVDET_MAX_PEERS];     // one [batch * anchors] key array per rank
+  long long rows;                                // batch * anchors
+  const unsigned long long* step;                // this rank's device-resident step counter
+  unsigned long long* keys[OVDET_MAX_PEERS];     // keys[2][rows] of every rank
 };
 int fused_launch(const float* const* obj_embeds, const int64_t* hw, const int64_t* stride_b,
                  const int64_t* stride_d, int num_levels, int64_t batch, int64_t dim,

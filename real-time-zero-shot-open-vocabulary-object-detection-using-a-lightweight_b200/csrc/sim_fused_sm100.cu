@@ -132,10 +132,13 @@ struct FusedParams {
   // [vp_class_offset, vp_class_offset + classes) of a vocabulary sharded over vp_world GPUs.  A row's
   // (score, global class) is packed into one 64-bit key and max-reduced straight into EVERY rank's
   // key array with system-scope atomics over NVLink peer mappings, from the epilogue warp that
-  // produced it - no local row_max / row_arg, no separate collective.
+  // produced it - no local row_max / row_arg, no separate collective.  The step counter lives in
+  // device memory (the key-array parity is its low bit), so a captured graph replays correctly.
   int vp_world;                    // 0: off
   int vp_class_offset;
-  unsigned long long* vp_keys[OVDET_MAX_PEERS];   // [batch * anchors] on every rank (peer-mapped)
+  long long vp_rows;               // batch * anchors
+  const unsigned long long* vp_step;              // this rank's counter: the step being contributed to
+  unsigned long long* vp_keys[OVDET_MAX_PEERS];   // keys[2][vp_rows] of every rank (peer-mapped)
   int dbg;
 };
 
@@ -513,10 +516,11 @@ sim_fused_kernel(const __grid_constant__ LevelMaps amaps, const __grid_constant_
     const bool vp = p.vp_world > 0;
     const bool want_max = p.row_max != nullptr || vp;
     // a finished row: local (score, class) or, vocabulary-parallel, one max-reduction per rank
+    const long long vp_off = vp ? (long long)(__ldcg(p.vp_step) & 1ull) * p.vp_rows : 0;
     auto emit_row = [&](long long row, float v, int idx) {
       if (vp) {
         const unsigned long long key = vp_pack_key(v, p.vp_class_offset + idx);
-        for (int g = 0; g < p.vp_world; ++g) atomicMax_system(p.vp_keys[g] + row, key);
+        for (int g = 0; g < p.vp_world; ++g) atomicMax_system(p.vp_keys[g] + vp_off + row, key);
       } else {
         p.row_max[row] = v;
         if (p.row_arg != nullptr) p.row_arg[row] = idx;
@@ -859,7 +863,7 @@ int fused_launch(const float* const* obj_embeds, const int64_t* hw, const int64_
   const int proj = level_ops != nullptr;
   if (vp) {                                         // vocabulary-parallel: keys instead of row_max / row_arg
     if (proj || split3 || logits || row_max || row_arg || alpha < 0.f) return OVDET_ERR_INVALID_ARG;
-    if (vp->world < 1 || vp->world > OVDET_MAX_PEERS || vp->class_offset < 0) return OVDET_ERR_INVALID_ARG;
+    if (vp->world < 1 || vp->world > OVDET_MAX_PEERS || vp->class_offset < 0 || !vp->step) return OVDET_ERR_INVALID_ARG;
     for (int g = 0; g < vp->world; ++g)
       if (!vp->keys[g] || ((uintptr_t)vp->keys[g] & 7)) return OVDET_ERR_INVALID_ARG;
   }
@@ -966,6 +970,8 @@ int fused_launch(const float* const* obj_embeds, const int64_t* hw, const int64_
   if (vp) {
     p.vp_world = vp->world;
     p.vp_class_offset = vp->class_offset;
+    p.vp_rows = vp->rows;
+    p.vp_step = vp->step;
     for (int g = 0; g < vp->world; ++g) p.vp_keys[g] = vp->keys[g];
   }
   // small launch: split the class tiles of every anchor tile over the idle CTA pairs

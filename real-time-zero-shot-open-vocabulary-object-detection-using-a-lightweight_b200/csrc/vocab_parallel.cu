@@ -9,6 +9,10 @@
 //   * the unpack of the merged keys into the scores / class ids K3 and K4 read,
 //   * pack / unpack for the library-collective baseline (all-reduce MAX over int64).
 //
+// Step counters live in the rank's own buffer (ctr[0] = step its next similarity kernel
+// contributes to, ctr[1] = step its next wait_unpack consumes; the signal kernel moves both), so no
+// kernel argument changes from step to step and the whole sequence can be replayed from a CUDA graph.
+//
 // Ordering argument (why one parity bit is enough).  Rank r hands keys[p] back (writes 0) in its
 // wait_unpack of step s.  A peer q touches r's keys[p] again in its similarity kernel of step
 // s + 2, which its stream runs after its wait_unpack of step s + 1, which returns only after r's
@@ -29,15 +33,26 @@ __host__ __device__ inline size_t vp_flags_offset(long long rows) {
   return ((size_t)rows * 16 + 127) / 128 * 128;            // after keys[2][rows]
 }
 
-__global__ void vp_signal_kernel(VpTarget t, long long flags_off, int rank, unsigned long long step) {
+// flags block (128 bytes): flags[8] u64, then ctr[2] u64
+constexpr int kCtrOffset = 64;
+
+__global__ void vp_signal_kernel(VpTarget t, long long flags_off, int rank) {
   // the similarity kernel of this step has completed (stream order); make its atomics and this
   // store ordered for every observer
+  unsigned long long* ctr = reinterpret_cast<unsigned long long*>(
+      reinterpret_cast<char*>(t.keys[rank]) + flags_off + kCtrOffset);
+  const unsigned long long step = __ldcg(ctr);
   __threadfence_system();
   const int g = threadIdx.x;
   if (g < t.world) {
     unsigned long long* flag = reinterpret_cast<unsigned long long*>(
         reinterpret_cast<char*>(t.keys[g]) + flags_off) + rank;
     asm volatile("st.release.sys.global.u64 [%0], %1;" :: "l"(flag), "l"(step) : "memory");
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    ctr[1] = step;                  // what this rank's wait_unpack consumes next
+    ctr[0] = step + 1;              // what its next similarity kernel contributes to
   }
 }
 
@@ -53,11 +68,13 @@ __device__ __forceinline__ unsigned long long global_timer_ns() {
 }
 
 __global__ void __launch_bounds__(256)
-vp_wait_unpack_kernel(unsigned long long* keys, const unsigned long long* flags, int world, long long rows,
-                      unsigned long long step, float* __restrict__ scores, int* __restrict__ class_ids,
+vp_wait_unpack_kernel(unsigned long long* keys2, const unsigned long long* flags, int world, long long rows,
+                      float* __restrict__ scores, int* __restrict__ class_ids,
                       int* status, unsigned long long timeout_ns) {
   __shared__ int s_timeout;
   if (threadIdx.x == 0) s_timeout = 0;
+  const unsigned long long step = __ldcg(flags + kCtrOffset / 8 + 1);
+  unsigned long long* keys = keys2 + (long long)(step & 1ull) * rows;
   __syncthreads();
   if ((int)threadIdx.x < world) {
     const unsigned long long t0 = global_timer_ns();
@@ -80,9 +97,9 @@ vp_wait_unpack_kernel(unsigned long long* keys, const unsigned long long* flags,
   keys[i] = 0ull;                                        // handed back for step + 2
 }
 
-__global__ void vp_init_kernel(unsigned long long* buf, long long words) {
+__global__ void vp_init_kernel(unsigned long long* buf, long long words, long long ctr0_word) {
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < words) buf[i] = 0ull;
+  if (i < words) buf[i] = i == ctr0_word ? 1ull : 0ull;       // first step is 1
 }
 
 __global__ void pack_keys_kernel(const float* __restrict__ scores, const int* __restrict__ class_ids,
@@ -101,13 +118,17 @@ __global__ void unpack_keys_kernel(const long long* __restrict__ keys, long long
   class_ids[i] = c;
 }
 
-int fill_target(VpTarget& t, void* const* peer_buffers, int world, long long rows, long long step) {
-  if (!peer_buffers || world < 1 || world > OVDET_MAX_PEERS || rows <= 0 || step < 1) return OVDET_ERR_INVALID_ARG;
+int fill_target(VpTarget& t, void* const* peer_buffers, int world, int rank, long long rows) {
+  if (!peer_buffers || world < 1 || world > OVDET_MAX_PEERS || rows <= 0 || rank < 0 || rank >= world)
+    return OVDET_ERR_INVALID_ARG;
   t.world = world;
+  t.rows = rows;
   for (int g = 0; g < world; ++g) {
     if (!peer_buffers[g] || ((uintptr_t)peer_buffers[g] & 127)) return OVDET_ERR_INVALID_ARG;
-    t.keys[g] = static_cast<unsigned long long*>(peer_buffers[g]) + (step & 1) * rows;
+    t.keys[g] = static_cast<unsigned long long*>(peer_buffers[g]);
   }
+  t.step = reinterpret_cast<const unsigned long long*>(
+      static_cast<char*>(peer_buffers[rank]) + vp_flags_offset(rows) + kCtrOffset);
   return OVDET_OK;
 }
 
@@ -164,7 +185,7 @@ extern "C" int ovdet_vp_buffer_init(void* buffer, int64_t rows, int world, void*
   if (int rc = check_device()) return rc;
   const long long words = (long long)(ovdet_vp_buffer_bytes(rows, world) / 8);
   vp_init_kernel<<<(unsigned)ceil_div<long long>(words, 256), 256, 0, as_stream(stream)>>>(
-      static_cast<unsigned long long*>(buffer), words);
+      static_cast<unsigned long long*>(buffer), words, (long long)((vp_flags_offset(rows) + kCtrOffset) / 8));
   OVDET_LAUNCH_CHECK();
   return OVDET_OK;
 }
@@ -175,7 +196,7 @@ extern "C" int ovdet_similarity_fused_vp(const void* const* obj_embeds, const in
                                          int64_t classes, int text_batched, float alpha, float beta,
                                          float* inv_norm, void* workspace, size_t workspace_bytes,
                                          int embed_dtype, int64_t class_offset,
-                                         void* const* peer_buffers, int world, int64_t step, void* stream) {
+                                         void* const* peer_buffers, int world, int rank, void* stream) {
   if (dim % 64 != 0) return OVDET_ERR_UNSUPPORTED_SHAPE;
   if (!hw || num_levels <= 0 || num_levels > OVDET_MAX_LEVELS || batch < 0) return OVDET_ERR_INVALID_ARG;
   if (class_offset < 0 || class_offset + classes >= (1ll << 31)) return OVDET_ERR_INVALID_ARG;
@@ -183,7 +204,7 @@ extern "C" int ovdet_similarity_fused_vp(const void* const* obj_embeds, const in
   for (int l = 0; l < num_levels; ++l) anchors += hw[l];
   VpTarget t{};
   if (batch == 0) return check_device();
-  if (int rc = fill_target(t, peer_buffers, world, batch * anchors, step)) return rc;
+  if (int rc = fill_target(t, peer_buffers, world, rank, batch * anchors)) return rc;
   t.class_offset = (int)class_offset;
   return fused_launch(reinterpret_cast<const float* const*>(obj_embeds), hw, stride_b, stride_d, num_levels,
                       batch, dim, text_op, nullptr, classes, text_batched, 1, 0, alpha, beta, nullptr,
@@ -191,32 +212,27 @@ extern "C" int ovdet_similarity_fused_vp(const void* const* obj_embeds, const in
                       workspace, workspace_bytes, &t);
 }
 
-extern "C" int ovdet_vp_signal(void* const* peer_buffers, int world, int rank, int64_t rows, int64_t step,
-                               void* stream) {
+extern "C" int ovdet_vp_signal(void* const* peer_buffers, int world, int rank, int64_t rows, void* stream) {
   VpTarget t{};
-  if (rank < 0 || rank >= world) return OVDET_ERR_INVALID_ARG;
-  if (int rc = fill_target(t, peer_buffers, world, rows, step)) return rc;
-  for (int g = 0; g < world; ++g) t.keys[g] = static_cast<unsigned long long*>(peer_buffers[g]);   // buffer bases
+  if (int rc = fill_target(t, peer_buffers, world, rank, rows)) return rc;
   if (int rc = check_device()) return rc;
-  vp_signal_kernel<<<1, 32, 0, as_stream(stream)>>>(t, (long long)vp_flags_offset(rows), rank,
-                                                    (unsigned long long)step);
+  vp_signal_kernel<<<1, 32, 0, as_stream(stream)>>>(t, (long long)vp_flags_offset(rows), rank);
   OVDET_LAUNCH_CHECK();
   return OVDET_OK;
 }
 
-extern "C" int ovdet_vp_wait_unpack(void* local_buffer, int world, int64_t rows, int64_t step,
+extern "C" int ovdet_vp_wait_unpack(void* local_buffer, int world, int64_t rows,
                                     float* scores, int32_t* class_ids, int32_t* status, int timeout_ms,
                                     void* stream) {
   if (!local_buffer || ((uintptr_t)local_buffer & 127) || !scores || !class_ids) return OVDET_ERR_INVALID_ARG;
-  if (world < 1 || world > OVDET_MAX_PEERS || rows <= 0 || step < 1 || timeout_ms < 0) return OVDET_ERR_INVALID_ARG;
+  if (world < 1 || world > OVDET_MAX_PEERS || rows <= 0 || timeout_ms < 0) return OVDET_ERR_INVALID_ARG;
   if (int rc = check_device()) return rc;
   unsigned long long* base = static_cast<unsigned long long*>(local_buffer);
   const unsigned long long* flags = reinterpret_cast<const unsigned long long*>(
       static_cast<char*>(local_buffer) + vp_flags_offset(rows));
   const unsigned long long timeout_ns = (unsigned long long)(timeout_ms ? timeout_ms : 2000) * 1000000ull;
   vp_wait_unpack_kernel<<<(unsigned)ceil_div<long long>(rows, 256), 256, 0, as_stream(stream)>>>(
-      base + (step & 1) * rows, flags, world, rows, (unsigned long long)step, scores, class_ids, status,
-      timeout_ns);
+      base, flags, world, rows, scores, class_ids, status, timeout_ns);
   OVDET_LAUNCH_CHECK();
   return OVDET_OK;
 }

@@ -220,6 +220,18 @@ class HeadPipeline:
             self.set_vocabulary(text)
         elif not self._vocab_ready:
             raise RuntimeError("ovdet: no vocabulary set (call set_vocabulary or pass text)")
+        a = self._fill_step_args(obj_embeds, box_preds)
+        self.last_path = "fused"
+        with torch.cuda.device(self.device):
+            _cabi.check(_cabi.lib().ovdet_head_step(ctypes.byref(a),
+                                                    torch.cuda.current_stream(self.device).cuda_stream),
+                        "ovdet_head_step")
+        return self.result
+
+    def _fill_step_args(self, obj_embeds, box_preds) -> "_cabi.HeadStepArgs":
+        """The ``ovdet_head_step_args`` of this pipeline (built once; per call only the input
+        pointers, strides and dtypes are refreshed)."""
+        cfg = self.cfg
         a = self._step_args
         if a is None:
             a = _cabi.HeadStepArgs()
@@ -257,12 +269,7 @@ class HeadPipeline:
         a.box_dtype = _cabi.OVDET_BF16 if box_preds[0].dtype == torch.bfloat16 else _cabi.OVDET_F32
         a.scale = self.scale.data_ptr() if self.use_geometry else None
         a.clip_wh = self.clip_wh.data_ptr() if self.use_geometry else None
-        self.last_path = "fused"
-        with torch.cuda.device(self.device):
-            _cabi.check(_cabi.lib().ovdet_head_step(ctypes.byref(a),
-                                                    torch.cuda.current_stream(self.device).cuda_stream),
-                        "ovdet_head_step")
-        return self.result
+        return a
 
     def _run_projected(self, hidden, box_preds, text, mark) -> ops.NmsResult:
         cfg = self.cfg

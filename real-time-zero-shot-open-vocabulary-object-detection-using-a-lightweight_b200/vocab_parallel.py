@@ -158,7 +158,6 @@ class VocabParallelHead:
         self.pipe = HeadPipeline(batch, level_shapes, self.c1 - self.c0, config, device=device)
         self.device = self.pipe.device
         self.rows = batch * self.pipe.anchors
-        self.step = 0
         self.status = torch.zeros(1, device=self.device, dtype=torch.int32)
         self.timeout_ms = 2000
         self._sim_ws = None
@@ -207,7 +206,6 @@ class VocabParallelHead:
         pipe, cfg = self.pipe, self.cfg
         if not ops.fused_supported(obj_embeds) or cfg.embed_dim != 512:
             raise ValueError("ovdet: inputs not addressable by the fused similarity kernel")
-        self.step += 1
         first = obj_embeds[0]
         n = len(obj_embeds)
         ptrs = (ctypes.c_void_p * n)(*[e.data_ptr() for e in obj_embeds])
@@ -226,7 +224,7 @@ class VocabParallelHead:
                     self.c1 - self.c0, 0, float(cfg.cls_alpha), float(cfg.cls_beta), pipe.inv_norm.data_ptr(),
                     self._sim_ws.data_ptr(), self._sim_ws.numel(),
                     _cabi.OVDET_BF16 if in16 else _cabi.OVDET_F32, self.c0, self.peer_ptrs, self.world,
-                    self.step, stream), "ovdet_similarity_fused_vp")
+                    self.rank, stream), "ovdet_similarity_fused_vp")
             else:
                 ops.similarity_fused(obj_embeds, pipe.text_op, cfg.cls_alpha, cfg.cls_beta, logits_dtype=None,
                                      want_max=True, row_max=pipe.scores, row_arg=pipe.class_ids,
@@ -234,7 +232,7 @@ class VocabParallelHead:
 
     def signal(self) -> None:
         with torch.cuda.device(self.device):
-            check(lib().ovdet_vp_signal(self.peer_ptrs, self.world, self.rank, self.rows, self.step,
+            check(lib().ovdet_vp_signal(self.peer_ptrs, self.world, self.rank, self.rows,
                                         torch.cuda.current_stream(self.device).cuda_stream), "ovdet_vp_signal")
 
     def merge(self) -> None:
@@ -242,7 +240,7 @@ class VocabParallelHead:
         pipe = self.pipe
         with torch.cuda.device(self.device):
             if self.exchange == "fused":
-                check(lib().ovdet_vp_wait_unpack(self.buffer.ptr, self.world, self.rows, self.step,
+                check(lib().ovdet_vp_wait_unpack(self.buffer.ptr, self.world, self.rows,
                                                  pipe.scores.data_ptr(), pipe.class_ids.data_ptr(),
                                                  self.status.data_ptr(), self.timeout_ms,
                                                  torch.cuda.current_stream(self.device).cuda_stream),
@@ -254,12 +252,40 @@ class VocabParallelHead:
 
     def run(self, obj_embeds: Sequence[torch.Tensor], box_preds: Sequence[torch.Tensor]):
         """One pass: sharded similarity + exchange, then K3 / K4 on the merged scores.  Every rank
-        returns the same detections."""
+        returns the same detections.  With the fused exchange the whole step is one C call
+        (``ovdet_head_step_vp``) whose arguments never change, so it can also be captured in a CUDA
+        graph (``capture`` / ``replay``)."""
+        if self.exchange == "fused" and self.pipe._single_call_ok(box_preds):
+            if not ops.fused_supported(obj_embeds) or self.cfg.embed_dim != 512:
+                raise ValueError("ovdet: inputs not addressable by the fused similarity kernel")
+            a = self.pipe._fill_step_args(obj_embeds, box_preds)
+            with torch.cuda.device(self.device):
+                check(lib().ovdet_head_step_vp(ctypes.byref(a), self.c0, self.peer_ptrs, self.world, self.rank,
+                                               self.status.data_ptr(), self.timeout_ms,
+                                               torch.cuda.current_stream(self.device).cuda_stream),
+                      "ovdet_head_step_vp")
+            return self.pipe.result
         self.similarity(obj_embeds)
         if self.exchange == "fused":
             self.signal()
         self.merge()
         return self.finish(box_preds)
+
+    def capture(self, obj_embeds: Sequence[torch.Tensor], box_preds: Sequence[torch.Tensor]) -> None:
+        """Record one step into a CUDA graph (fused exchange only: its step counters live in device
+        memory).  Every rank must capture, and later replay the same number of times."""
+        assert self.exchange == "fused"
+        self.run(obj_embeds, box_preds)                       # warm: attributes, workspaces, tensor maps
+        torch.cuda.synchronize(self.device)
+        if self._dist is not None:
+            self._dist.barrier(group=self.group)
+        self._graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self._graph):
+            self.run(obj_embeds, box_preds)
+
+    def replay(self):
+        self._graph.replay()
+        return self.pipe.result
 
     def finish(self, box_preds: Sequence[torch.Tensor]):
         return self.pipe._decode_and_nms(box_preds, lambda name, begin: None)

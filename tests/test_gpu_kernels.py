@@ -747,6 +747,46 @@ def test_vocab_parallel_virtual_ranks_equal_full_vocabulary(ov, cuda_device, wor
             h.close()
 
 
+def test_vocab_parallel_single_call_and_graph(ov, cuda_device):
+    """ovdet_head_step_vp (the whole sharded step behind one C call) and its CUDA-graph replay, with
+    a world of one rank - the exchange then runs against the rank's own buffer, through the same
+    kernels and counters as across GPUs."""
+    from ovdet import synth
+    from ovdet import vocab_parallel as vp
+    from ovdet.pipeline import HeadConfig, HeadPipeline
+    shapes = [(32, 32), (16, 16), (8, 8)]
+    cfg = HeadConfig(precision="bf16", max_det=64)
+    ins = [synth.make_inputs(batch=2, image_size=256, num_classes=300, seed=s, device=cuda_device)
+           for s in (61, 62)]
+    full = HeadPipeline(2, shapes, 300, cfg, device=cuda_device)
+    full.set_vocabulary(ins[0].text)
+    head = vp.VocabParallelHead(2, shapes, 300, cfg, device=cuda_device, rank=0, world=1)
+    head.connect([head.buffer.ptr])
+    head.set_vocabulary(ins[0].text)
+    try:
+        def check(res, x):
+            r = full.run(x.obj_embeds, x.box_preds, events={})
+            torch.cuda.synchronize()
+            assert torch.equal(head.scores, full.scores) and torch.equal(head.class_ids, full.class_ids)
+            assert torch.equal(res.count, r.count) and int(r.count.sum()) > 0
+            for b, k in enumerate(r.count.tolist()):
+                assert torch.equal(res.anchor[b, :k], r.anchor[b, :k])
+        for it in range(4):
+            x = ins[it % 2]
+            check(head.run(x.obj_embeds, x.box_preds), x)
+        bufs_e = [t.clone() for t in ins[0].obj_embeds]
+        bufs_p = [t.clone() for t in ins[0].box_preds]
+        head.capture(bufs_e, bufs_p)
+        for it in range(5):                                   # odd count: both key-array parities
+            x = ins[it % 2]
+            for dst, src in zip(bufs_e + bufs_p, x.obj_embeds + x.box_preds):
+                dst.copy_(src)
+            check(head.replay(), x)
+        assert not head.timed_out()
+    finally:
+        head.close()
+
+
 def test_vocab_parallel_wait_is_bounded(ov, cuda_device):
     """A rank whose peer never signals does not hang the GPU: the wait expires and is reported."""
     from ovdet import synth

@@ -42,6 +42,8 @@ def main():
         for batch in args.batch:
             # the same inputs on every rank (the batch is replicated, the vocabulary sharded)
             inp = synth.make_inputs(batch=batch, image_size=s, num_classes=classes, device=dev, seed=77)
+            for t in inp.obj_embeds + inp.box_preds + [inp.text]:
+                dist.broadcast(t, 0)                            # byte-identical on every rank
             full = HeadPipeline(batch, shapes, classes, cfg, device=dev)
             full.set_vocabulary(inp.text)
             r = full.run(inp.obj_embeds, inp.box_preds, events={})
@@ -52,11 +54,13 @@ def main():
                 head = vp.VocabParallelHead(batch, shapes, classes, cfg, device=dev, exchange=mode)
                 head.set_vocabulary(inp.text)
                 ok = True
+                bad_scores = 0
                 for _ in range(3):                              # parity over both buffer parities
                     res = head.run(inp.obj_embeds, inp.box_preds)
                     torch.cuda.synchronize()
                     ok &= torch.equal(head.scores, want[0]) and torch.equal(res.count, want[2])
                     same_cls = float((head.class_ids == want[1]).float().mean())
+                    bad_scores += int((head.scores != want[0]).sum())
                     for b, k in enumerate(want[2].tolist()):
                         ok &= torch.equal(res.anchor[b, :k], want[3][b, :k])
                 for _ in range(args.warmup):
@@ -73,9 +77,25 @@ def main():
                 p50 = statistics.median(a.elapsed_time(b) for a, b in ev)
                 total = ev[0][0].elapsed_time(ev[-1][1]) / args.steps
                 timed_out = head.timed_out() if mode == "fused" else False
-                line[mode] = {"parity": bool(ok), "class_agreement": same_cls,
+                line[mode] = {"parity": bool(ok), "class_agreement": same_cls, "score_mismatches": bad_scores,
                               "p50_ms": shard.max_over_ranks(p50, dev),
                               "ms_per_step": shard.max_over_ranks(total, dev), "timed_out": timed_out}
+                if mode == "fused":
+                    # the same step replayed from a CUDA graph (device-resident step counters)
+                    head.capture(inp.obj_embeds, inp.box_preds)
+                    for _ in range(args.warmup):
+                        head.replay()
+                    dist.barrier()
+                    torch.cuda.synchronize()
+                    for a, b in ev:
+                        a.record()
+                        res = head.replay()
+                        b.record()
+                    torch.cuda.synchronize()
+                    g_ok = torch.equal(head.scores, want[0]) and torch.equal(res.count, want[2])
+                    line[mode]["graph_p50_ms"] = shard.max_over_ranks(
+                        statistics.median(a.elapsed_time(b) for a, b in ev), dev)
+                    line[mode]["graph_parity"] = bool(g_ok) and not head.timed_out()
                 head.close()
             # one GPU, whole vocabulary, same step
             for _ in range(args.warmup):
@@ -91,6 +111,16 @@ def main():
             line["one_gpu_full_vocabulary"] = {
                 "p50_ms": statistics.median(a.elapsed_time(b) for a, b in ev),
                 "ms_per_step": ev[0][0].elapsed_time(ev[-1][1]) / args.steps}
+            full.capture(inp.obj_embeds, inp.box_preds)
+            for _ in range(args.warmup):
+                full.replay()
+            torch.cuda.synchronize()
+            for a, b in ev:
+                a.record()
+                full.replay()
+                b.record()
+            torch.cuda.synchronize()
+            line["one_gpu_full_vocabulary"]["graph_p50_ms"] = statistics.median(a.elapsed_time(b) for a, b in ev)
             if rank == 0:
                 print(json.dumps(line), flush=True)
             del full
