@@ -112,8 +112,9 @@ def test_new_entries_validate_arguments(handle):
     assert handle.ovdet_peer_buffer_create(0, None, None) == -1
     assert handle.ovdet_peer_buffer_open(None, None) == -1
     assert handle.ovdet_vp_buffer_init(None, 10, 2, None) == -1
-    assert handle.ovdet_vp_signal(None, 2, 0, 10, 1, None) == -1
-    assert handle.ovdet_vp_wait_unpack(None, 2, 10, 1, None, None, None, 0, None) == -1
+    assert handle.ovdet_vp_signal(None, 2, 0, 10, None) == -1
+    assert handle.ovdet_vp_wait_unpack(None, 2, 10, None, None, None, 0, None) == -1
+    assert handle.ovdet_head_step_vp(None, 0, None, 2, 0, None, 0, None) == -1
     assert handle.ovdet_pack_score_keys(None, None, 1, 0, None, None) == -1
     assert handle.ovdet_unpack_score_keys(None, 1, None, None, None) == -1
 
