@@ -42,6 +42,8 @@
 #include "common.cuh"
 #include "ptx.cuh"
 #include <cstdlib>
+#include <cstring>
+#include <mutex>
 
 namespace ovdet {
 namespace {
@@ -82,7 +84,8 @@ struct FSmem {
   static constexpr int b_off = 0;
   static constexpr int a_off = b_off + b_stages * b_stage_bytes;                     // 64 KiB
   static constexpr int epi_off = a_off + F_A_STAGES * F_A_STAGE_BYTES;               // +128 KiB
-  static constexpr int epi_bytes = 4 * 32 * F_VPITCH * 4;
+  static constexpr int epi_warp_bytes = 32 * F_VPITCH * 4;           // 4608: fp32 staging, or two 2 KiB TMA-store buffers
+  static constexpr int epi_bytes = 4 * epi_warp_bytes;
   static constexpr int norm_off = epi_off + epi_bytes;
   static constexpr int norm_bytes = 3 * F_BLOCK_M * 4;
   static constexpr int bar_off = norm_off + norm_bytes;
@@ -117,6 +120,7 @@ struct FusedParams {
   float alpha, beta;
   void* logits;
   int logits_bf16;
+  int logits_tma;                  // bf16 logits leave through TMA stores (cmaps: one [classes, hw, batch] map per level)
   long long ldc;
   float* row_max;
   int* row_arg;
@@ -187,7 +191,7 @@ __device__ __forceinline__ TileCoord decode_tile(const FusedParams& p, int tile)
 template <int KB_T, bool SPLIT3, int CG, bool PROJ, bool IN16 = false>
 __global__ void __launch_bounds__(F_THREADS, 1)
 sim_fused_kernel(const __grid_constant__ LevelMaps amaps, const __grid_constant__ LevelMaps bmaps,
-                 const FusedParams p) {
+                 const __grid_constant__ LevelMaps cmaps, const FusedParams p) {
   using FSmem = ovdet::FSmem<CG>;
   constexpr int F_B_STAGES = FSmem::b_stages;
   constexpr int F_B_STAGE_BYTES = FSmem::b_stage_bytes;
@@ -512,7 +516,9 @@ sim_fused_kernel(const __grid_constant__ LevelMaps amaps, const __grid_constant_
   } else if (warp >= 8) {
     // ================================ epilogue ===============================================
     const int lg = warp & 3;
-    float* stage = epi_stage + lg * 32 * F_VPITCH;
+    float* stage = epi_stage + lg * (FSmem::epi_warp_bytes / 4);
+    const uint32_t stage_u32 = ptx::smem_u32(stage);          // 4608 bytes per warp, 512-byte aligned
+    uint32_t tma_chunk = 0;
     const bool vp = p.vp_world > 0;
     const bool want_max = p.row_max != nullptr || vp;
     // a finished row: local (score, class) or, vocabulary-parallel, one max-reduction per rank
@@ -631,7 +637,37 @@ sim_fused_kernel(const __grid_constant__ LevelMaps amaps, const __grid_constant_
               }
             }
           }
-          if (p.logits != nullptr && vec_logits && p.logits_bf16) {
+          if (p.logits_tma) {
+            // bf16 logits, 16-byte aligned rows: the warp's 32 x 32 block goes to shared memory (64-byte
+            // rows in the 64-byte swizzle pattern: the 16-byte writes by row are bank-conflict free)
+            // and leaves as ONE bulk tensor store; rows past the level's last anchor and columns past
+            // the last class are clipped by the TMA unit.  Two buffers per warp: the store of chunk
+            // c - 1 may still be reading its buffer while chunk c is packed (a third buffer measured no
+            // faster: the epilogue's arithmetic, not the store queue, sets the pace).  The per-thread
+            // 16-byte global stores this replaces (32 rows per instruction) were LSU-bound.
+            const uint32_t buf = stage_u32 + (tma_chunk & 1u) * 2048u;
+            ++tma_chunk;
+            if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+            __syncwarp();
+            const uint32_t rowaddr = buf + lane * 64u;
+            const uint32_t sw = (lane >> 1) & 3u;
+#pragma unroll
+            for (int v = 0; v < 4; ++v)
+              asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::
+                  "r"(rowaddr + (((uint32_t)v ^ sw) << 4)),
+                  "r"(pack_bf16x2(__uint_as_float(r[8 * v + 0]), __uint_as_float(r[8 * v + 1]))),
+                  "r"(pack_bf16x2(__uint_as_float(r[8 * v + 2]), __uint_as_float(r[8 * v + 3]))),
+                  "r"(pack_bf16x2(__uint_as_float(r[8 * v + 4]), __uint_as_float(r[8 * v + 5]))),
+                  "r"(pack_bf16x2(__uint_as_float(r[8 * v + 6]), __uint_as_float(r[8 * v + 7]))) : "memory");
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            __syncwarp();
+            if (lane == 0 && tc.rows > lg * 32) {
+              asm volatile(
+                  "cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%1, %2, %3}], [%4];"
+                  :: "l"(&cmaps.m[tc.level]), "r"(n0 + c0), "r"(tc.m0 + lg * 32), "r"(tc.b), "r"(buf) : "memory");
+              asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+            }
+          } else if (p.logits != nullptr && vec_logits && p.logits_bf16) {
             // 16-byte aligned rows (padded leading dimension), bf16: every thread writes its own
             // row's 32 classes (64 bytes) straight from registers with four 16-byte stores; measured
             // faster than turning the block through shared memory (3.15 vs 3.48 ms at batch 256).
@@ -819,6 +855,8 @@ sim_fused_kernel(const __grid_constant__ LevelMaps amaps, const __grid_constant_
         emit_row(grow, best, best_idx);
       }
     }
+    // outstanding logit stores read this warp's staging buffers
+    if (p.logits_tma && lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
   }
 
   ptx::tc_fence_before();
@@ -845,6 +883,52 @@ EncodeTiledFn fused_encode_fn() {
     return reinterpret_cast<EncodeTiledFn>(f);
   }();
   return fn;
+}
+
+// Tensor maps are a pure function of the encode arguments, so they are cached by those arguments
+// ("an internal cache of CUtensorMaps keyed by (ptr, dims, strides)"): a serving
+// loop that reuses its buffers pays cuTensorMapEncodeTiled once per buffer, not four to eight
+// times per step.  64 entries, round-robin replacement, one mutex; a stale entry can never be
+// returned for different arguments because the whole argument list is the key.
+struct MapKey {
+  const void* addr;
+  cuuint64_t dims[3], strides[2];
+  cuuint32_t box[3];
+  int dtype, swizzle, l2;
+  bool operator==(const MapKey& o) const { return memcmp(this, &o, sizeof(MapKey)) == 0; }
+};
+struct MapCache {
+  static constexpr int kEntries = 64;
+  std::mutex mu;
+  MapKey keys[kEntries];
+  CUtensorMap maps[kEntries];
+  int used = 0, next = 0;
+};
+
+CUresult encode3(EncodeTiledFn enc, CUtensorMap* out, CUtensorMapDataType dtype, const void* addr,
+                 const cuuint64_t (&dims)[3], const cuuint64_t (&strides)[2], const cuuint32_t (&box)[3],
+                 CUtensorMapSwizzle swizzle, CUtensorMapL2promotion l2) {
+  static MapCache cache;
+  MapKey k;
+  memset(&k, 0, sizeof(k));                          // padding bytes take part in the comparison
+  k.addr = addr;
+  for (int i = 0; i < 3; ++i) { k.dims[i] = dims[i]; k.box[i] = box[i]; }
+  k.strides[0] = strides[0]; k.strides[1] = strides[1];
+  k.dtype = (int)dtype; k.swizzle = (int)swizzle; k.l2 = (int)l2;
+  {
+    std::lock_guard<std::mutex> lock(cache.mu);
+    for (int i = 0; i < cache.used; ++i)
+      if (cache.keys[i] == k) { *out = cache.maps[i]; return CUDA_SUCCESS; }
+  }
+  const cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = enc(out, dtype, 3, const_cast<void*>(addr), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   swizzle, l2, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return r;
+  std::lock_guard<std::mutex> lock(cache.mu);
+  const int slot = cache.used < MapCache::kEntries ? cache.used++ : (cache.next++ % MapCache::kEntries);
+  cache.keys[slot] = k;
+  cache.maps[slot] = *out;
+  return CUDA_SUCCESS;
 }
 
 }  // namespace
@@ -891,7 +975,7 @@ int fused_launch(const float* const* obj_embeds, const int64_t* hw, const int64_
   const int cg = (cg_env == 2 && !split3 && ((!proj && kb == 8) || (proj && kb_in == 4))) ? 2 : 1;
   EncodeTiledFn enc = nullptr;
   FusedParams p{};
-  LevelMaps maps, bmaps;
+  LevelMaps maps, bmaps, cmaps;
   long long anchors = 0, tiles = 0;
   for (int l = 0; l < num_levels; ++l) {
     if (!obj_embeds[l] || hw[l] <= 0) return OVDET_ERR_INVALID_ARG;
@@ -920,12 +1004,10 @@ int fused_launch(const float* const* obj_embeds, const int64_t* hw, const int64_
     const cuuint64_t esz = in_bf16 ? 2 : 4;
     cuuint64_t strides[2] = {(cuuint64_t)stride_d[l] * esz, (cuuint64_t)stride_b[l] * esz};
     cuuint32_t box[3] = {(cuuint32_t)F_BLOCK_M, (cuuint32_t)F_BLOCK_K, 1};
-    cuuint32_t estr[3] = {1, 1, 1};
     if (batch == 1) strides[1] = (cuuint64_t)dim * stride_d[l] * esz;    // unused but must be valid
-    CUresult r = enc(&maps.m[l], in_bf16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3,
-                     const_cast<float*>(obj_embeds[l]),
-                     dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
-                     CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    CUresult r = encode3(enc, &maps.m[l], in_bf16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32,
+                         obj_embeds[l], dims, strides, box, CU_TENSOR_MAP_SWIZZLE_NONE,
+                         CU_TENSOR_MAP_L2_PROMOTION_L2_256B);
     if (r != CUDA_SUCCESS) return OVDET_ERR_DRIVER;
   }
   for (int l = num_levels; l < F_MAX_LEVELS; ++l) maps.m[l] = maps.m[0];
@@ -937,14 +1019,32 @@ int fused_launch(const float* const* obj_embeds, const int64_t* hw, const int64_
     cuuint64_t dims[3] = {(cuuint64_t)kop, (cuuint64_t)op_rows, (cuuint64_t)tb};
     cuuint64_t strides[2] = {(cuuint64_t)kop * 2, (cuuint64_t)op_rows * (cuuint64_t)kop * 2};
     cuuint32_t box[3] = {(cuuint32_t)F_BLOCK_K, (cuuint32_t)(F_BLOCK_N / cg), 1};
-    cuuint32_t estr[3] = {1, 1, 1};
     const void* op = proj ? level_ops[l] : text_op;
-    CUresult r = enc(&bmaps.m[l], CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(op), dims, strides,
-                     box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
-                     CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    CUresult r = encode3(enc, &bmaps.m[l], CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, op, dims, strides, box,
+                         CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B);
     if (r != CUDA_SUCCESS) return OVDET_ERR_DRIVER;
   }
   for (int l = (proj ? num_levels : 1); l < F_MAX_LEVELS; ++l) bmaps.m[l] = bmaps.m[0];
+  // bf16 logits with 16-byte aligned rows leave through TMA stores: one [classes, hw, batch] map per
+  // level over the level's rows of the [batch, anchors, ldc] array (OVDET_DBG=4: per-thread stores)
+  static const int dbg_env0 = []() { const char* e = getenv("OVDET_DBG"); return e ? atoi(e) : 0; }();
+  int logits_tma = 0;
+  if (logits && logits_dtype == OVDET_BF16 && !((uintptr_t)logits & 15) && (ldc * 2) % 16 == 0 && !(dbg_env0 & 4)) {
+    logits_tma = 1;
+    long long off = 0;
+    for (int l = 0; l < num_levels; ++l) {
+      cuuint64_t dims[3] = {(cuuint64_t)classes, (cuuint64_t)hw[l], (cuuint64_t)batch};
+      cuuint64_t strides[2] = {(cuuint64_t)ldc * 2, (cuuint64_t)anchors * (cuuint64_t)ldc * 2};
+      cuuint32_t box[3] = {32, 32, 1};
+      void* base = static_cast<char*>(logits) + (size_t)off * (size_t)ldc * 2;
+      CUresult r = encode3(enc, &cmaps.m[l], CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, base, dims, strides, box,
+                           CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_NONE);
+      if (r != CUDA_SUCCESS) { logits_tma = 0; break; }
+      off += hw[l];
+    }
+  }
+  for (int l = logits_tma ? num_levels : 0; l < F_MAX_LEVELS; ++l) cmaps.m[l] = maps.m[0];
+  p.logits_tma = logits_tma;
   p.levels = num_levels;
   p.batch = (int)batch;
   p.tile_start[num_levels] = (int)tiles;
@@ -1020,22 +1120,22 @@ int fused_launch(const float* const* obj_embeds, const int64_t* hw, const int64_
     attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    if (proj) OVDET_CUDA_TRY(cudaLaunchKernelEx(&cfg, sim_fused_kernel<4, false, 2, true>, maps, bmaps, p));
-    else if (in_bf16) OVDET_CUDA_TRY(cudaLaunchKernelEx(&cfg, sim_fused_kernel<8, false, 2, false, true>, maps, bmaps, p));
-    else OVDET_CUDA_TRY(cudaLaunchKernelEx(&cfg, sim_fused_kernel<8, false, 2, false>, maps, bmaps, p));
+    if (proj) OVDET_CUDA_TRY(cudaLaunchKernelEx(&cfg, sim_fused_kernel<4, false, 2, true>, maps, bmaps, cmaps, p));
+    else if (in_bf16) OVDET_CUDA_TRY(cudaLaunchKernelEx(&cfg, sim_fused_kernel<8, false, 2, false, true>, maps, bmaps, cmaps, p));
+    else OVDET_CUDA_TRY(cudaLaunchKernelEx(&cfg, sim_fused_kernel<8, false, 2, false>, maps, bmaps, cmaps, p));
     return OVDET_OK;
   }
   const int grid = (int)(tiles < sm_count() ? tiles : sm_count());
   if (in_bf16)
-    sim_fused_kernel<0, false, 1, false, true><<<grid, F_THREADS, FSmem<1>::bytes, as_stream(stream)>>>(maps, bmaps, p);
+    sim_fused_kernel<0, false, 1, false, true><<<grid, F_THREADS, FSmem<1>::bytes, as_stream(stream)>>>(maps, bmaps, cmaps, p);
   else if (proj)
-    sim_fused_kernel<0, false, 1, true><<<grid, F_THREADS, FSmem<1>::bytes, as_stream(stream)>>>(maps, bmaps, p);
+    sim_fused_kernel<0, false, 1, true><<<grid, F_THREADS, FSmem<1>::bytes, as_stream(stream)>>>(maps, bmaps, cmaps, p);
   else if (split3)
-    sim_fused_kernel<0, true, 1, false><<<grid, F_THREADS, FSmem<1>::bytes, as_stream(stream)>>>(maps, bmaps, p);
+    sim_fused_kernel<0, true, 1, false><<<grid, F_THREADS, FSmem<1>::bytes, as_stream(stream)>>>(maps, bmaps, cmaps, p);
   else if (p.kb == 8)
-    sim_fused_kernel<8, false, 1, false><<<grid, F_THREADS, FSmem<1>::bytes, as_stream(stream)>>>(maps, bmaps, p);
+    sim_fused_kernel<8, false, 1, false><<<grid, F_THREADS, FSmem<1>::bytes, as_stream(stream)>>>(maps, bmaps, cmaps, p);
   else
-    sim_fused_kernel<0, false, 1, false><<<grid, F_THREADS, FSmem<1>::bytes, as_stream(stream)>>>(maps, bmaps, p);
+    sim_fused_kernel<0, false, 1, false><<<grid, F_THREADS, FSmem<1>::bytes, as_stream(stream)>>>(maps, bmaps, cmaps, p);
   OVDET_LAUNCH_CHECK();
   return OVDET_OK;
 }
