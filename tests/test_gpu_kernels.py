@@ -787,6 +787,29 @@ def test_vocab_parallel_single_call_and_graph(ov, cuda_device):
         head.close()
 
 
+def test_vocab_parallel_across_gpus(ov, cuda_device):
+    """The real thing when the box has more than one GPU: one process per GPU under torchrun, CUDA
+    IPC peer mappings over NVLink, both exchange implementations and the graph replay against one
+    GPU holding the whole vocabulary (tools/vp_check.py --assert-parity)."""
+    import socket
+    import subprocess
+    import sys
+    n = torch.cuda.device_count()
+    if n < 2:
+        pytest.skip("needs at least 2 GPUs (measured runs: profiles/r1_vocab_parallel_n2.jsonl, _n8.jsonl)")
+    n = 2 if n < 4 else (4 if n < 8 else 8)
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    root = os.path.join(os.path.dirname(os.path.abspath(__file__)), "..")
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={n}",
+           "--master-addr", "127.0.0.1", "--master-port", str(port), os.path.join(root, "tools", "vp_check.py"),
+           "--classes", "1203", "--batch", "1", "3", "--image-size", "256", "--steps", "20", "--warmup", "3",
+           "--assert-parity"]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+
+
 def test_vocab_parallel_wait_is_bounded(ov, cuda_device):
     """A rank whose peer never signals does not hang the GPU: the wait expires and is reported."""
     from ovdet import synth

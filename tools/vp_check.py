@@ -29,7 +29,9 @@ def main():
     ap.add_argument("--image-size", type=int, default=640)
     ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=20)
+    ap.add_argument("--assert-parity", action="store_true", help="exit 1 on any mismatch or timeout")
     args = ap.parse_args()
+    failed = False
     rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
     local = int(os.environ.get("LOCAL_RANK", rank))
     torch.cuda.set_device(local)
@@ -96,6 +98,8 @@ def main():
                     line[mode]["graph_p50_ms"] = shard.max_over_ranks(
                         statistics.median(a.elapsed_time(b) for a, b in ev), dev)
                     line[mode]["graph_parity"] = bool(g_ok) and not head.timed_out()
+                    failed |= not line[mode]["graph_parity"]
+                failed |= (not ok) or timed_out or same_cls < 1.0
                 head.close()
             # one GPU, whole vocabulary, same step
             for _ in range(args.warmup):
@@ -125,7 +129,11 @@ def main():
                 print(json.dumps(line), flush=True)
             del full
             torch.cuda.empty_cache()
+    flag = torch.tensor([int(failed)], device=dev)
+    dist.all_reduce(flag, op=dist.ReduceOp.MAX)
     dist.destroy_process_group()
+    if args.assert_parity and int(flag.item()):
+        sys.exit(1)
 
 
 if __name__ == "__main__":
