@@ -123,7 +123,7 @@ def ncu_traffic(kernel_substr: str, batch: int):
     """DRAM bytes per launch (dram__bytes_read.sum + dram__bytes_write.sum) of the dominant kernel
     from the committed `ncu --set full` capture of this same workload (profiles/, batch 256);
     None when the run's shape differs from the captured one."""
-    path = os.path.join(ROOT, "profiles", "r1_ncu_full_pipeline_b256_v5.json")
+    path = os.path.join(ROOT, "profiles", "r1_ncu_full_pipeline_b256_v6.json")
     if batch != 256 or (IMAGE_SIZE, NUM_CLASSES) != (640, 1203) or not os.path.exists(path):
         return None
     scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
@@ -441,7 +441,7 @@ def run_ours(args):
         # north_star quotes nominal figures too: 2.25 PFLOP/s dense bf16, ~8 TB/s HBM3e
         roofline["frac_of_nominal"] = roofline["achieved"] / (2250.0 if roofline["bound"] == "tensor" else 8000.0)
         roofline.update({"traffic": None if proj else ncu_traffic("sim_fused" if fused else "sim_gemm", batch),
-                         "traffic_source": "profiles/r1_ncu_full_pipeline_b256_v5.json (ncu --set full, bytes per launch)",
+                         "traffic_source": "profiles/r1_ncu_full_pipeline_b256_v6.json (ncu --set full, bytes per launch)",
                          "algorithmic_bytes": alg_bytes, "algorithmic_flops": flops,
                          "ms_per_launch": stages["similarity"]})
         k1_bytes = batch * anchors * (EMBED_DIM * 4 + EMBED_DIM * 2 + 4)
