@@ -399,6 +399,39 @@ def test_full_size_properties(ov, cuda_device):
         assert again.anchor[i, :k].tolist() == list(range(k))
 
 
+@pytest.mark.parametrize("image_size,classes", [(1280, 1203), (640, 4800)])
+def test_config4_config5_shapes_vs_oracle(ov, cuda_device, image_size, classes):
+    """BASELINE configs[3] (1280^2: 33 600 anchors per image - the multi-chunk K4 path and the
+    vectorised K3) and configs[4] (4800 prompts: 38 class tiles per anchor tile) at full per-image
+    size, two images: scores inside the bf16 bar, post-processing bit-exact on identical inputs."""
+    from ovdet import synth
+    from ovdet.pipeline import HeadConfig, HeadPipeline
+    b = 2
+    inp = synth.make_inputs(batch=b, image_size=image_size, num_classes=classes, seed=7)
+    tail = ref_port.head_tail(inp.obj_embeds, inp.text_batched(), inp.box_preds)
+    s = image_size
+    shapes = [(s // 8, s // 8), (s // 16, s // 16), (s // 32, s // 32)]
+    pipe = HeadPipeline(b, shapes, classes, HeadConfig(precision="bf16"), device=cuda_device)
+    pipe.set_vocabulary(inp.text.to(cuda_device))
+    sizes = [(s, s)] * b
+    pipe.set_geometry(sizes, [1.0] * b)
+    res = pipe.run([e.to(cuda_device) for e in inp.obj_embeds], [p.to(cuda_device) for p in inp.box_preds])
+    torch.cuda.synchronize()
+    assert pipe.last_path == "fused"
+    assert_logits_close(pipe.scores, tail["scores"], "bf16")
+    agree = (pipe.class_ids.cpu().long() == tail["class_ids"]).float().mean()
+    assert agree >= 0.97                                  # bf16 near-ties between background classes
+    torch.testing.assert_close(pipe.boxes.cpu(), tail["boxes"], rtol=1e-4, atol=1e-3)
+    fed = {"boxes": pipe.boxes.cpu(), "scores": pipe.scores.cpu(), "class_ids": pipe.class_ids.cpu().long()}
+    want = ref_port.postprocess_batch(fed, sizes, [1.0] * b)
+    for i in range(b):
+        k = int(res.count[i])
+        assert k == len(want[i]["keep"]) and k > 20
+        np.testing.assert_array_equal(res.keep[i, :k].cpu().numpy(), want[i]["keep"])
+        np.testing.assert_array_equal(res.classes[i, :k].cpu().numpy(), want[i]["class_ids"])
+        np.testing.assert_array_equal(res.boxes[i, :k].cpu().numpy(), want[i]["boxes"])
+
+
 # ------------------------------------------------------------------------------------------
 # K1+K2 fused (fp32 NCHW in, A operand resident in tensor memory)
 # ------------------------------------------------------------------------------------------
