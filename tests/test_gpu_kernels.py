@@ -721,6 +721,33 @@ def test_single_call_step_with_changing_inputs(ov, cuda_device):
                 assert torch.equal(got[j][b, :k], ref[i][j][b, :k]), (it, j, b)
 
 
+def test_single_call_step_bench_shape_changing_inputs(ov, cuda_device):
+    """The same check at the benchmark's per-image shape (640^2, 1203 prompts, batch 32): here the
+    similarity kernel runs for hundreds of microseconds, so a K3 / K4 that did not wait for it would
+    read a mostly unwritten score array."""
+    from ovdet import synth
+    from ovdet.pipeline import HeadConfig, HeadPipeline
+    shapes = [(80, 80), (40, 40), (20, 20)]
+    ins = [synth.make_inputs(batch=32, image_size=640, num_classes=1203, seed=s, device=cuda_device)
+           for s in (71, 72)]
+    pipe = HeadPipeline(32, shapes, 1203, HeadConfig(precision="bf16", max_det=300), device=cuda_device)
+    pipe.set_vocabulary(ins[0].text)
+    ref = []
+    for x in ins:
+        r = pipe.run(x.obj_embeds, x.box_preds, events={})
+        torch.cuda.synchronize()
+        ref.append([t.clone() for t in (pipe.scores, pipe.pass_mask, pipe.boxes, r.count, r.anchor)])
+    assert not torch.equal(ref[0][1], ref[1][1])
+    for it in range(8):
+        i = it % 2
+        r = pipe.run(ins[i].obj_embeds, ins[i].box_preds)
+        torch.cuda.synchronize()
+        for j, g in enumerate((pipe.scores, pipe.pass_mask, pipe.boxes, r.count)):
+            assert torch.equal(g, ref[i][j]), (it, j)
+        for b, k in enumerate(ref[i][3].tolist()):
+            assert torch.equal(r.anchor[b, :k], ref[i][4][b, :k]), (it, b)
+
+
 # ------------------------------------------------------------------------------------------
 # Vocabulary-parallel exchange (SURVEY 8 e / f-4) on ONE device: several virtual ranks share the
 # GPU, their "peer" buffers are plain local pointers - the kernels cannot tell the difference.
