@@ -188,7 +188,11 @@ __device__ __forceinline__ TileCoord decode_tile(const FusedParams& p, int tile)
 // IN16: the activations arrive as bf16 (the head ran under autocast) instead of fp32: the TMA box
 // is [64 k x 128 anchors] bf16 (16 KiB of the 32 KiB stage), the converter widens, accumulates the
 // sum of squares in fp32 and re-packs - half the HBM and PCIe bytes of the fp32 input.
-template <int KB_T, bool SPLIT3, int CG, bool PROJ, bool IN16 = false>
+// MODE (what the epilogue produces; compile-time so that the scores-only kernel carries none of the
+// other modes' code or live registers - with them folded in at run time the projected mode lost 6 %
+// and the main mode 1.5 %): 0 = row max / argmax only, 1 = logits (and optionally max / argmax),
+// 2 = vocabulary-parallel keys.
+template <int KB_T, bool SPLIT3, int CG, bool PROJ, bool IN16 = false, int MODE = 0>
 __global__ void __launch_bounds__(F_THREADS, 1)
 sim_fused_kernel(const __grid_constant__ LevelMaps amaps, const __grid_constant__ LevelMaps bmaps,
                  const __grid_constant__ LevelMaps cmaps, const FusedParams p) {
@@ -519,7 +523,9 @@ sim_fused_kernel(const __grid_constant__ LevelMaps amaps, const __grid_constant_
     float* stage = epi_stage + lg * (FSmem::epi_warp_bytes / 4);
     const uint32_t stage_u32 = ptx::smem_u32(stage);          // 4608 bytes per warp, 512-byte aligned
     uint32_t tma_chunk = 0;
-    const bool vp = p.vp_world > 0;
+    constexpr bool vp = MODE == 2;
+    void* const logits_ptr = MODE == 1 ? p.logits : nullptr;
+    const bool logits_tma = MODE == 1 && p.logits_tma;
     const bool want_max = p.row_max != nullptr || vp;
     // a finished row: local (score, class) or, vocabulary-parallel, one max-reduction per rank
     const long long vp_off = vp ? (long long)(__ldcg(p.vp_step) & 1ull) * p.vp_rows : 0;
@@ -555,9 +561,9 @@ sim_fused_kernel(const __grid_constant__ LevelMaps amaps, const __grid_constant_
       // per value, no FFMA; the class returned is the argmax of the fp32 accumulators (lowest
       // index among equal accumulators).
       // logits rows start 16-byte aligned when the leading dimension is padded to 16 bytes
-      const bool vec_logits = p.logits != nullptr && ((uintptr_t)p.logits & 15) == 0 &&
+      const bool vec_logits = logits_ptr != nullptr && ((uintptr_t)logits_ptr & 15) == 0 &&
                               (p.ldc * (p.logits_bf16 ? 2 : 4)) % 16 == 0;
-      const bool raw_mode = PROJ || (want_max && p.logits == nullptr && p.alpha >= 0.f && !(p.dbg & 2));
+      const bool raw_mode = PROJ || (want_max && logits_ptr == nullptr && p.alpha >= 0.f && !(p.dbg & 2));
       const bool max_only = raw_mode && p.row_arg == nullptr && !vp;
       float raw_best = -INFINITY;
       for (int nt = nt_b; nt < nt_e; ++nt, ++acc_it) {
@@ -627,17 +633,23 @@ sim_fused_kernel(const __grid_constant__ LevelMaps amaps, const __grid_constant_
 #pragma unroll
               for (int j = 0; j < 32; ++j) {
                 const float v = __uint_as_float(r[j]);
-                if (v > bv[j & 3]) { bv[j & 3] = v; bi[j & 3] = col + j; }
+                const float old = bv[j & 3];
+                bv[j & 3] = fmaxf(old, v);                 // value chain: one FMNMX per element ...
+                if (v > old) bi[j & 3] = col + j;           // ... the predicate is off that chain
               }
             } else {
 #pragma unroll
               for (int j = 0; j < 32; ++j) {
                 const float v = __uint_as_float(r[j]);
-                if (j < valid && v > bv[j & 3]) { bv[j & 3] = v; bi[j & 3] = col + j; }
+                const float old = bv[j & 3];
+                if (j < valid) {
+                  bv[j & 3] = fmaxf(old, v);
+                  if (v > old) bi[j & 3] = col + j;
+                }
               }
             }
           }
-          if (p.logits_tma) {
+          if (logits_tma) {
             // bf16 logits, 16-byte aligned rows: the warp's 32 x 32 block goes to shared memory (64-byte
             // rows in the 64-byte swizzle pattern: the 16-byte writes by row are bank-conflict free)
             // and leaves as ONE bulk tensor store; rows past the level's last anchor and columns past
@@ -667,13 +679,13 @@ sim_fused_kernel(const __grid_constant__ LevelMaps amaps, const __grid_constant_
                   :: "l"(&cmaps.m[tc.level]), "r"(n0 + c0), "r"(tc.m0 + lg * 32), "r"(tc.b), "r"(buf) : "memory");
               asm volatile("cp.async.bulk.commit_group;" ::: "memory");
             }
-          } else if (p.logits != nullptr && vec_logits && p.logits_bf16) {
+          } else if (logits_ptr != nullptr && vec_logits && p.logits_bf16) {
             // 16-byte aligned rows (padded leading dimension), bf16: every thread writes its own
             // row's 32 classes (64 bytes) straight from registers with four 16-byte stores; measured
             // faster than turning the block through shared memory (3.15 vs 3.48 ms at batch 256).
             if (row_ok) {
               const int col0 = n0 + c0;
-              uint4* dst = reinterpret_cast<uint4*>(static_cast<__nv_bfloat16*>(p.logits) + grow * p.ldc + col0);
+              uint4* dst = reinterpret_cast<uint4*>(static_cast<__nv_bfloat16*>(logits_ptr) + grow * p.ldc + col0);
 #pragma unroll
               for (int v = 0; v < 4; ++v)
                 if (col0 + 8 * v < (int)p.ldc)
@@ -682,7 +694,7 @@ sim_fused_kernel(const __grid_constant__ LevelMaps amaps, const __grid_constant_
                                       pack_bf16x2(__uint_as_float(r[8 * v + 4]), __uint_as_float(r[8 * v + 5])),
                                       pack_bf16x2(__uint_as_float(r[8 * v + 6]), __uint_as_float(r[8 * v + 7])));
             }
-          } else if (p.logits != nullptr && vec_logits) {
+          } else if (logits_ptr != nullptr && vec_logits) {
             // fp32: the warp's 32 x 32 block is turned through shared memory (144-byte pitch: the
             // 128-bit writes by row and the 128-bit reads by quarter-row are both bank-conflict free)
             // so that one store instruction writes 4 rows x 128 contiguous bytes instead of 32 rows
@@ -697,7 +709,7 @@ sim_fused_kernel(const __grid_constant__ LevelMaps amaps, const __grid_constant_
             const int rows_here = min(32, tc.rows - lg * 32);
             const long long out_row0 = tc.out_row0 + lg * 32;
             {
-              float* out = static_cast<float*>(p.logits);
+              float* out = static_cast<float*>(logits_ptr);
               const int c4 = (lane & 7) * 4;                             // 8 lanes x 4 classes per row
 #pragma unroll
               for (int i = 0; i < 8; ++i) {
@@ -708,7 +720,7 @@ sim_fused_kernel(const __grid_constant__ LevelMaps amaps, const __grid_constant_
               }
             }
             __syncwarp();
-          } else if (p.logits != nullptr) {
+          } else if (logits_ptr != nullptr) {
 #pragma unroll
             for (int j = 0; j < 32; ++j) stage[lane * F_PITCH + j] = __uint_as_float(r[j]);
             __syncwarp();
@@ -720,11 +732,11 @@ sim_fused_kernel(const __grid_constant__ LevelMaps amaps, const __grid_constant_
             // lanes = 32 consecutive classes, 2- or 4-byte stores.  Slow (5.4 ms at batch 256, bf16):
             // callers that can pad the leading dimension to 16 bytes get the paths above.
             if (p.logits_bf16) {
-              __nv_bfloat16* out = static_cast<__nv_bfloat16*>(p.logits);
+              __nv_bfloat16* out = static_cast<__nv_bfloat16*>(logits_ptr);
               for (int i = 0; i < rows_here; ++i)
                 if (col_ok) out[(out_row0 + i) * p.ldc + col] = __float2bfloat16_rn(stage[i * F_PITCH + lane]);
             } else {
-              float* out = static_cast<float*>(p.logits);
+              float* out = static_cast<float*>(logits_ptr);
               for (int i = 0; i < rows_here; ++i)
                 if (col_ok) out[(out_row0 + i) * p.ldc + col] = stage[i * F_PITCH + lane];
             }
@@ -753,8 +765,13 @@ sim_fused_kernel(const __grid_constant__ LevelMaps amaps, const __grid_constant_
             } else {
 #pragma unroll
               for (int j = 0; j < 32; ++j) {
+                // running max as FMNMX (4-cycle chain); the compare that decides the index reads the
+                // previous value and is not on the chain (an FSETP -> FSEL pair per element was: the
+                // epilogue warps sat in fixed-latency waits for 39 % of their samples)
                 const float v = __uint_as_float(r[j]);
-                if (v > bv[j & 3]) { bv[j & 3] = v; bi[j & 3] = col + j; }
+                const float old = bv[j & 3];
+                bv[j & 3] = fmaxf(old, v);
+                if (v > old) bi[j & 3] = col + j;
               }
             }
           };
@@ -856,7 +873,7 @@ sim_fused_kernel(const __grid_constant__ LevelMaps amaps, const __grid_constant_
       }
     }
     // outstanding logit stores read this warp's staging buffers
-    if (p.logits_tma && lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+    if (logits_tma && lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
   }
 
   ptx::tc_fence_before();
@@ -1096,46 +1113,56 @@ int fused_launch(const float* const* obj_embeds, const int64_t* hw, const int64_
   static const int dbg_env = []() { const char* e = getenv("OVDET_DBG"); return e ? atoi(e) : 0; }();
   p.dbg = dbg_env;
 
+  // every (shape variant, epilogue mode) instantiation the dispatch below can pick
+  const int mode = vp ? 2 : (logits ? 1 : 0);
+  if (vp && cg != 2) return OVDET_ERR_UNSUPPORTED_SHAPE;      // key exchange: the dim = 512 CTA-pair kernel only
+#define OVDET_FOR_EACH_FUSED(X)                                                                        \
+  X(8, false, 2, false, false, 0) X(8, false, 2, false, false, 1) X(8, false, 2, false, false, 2)      \
+  X(8, false, 2, false, true, 0)  X(8, false, 2, false, true, 1)  X(8, false, 2, false, true, 2)       \
+  X(4, false, 2, true, false, 0)                                                                       \
+  X(8, false, 1, false, false, 0) X(8, false, 1, false, false, 1)                                      \
+  X(0, false, 1, false, false, 0) X(0, false, 1, false, false, 1)                                      \
+  X(0, true, 1, false, false, 0)  X(0, true, 1, false, false, 1)                                       \
+  X(0, false, 1, true, false, 0)                                                                       \
+  X(0, false, 1, false, true, 0)  X(0, false, 1, false, true, 1)
   if (first_use_on_device(1)) {
-    OVDET_CUDA_TRY(cudaFuncSetAttribute(sim_fused_kernel<8, false, 1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, FSmem<1>::bytes));
-    OVDET_CUDA_TRY(cudaFuncSetAttribute(sim_fused_kernel<0, false, 1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, FSmem<1>::bytes));
-    OVDET_CUDA_TRY(cudaFuncSetAttribute(sim_fused_kernel<0, true, 1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, FSmem<1>::bytes));
-    OVDET_CUDA_TRY(cudaFuncSetAttribute(sim_fused_kernel<8, false, 2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, FSmem<2>::bytes));
-    OVDET_CUDA_TRY(cudaFuncSetAttribute(sim_fused_kernel<0, false, 1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, FSmem<1>::bytes));
-    OVDET_CUDA_TRY(cudaFuncSetAttribute(sim_fused_kernel<4, false, 2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, FSmem<2>::bytes));
-    OVDET_CUDA_TRY(cudaFuncSetAttribute(sim_fused_kernel<8, false, 2, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, FSmem<2>::bytes));
-    OVDET_CUDA_TRY(cudaFuncSetAttribute(sim_fused_kernel<0, false, 1, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, FSmem<1>::bytes));
+#define OVDET_SET_SMEM(KB, S3, CGV, PR, I16, MD)                                                        \
+    OVDET_CUDA_TRY(cudaFuncSetAttribute(sim_fused_kernel<KB, S3, CGV, PR, I16, MD>,                     \
+                                        cudaFuncAttributeMaxDynamicSharedMemorySize, FSmem<CGV>::bytes));
+    OVDET_FOR_EACH_FUSED(OVDET_SET_SMEM)
+#undef OVDET_SET_SMEM
   }
+  // shape variant of this launch
+  const int v_kb = cg == 2 ? (proj ? 4 : 8) : ((!in_bf16 && !proj && !split3 && p.kb == 8) ? 8 : 0);
+  cudaLaunchConfig_t cfg{};
+  cudaLaunchAttribute attr[1];
+  cfg.blockDim = dim3(F_THREADS);
+  cfg.stream = as_stream(stream);
   if (cg == 2) {
     // one CTA per SM, launched as clusters of two (the pair shares a TPC)
     const long long pairs = (tiles + 1) / 2 * p.nsplit;                // work items
     const int max_pairs = sm_count() / 2;
-    cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3((unsigned)(2 * (pairs < max_pairs ? pairs : max_pairs)));
-    cfg.blockDim = dim3(F_THREADS);
     cfg.dynamicSmemBytes = FSmem<2>::bytes;
-    cfg.stream = as_stream(stream);
-    cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeClusterDimension;
     attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    if (proj) OVDET_CUDA_TRY(cudaLaunchKernelEx(&cfg, sim_fused_kernel<4, false, 2, true>, maps, bmaps, cmaps, p));
-    else if (in_bf16) OVDET_CUDA_TRY(cudaLaunchKernelEx(&cfg, sim_fused_kernel<8, false, 2, false, true>, maps, bmaps, cmaps, p));
-    else OVDET_CUDA_TRY(cudaLaunchKernelEx(&cfg, sim_fused_kernel<8, false, 2, false>, maps, bmaps, cmaps, p));
-    return OVDET_OK;
+  } else {
+    cfg.gridDim = dim3((unsigned)(tiles < sm_count() ? tiles : sm_count()));
+    cfg.dynamicSmemBytes = FSmem<1>::bytes;
   }
-  const int grid = (int)(tiles < sm_count() ? tiles : sm_count());
-  if (in_bf16)
-    sim_fused_kernel<0, false, 1, false, true><<<grid, F_THREADS, FSmem<1>::bytes, as_stream(stream)>>>(maps, bmaps, cmaps, p);
-  else if (proj)
-    sim_fused_kernel<0, false, 1, true><<<grid, F_THREADS, FSmem<1>::bytes, as_stream(stream)>>>(maps, bmaps, cmaps, p);
-  else if (split3)
-    sim_fused_kernel<0, true, 1, false><<<grid, F_THREADS, FSmem<1>::bytes, as_stream(stream)>>>(maps, bmaps, cmaps, p);
-  else if (p.kb == 8)
-    sim_fused_kernel<8, false, 1, false><<<grid, F_THREADS, FSmem<1>::bytes, as_stream(stream)>>>(maps, bmaps, cmaps, p);
-  else
-    sim_fused_kernel<0, false, 1, false><<<grid, F_THREADS, FSmem<1>::bytes, as_stream(stream)>>>(maps, bmaps, cmaps, p);
+  bool launched = false;
+#define OVDET_TRY_LAUNCH(KB, S3, CGV, PR, I16, MD)                                                      \
+  if (!launched && v_kb == KB && (split3 != 0) == S3 && cg == CGV && (proj != 0) == PR &&               \
+      (in_bf16 != 0) == I16 && mode == MD) {                                                            \
+    OVDET_CUDA_TRY(cudaLaunchKernelEx(&cfg, sim_fused_kernel<KB, S3, CGV, PR, I16, MD>, maps, bmaps, cmaps, p)); \
+    launched = true;                                                                                    \
+  }
+  OVDET_FOR_EACH_FUSED(OVDET_TRY_LAUNCH)
+#undef OVDET_TRY_LAUNCH
+#undef OVDET_FOR_EACH_FUSED
+  if (!launched) return OVDET_ERR_UNSUPPORTED_SHAPE;
   OVDET_LAUNCH_CHECK();
   return OVDET_OK;
 }
