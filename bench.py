@@ -57,7 +57,7 @@ def workload_name(batch):
 class ClockSampler:
     QUERY = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
-             "clocks_event_reasons.sw_power_cap")
+             "clocks_event_reasons.sw_power_cap,enforced.power.limit,clocks_event_reasons.active")
 
     def __init__(self, index: int):
         self.index = index
@@ -90,6 +90,7 @@ class ClockSampler:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         self.proc.terminate()
         sm, smax, reasons = [], None, set()
+        power, limit, masks = [], None, set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         for t, row in self.rows:
             if (t0 is not None and t < t0) or (t1 is not None and t > t1):
@@ -105,8 +106,20 @@ class ClockSampler:
             for name, val in zip(names, parts[3:7]):
                 if val.lower().startswith("active"):
                     reasons.add(name)
+            try:
+                power.append(float(parts[2]))
+                if len(parts) > 7:
+                    limit = float(parts[7])
+            except ValueError:
+                pass
+            if len(parts) > 8:
+                masks.add(parts[8])
+        # the per-reason flags are sampled states and can read "Not Active" between two cap events; the
+        # board power beside its enforced limit and the raw reasons bitmask are reported as well
         return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": smax,
-                "samples": len(sm), "window": window, "reasons": sorted(reasons)}
+                "samples": len(sm), "window": window, "reasons": sorted(reasons),
+                "power_w": statistics.median(power) if power else None, "power_limit_w": limit,
+                "reasons_bitmask": sorted(masks)}
 
 
 def measured_peaks():
@@ -123,7 +136,7 @@ def ncu_traffic(kernel_substr: str, batch: int):
     """DRAM bytes per launch (dram__bytes_read.sum + dram__bytes_write.sum) of the dominant kernel
     from the committed `ncu --set full` capture of this same workload (profiles/, batch 256);
     None when the run's shape differs from the captured one."""
-    path = os.path.join(ROOT, "profiles", "r1_ncu_full_pipeline_b256_v6.json")
+    path = os.path.join(ROOT, "profiles", "r1_ncu_full_pipeline_b256_v7.json")
     if batch != 256 or (IMAGE_SIZE, NUM_CLASSES) != (640, 1203) or not os.path.exists(path):
         return None
     scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
@@ -441,7 +454,7 @@ def run_ours(args):
         # north_star quotes nominal figures too: 2.25 PFLOP/s dense bf16, ~8 TB/s HBM3e
         roofline["frac_of_nominal"] = roofline["achieved"] / (2250.0 if roofline["bound"] == "tensor" else 8000.0)
         roofline.update({"traffic": None if proj else ncu_traffic("sim_fused" if fused else "sim_gemm", batch),
-                         "traffic_source": "profiles/r1_ncu_full_pipeline_b256_v6.json (ncu --set full, bytes per launch)",
+                         "traffic_source": "profiles/r1_ncu_full_pipeline_b256_v7.json (ncu --set full, bytes per launch)",
                          "algorithmic_bytes": alg_bytes, "algorithmic_flops": flops,
                          "ms_per_launch": stages["similarity"]})
         k1_bytes = batch * anchors * (EMBED_DIM * 4 + EMBED_DIM * 2 + 4)
