@@ -192,8 +192,12 @@ __device__ __forceinline__ TileCoord decode_tile(const FusedParams& p, int tile)
 // other modes' code or live registers - with them folded in at run time the projected mode lost 6 %
 // and the main mode 1.5 %): 0 = row max / argmax only, 1 = logits (and optionally max / argmax),
 // 2 = vocabulary-parallel keys.
-template <int KB_T, bool SPLIT3, int CG, bool PROJ, bool IN16 = false, int MODE = 0>
-__global__ void __launch_bounds__(F_THREADS, 1)
+// EPI2 (MODE 0 only, whose kernels fit 128 registers): a SECOND epilogue warpgroup (warps 12-15,
+// 512 threads).  Group e drains the N tiles whose accumulator stage is e, so the two stages are
+// emptied concurrently; the groups' partial (max, argmax, q) of a row meet in shared memory at the
+// end of the anchor tile and group 0 emits.
+template <int KB_T, bool SPLIT3, int CG, bool PROJ, bool IN16 = false, int MODE = 0, bool EPI2 = false>
+__global__ void __launch_bounds__(EPI2 ? F_THREADS + 128 : F_THREADS, 1)
 sim_fused_kernel(const __grid_constant__ LevelMaps amaps, const __grid_constant__ LevelMaps bmaps,
                  const __grid_constant__ LevelMaps cmaps, const FusedParams p) {
   using FSmem = ovdet::FSmem<CG>;
@@ -203,6 +207,7 @@ sim_fused_kernel(const __grid_constant__ LevelMaps amaps, const __grid_constant_
   constexpr int F_B_SUB_BYTES = FSmem::b_sub_bytes;
   static_assert(CG == 1 || KB_T > 0, "CTA pairs need a compile-time k-block count");
   static_assert(!(PROJ && SPLIT3), "the projected mode is a single bf16 pass");
+  static_assert(!EPI2 || MODE == 0, "two epilogue groups: scores-only kernels");
   // cluster rank: 0 = leader (issues the MMAs, owns the barriers the pair synchronises on)
   const uint32_t rank = CG == 2 ? ptx::cluster_ctarank() : 0u;
   const int pair0 = blockIdx.x / CG, pair_stride = gridDim.x / CG;
@@ -239,7 +244,7 @@ sim_fused_kernel(const __grid_constant__ LevelMaps amaps, const __grid_constant_
     // a_ready / t_empty collect the converter / epilogue warps of BOTH CTAs on the leader
     for (int k = 0; k < F_MAX_KB; ++k) { ptx::mbar_init(a_ready0 + 8u * k, 4 * CG);
       // projected: the epilogue warps read x' back from the A region, so they release it too
-      ptx::mbar_init(a_free0 + 8u * k, PROJ ? 5 : 1); }
+      ptx::mbar_init(a_free0 + 8u * k, PROJ ? (EPI2 ? 9 : 5) : 1); }
     for (int s = 0; s < 2; ++s) { ptx::mbar_init(t_full0 + 8u * s, 1); ptx::mbar_init(t_empty0 + 8u * s, 4 * CG); }
     for (int s = 0; s < 3; ++s) ptx::mbar_init(n_ready0 + 8u * s, 4);
     ptx::fence_mbar_init();
@@ -520,6 +525,7 @@ sim_fused_kernel(const __grid_constant__ LevelMaps amaps, const __grid_constant_
   } else if (warp >= 8) {
     // ================================ epilogue ===============================================
     const int lg = warp & 3;
+    const int eg = EPI2 ? (warp - 8) >> 2 : 0;                 // epilogue group = accumulator stage it drains
     float* stage = epi_stage + lg * (FSmem::epi_warp_bytes / 4);
     const uint32_t stage_u32 = ptx::smem_u32(stage);          // 4608 bytes per warp, 512-byte aligned
     uint32_t tma_chunk = 0;
@@ -566,7 +572,12 @@ sim_fused_kernel(const __grid_constant__ LevelMaps amaps, const __grid_constant_
       const bool raw_mode = PROJ || (want_max && logits_ptr == nullptr && p.alpha >= 0.f && !(p.dbg & 2));
       const bool max_only = raw_mode && p.row_arg == nullptr && !vp;
       float raw_best = -INFINITY;
+      // projected + EPI2: every epilogue warp releases the A region once per anchor tile - after the
+      // last G' tile it drains, or (none of them its own) once its first tile of this anchor tile
+      // has arrived, which proves that the MMA warp has moved on to this anchor tile
+      bool a_released = false;
       for (int nt = nt_b; nt < nt_e; ++nt, ++acc_it) {
+        if (EPI2 && (int)(acc_it & 1u) != eg) continue;
         const int n0 = (nt - NG) * F_BLOCK_N;          // first class of a class tile
         const int n_valid = ntile_valid(nt);
         const int nchunks = (n_valid + 31) >> 5;
@@ -598,10 +609,17 @@ sim_fused_kernel(const __grid_constant__ LevelMaps amaps, const __grid_constant_
           if (lane == 0) {
             if constexpr (CG == 2) ptx::mbar_arrive_cluster(lead_t_empty0 + 8u * as);
             else ptx::mbar_arrive(t_empty0 + 8u * as);
-            if (nt == NG - 1)                                          // done reading x': the A region may be rewritten
+            if (EPI2 ? (nt + 2 >= NG) : (nt == NG - 1)) {              // done reading x': the A region may be rewritten
               for (int kb = 0; kb < KB_IN; ++kb) ptx::mbar_arrive(a_free0 + 8u * kb);
+            }
           }
+          if (EPI2 && nt + 2 >= NG) a_released = true;
           continue;
+        }
+        if (PROJ && EPI2 && !a_released) {                              // this group drained no G' tile
+          a_released = true;
+          if (lane == 0)
+            for (int kb = 0; kb < KB_IN; ++kb) ptx::mbar_arrive(a_free0 + 8u * kb);
         }
 
         auto consume = [&](uint32_t (&r)[32], int c) {
@@ -812,6 +830,35 @@ sim_fused_kernel(const __grid_constant__ LevelMaps amaps, const __grid_constant_
           if constexpr (CG == 2) ptx::mbar_arrive_cluster(lead_t_empty0 + 8u * as);
           else ptx::mbar_arrive(t_empty0 + 8u * as);
         }
+      }
+      if constexpr (EPI2) {
+        // the two groups' partial results of this row meet in shared memory (one buffer per anchor-
+        // tile parity, one named barrier per anchor tile: group 1's write for tile lt + 2 follows the
+        // barrier of lt + 1, which group 0 reaches only after its read for lt); group 0 emits
+        float best = bv[0];
+        int best_idx = bi[0];
+#pragma unroll
+        for (int qd = 1; qd < 4; ++qd)
+          if (bv[qd] > best || (bv[qd] == best && bi[qd] < best_idx)) { best = bv[qd]; best_idx = bi[qd]; }
+        float* xbuf = epi_stage + (lt & 1u) * (3 * F_BLOCK_M);
+        if (eg == 1) {
+          xbuf[r_in_tile] = max_only ? raw_best : best;
+          reinterpret_cast<int*>(xbuf)[F_BLOCK_M + r_in_tile] = best_idx;
+          xbuf[2 * F_BLOCK_M + r_in_tile] = q;
+        }
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+        if (eg == 1) continue;
+        const float ob = xbuf[r_in_tile];
+        const int oi = reinterpret_cast<const int*>(xbuf)[F_BLOCK_M + r_in_tile];
+        q += xbuf[2 * F_BLOCK_M + r_in_tile];
+        if (max_only) {
+          raw_best = fmaxf(raw_best, ob);
+        } else if (ob > best || (ob == best && oi < best_idx)) {
+          best = ob;
+          best_idx = oi;
+        }
+        bv[0] = best; bi[0] = best_idx;
+        bv[1] = bv[2] = bv[3] = -INFINITY;
       }
       if (!PROJ && NSPLIT > 1) {
         // partial result of this class range -> scratch; the last part to arrive merges
@@ -1117,21 +1164,26 @@ int fused_launch(const float* const* obj_embeds, const int64_t* hw, const int64_
   const int mode = vp ? 2 : (logits ? 1 : 0);
   if (vp && cg != 2) return OVDET_ERR_UNSUPPORTED_SHAPE;      // key exchange: the dim = 512 CTA-pair kernel only
 #define OVDET_FOR_EACH_FUSED(X)                                                                        \
-  X(8, false, 2, false, false, 0) X(8, false, 2, false, false, 1) X(8, false, 2, false, false, 2)      \
-  X(8, false, 2, false, true, 0)  X(8, false, 2, false, true, 1)  X(8, false, 2, false, true, 2)       \
-  X(4, false, 2, true, false, 0)                                                                       \
-  X(8, false, 1, false, false, 0) X(8, false, 1, false, false, 1)                                      \
-  X(0, false, 1, false, false, 0) X(0, false, 1, false, false, 1)                                      \
-  X(0, true, 1, false, false, 0)  X(0, true, 1, false, false, 1)                                       \
-  X(0, false, 1, true, false, 0)                                                                       \
-  X(0, false, 1, false, true, 0)  X(0, false, 1, false, true, 1)
+  X(8, false, 2, false, false, 0, false) X(8, false, 2, false, false, 1, false) X(8, false, 2, false, false, 2, false) \
+  X(8, false, 2, false, true, 0, false)  X(8, false, 2, false, true, 1, false)  X(8, false, 2, false, true, 2, false)  \
+  X(4, false, 2, true, false, 0, false)                                                                \
+  X(8, false, 2, false, false, 0, true)  X(8, false, 2, false, true, 0, true)  X(4, false, 2, true, false, 0, true)     \
+  X(8, false, 1, false, false, 0, false) X(8, false, 1, false, false, 1, false)                        \
+  X(0, false, 1, false, false, 0, false) X(0, false, 1, false, false, 1, false)                        \
+  X(0, true, 1, false, false, 0, false)  X(0, true, 1, false, false, 1, false)                         \
+  X(0, false, 1, true, false, 0, false)                                                                \
+  X(0, false, 1, false, true, 0, false)  X(0, false, 1, false, true, 1, false)
   if (first_use_on_device(1)) {
-#define OVDET_SET_SMEM(KB, S3, CGV, PR, I16, MD)                                                        \
-    OVDET_CUDA_TRY(cudaFuncSetAttribute(sim_fused_kernel<KB, S3, CGV, PR, I16, MD>,                     \
+#define OVDET_SET_SMEM(KB, S3, CGV, PR, I16, MD, E2)                                                    \
+    OVDET_CUDA_TRY(cudaFuncSetAttribute(sim_fused_kernel<KB, S3, CGV, PR, I16, MD, E2>,                 \
                                         cudaFuncAttributeMaxDynamicSharedMemorySize, FSmem<CGV>::bytes));
     OVDET_FOR_EACH_FUSED(OVDET_SET_SMEM)
 #undef OVDET_SET_SMEM
   }
+  // second epilogue warpgroup (CTA-pair scores-only kernels): OVDET_EPI2 bit 0 = projected mode (the
+  // epilogue is on its critical path: K = 272 per tile), bit 1 = cosine mode
+  static const int epi2_env = []() { const char* e = getenv("OVDET_EPI2"); return e ? atoi(e) : 1; }();
+  const bool epi2 = cg == 2 && mode == 0 && ((proj && (epi2_env & 1)) || (!proj && (epi2_env & 2)));
   // shape variant of this launch
   const int v_kb = cg == 2 ? (proj ? 4 : 8) : ((!in_bf16 && !proj && !split3 && p.kb == 8) ? 8 : 0);
   cudaLaunchConfig_t cfg{};
@@ -1153,10 +1205,11 @@ int fused_launch(const float* const* obj_embeds, const int64_t* hw, const int64_
     cfg.dynamicSmemBytes = FSmem<1>::bytes;
   }
   bool launched = false;
-#define OVDET_TRY_LAUNCH(KB, S3, CGV, PR, I16, MD)                                                      \
+#define OVDET_TRY_LAUNCH(KB, S3, CGV, PR, I16, MD, E2)                                                  \
   if (!launched && v_kb == KB && (split3 != 0) == S3 && cg == CGV && (proj != 0) == PR &&               \
-      (in_bf16 != 0) == I16 && mode == MD) {                                                            \
-    OVDET_CUDA_TRY(cudaLaunchKernelEx(&cfg, sim_fused_kernel<KB, S3, CGV, PR, I16, MD>, maps, bmaps, cmaps, p)); \
+      (in_bf16 != 0) == I16 && mode == MD && epi2 == E2) {                                              \
+    cfg.blockDim = dim3(E2 ? F_THREADS + 128 : F_THREADS);                                              \
+    OVDET_CUDA_TRY(cudaLaunchKernelEx(&cfg, sim_fused_kernel<KB, S3, CGV, PR, I16, MD, E2>, maps, bmaps, cmaps, p)); \
     launched = true;                                                                                    \
   }
   OVDET_FOR_EACH_FUSED(OVDET_TRY_LAUNCH)
