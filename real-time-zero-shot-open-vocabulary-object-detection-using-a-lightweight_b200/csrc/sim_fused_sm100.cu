@@ -88,7 +88,9 @@ struct FSmem {
   static constexpr int epi_bytes = 4 * epi_warp_bytes;
   static constexpr int norm_off = epi_off + epi_bytes;
   static constexpr int norm_bytes = 3 * F_BLOCK_M * 4;
-  static constexpr int bar_off = norm_off + norm_bytes;
+  static constexpr int xbuf_off = norm_off + norm_bytes;              // EPI2: group 1's partial rows, two parities
+  static constexpr int xbuf_bytes = 2 * 3 * F_BLOCK_M * 4;
+  static constexpr int bar_off = xbuf_off + xbuf_bytes;
   // b_full, b_empty, as_full, as_empty, a_ready, a_free, tmem_full, tmem_empty, norm_ready
   static constexpr int num_bars = 2 * b_stages + 2 * F_A_STAGES + 2 * F_MAX_KB + 2 + 2 + 3;
   static constexpr int tmem_ptr_off = bar_off + num_bars * 8;
@@ -192,8 +194,8 @@ __device__ __forceinline__ TileCoord decode_tile(const FusedParams& p, int tile)
 // other modes' code or live registers - with them folded in at run time the projected mode lost 6 %
 // and the main mode 1.5 %): 0 = row max / argmax only, 1 = logits (and optionally max / argmax),
 // 2 = vocabulary-parallel keys.
-// EPI2 (MODE 0 only, whose kernels fit 128 registers): a SECOND epilogue warpgroup (warps 12-15,
-// 512 threads).  Group e drains the N tiles whose accumulator stage is e, so the two stages are
+// EPI2 (kernels that fit 128 registers; with logits only the TMA-store path, one 2 KiB staging
+// buffer per warp): a SECOND epilogue warpgroup (warps 12-15, 512 threads).  Group e drains the N tiles whose accumulator stage is e, so the two stages are
 // emptied concurrently; the groups' partial (max, argmax, q) of a row meet in shared memory at the
 // end of the anchor tile and group 0 emits.
 template <int KB_T, bool SPLIT3, int CG, bool PROJ, bool IN16 = false, int MODE = 0, bool EPI2 = false>
@@ -207,7 +209,7 @@ sim_fused_kernel(const __grid_constant__ LevelMaps amaps, const __grid_constant_
   constexpr int F_B_SUB_BYTES = FSmem::b_sub_bytes;
   static_assert(CG == 1 || KB_T > 0, "CTA pairs need a compile-time k-block count");
   static_assert(!(PROJ && SPLIT3), "the projected mode is a single bf16 pass");
-  static_assert(!EPI2 || MODE == 0, "two epilogue groups: scores-only kernels");
+  static_assert(!EPI2 || MODE != 2, "two epilogue groups: not for the key exchange");
   // cluster rank: 0 = leader (issues the MMAs, owns the barriers the pair synchronises on)
   const uint32_t rank = CG == 2 ? ptx::cluster_ctarank() : 0u;
   const int pair0 = blockIdx.x / CG, pair_stride = gridDim.x / CG;
@@ -526,12 +528,14 @@ sim_fused_kernel(const __grid_constant__ LevelMaps amaps, const __grid_constant_
     // ================================ epilogue ===============================================
     const int lg = warp & 3;
     const int eg = EPI2 ? (warp - 8) >> 2 : 0;                 // epilogue group = accumulator stage it drains
-    float* stage = epi_stage + lg * (FSmem::epi_warp_bytes / 4);
-    const uint32_t stage_u32 = ptx::smem_u32(stage);          // 4608 bytes per warp, 512-byte aligned
+    // staging: 4608 bytes per warp; with two groups 2048 bytes each (one TMA-store buffer).  Both are
+    // multiples of 512: the 64-byte swizzle is a function of the absolute shared-memory address
+    float* stage = epi_stage + (EPI2 ? (warp - 8) * 512 : lg * (FSmem::epi_warp_bytes / 4));
+    const uint32_t stage_u32 = ptx::smem_u32(stage);
     uint32_t tma_chunk = 0;
     constexpr bool vp = MODE == 2;
     void* const logits_ptr = MODE == 1 ? p.logits : nullptr;
-    const bool logits_tma = MODE == 1 && p.logits_tma;
+    const bool logits_tma = MODE == 1 && (EPI2 || p.logits_tma);      // EPI2 + logits: the host guarantees the TMA path
     const bool want_max = p.row_max != nullptr || vp;
     // a finished row: local (score, class) or, vocabulary-parallel, one max-reduction per rank
     const long long vp_off = vp ? (long long)(__ldcg(p.vp_step) & 1ull) * p.vp_rows : 0;
@@ -675,9 +679,12 @@ sim_fused_kernel(const __grid_constant__ LevelMaps amaps, const __grid_constant_
             // c - 1 may still be reading its buffer while chunk c is packed (a third buffer measured no
             // faster: the epilogue's arithmetic, not the store queue, sets the pace).  The per-thread
             // 16-byte global stores this replaces (32 rows per instruction) were LSU-bound.
-            const uint32_t buf = stage_u32 + (tma_chunk & 1u) * 2048u;
+            const uint32_t buf = EPI2 ? stage_u32 : stage_u32 + (tma_chunk & 1u) * 2048u;
             ++tma_chunk;
-            if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+            if (lane == 0) {
+              if constexpr (EPI2) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+              else asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+            }
             __syncwarp();
             const uint32_t rowaddr = buf + lane * 64u;
             const uint32_t sw = (lane >> 1) & 3u;
@@ -697,7 +704,7 @@ sim_fused_kernel(const __grid_constant__ LevelMaps amaps, const __grid_constant_
                   :: "l"(&cmaps.m[tc.level]), "r"(n0 + c0), "r"(tc.m0 + lg * 32), "r"(tc.b), "r"(buf) : "memory");
               asm volatile("cp.async.bulk.commit_group;" ::: "memory");
             }
-          } else if (logits_ptr != nullptr && vec_logits && p.logits_bf16) {
+          } else if (!EPI2 && logits_ptr != nullptr && vec_logits && p.logits_bf16) {
             // 16-byte aligned rows (padded leading dimension), bf16: every thread writes its own
             // row's 32 classes (64 bytes) straight from registers with four 16-byte stores; measured
             // faster than turning the block through shared memory (3.15 vs 3.48 ms at batch 256).
@@ -712,7 +719,7 @@ sim_fused_kernel(const __grid_constant__ LevelMaps amaps, const __grid_constant_
                                       pack_bf16x2(__uint_as_float(r[8 * v + 4]), __uint_as_float(r[8 * v + 5])),
                                       pack_bf16x2(__uint_as_float(r[8 * v + 6]), __uint_as_float(r[8 * v + 7])));
             }
-          } else if (logits_ptr != nullptr && vec_logits) {
+          } else if (!EPI2 && logits_ptr != nullptr && vec_logits) {
             // fp32: the warp's 32 x 32 block is turned through shared memory (144-byte pitch: the
             // 128-bit writes by row and the 128-bit reads by quarter-row are both bank-conflict free)
             // so that one store instruction writes 4 rows x 128 contiguous bytes instead of 32 rows
@@ -738,7 +745,7 @@ sim_fused_kernel(const __grid_constant__ LevelMaps amaps, const __grid_constant_
               }
             }
             __syncwarp();
-          } else if (logits_ptr != nullptr) {
+          } else if (!EPI2 && logits_ptr != nullptr) {
 #pragma unroll
             for (int j = 0; j < 32; ++j) stage[lane * F_PITCH + j] = __uint_as_float(r[j]);
             __syncwarp();
@@ -840,7 +847,7 @@ sim_fused_kernel(const __grid_constant__ LevelMaps amaps, const __grid_constant_
 #pragma unroll
         for (int qd = 1; qd < 4; ++qd)
           if (bv[qd] > best || (bv[qd] == best && bi[qd] < best_idx)) { best = bv[qd]; best_idx = bi[qd]; }
-        float* xbuf = epi_stage + (lt & 1u) * (3 * F_BLOCK_M);
+        float* xbuf = reinterpret_cast<float*>(base_ptr + FSmem::xbuf_off) + (lt & 1u) * (3 * F_BLOCK_M);
         if (eg == 1) {
           xbuf[r_in_tile] = max_only ? raw_best : best;
           reinterpret_cast<int*>(xbuf)[F_BLOCK_M + r_in_tile] = best_idx;
@@ -1168,6 +1175,7 @@ int fused_launch(const float* const* obj_embeds, const int64_t* hw, const int64_
   X(8, false, 2, false, true, 0, false)  X(8, false, 2, false, true, 1, false)  X(8, false, 2, false, true, 2, false)  \
   X(4, false, 2, true, false, 0, false)                                                                \
   X(8, false, 2, false, false, 0, true)  X(8, false, 2, false, true, 0, true)  X(4, false, 2, true, false, 0, true)     \
+  X(8, false, 2, false, false, 1, true)  X(8, false, 2, false, true, 1, true)                           \
   X(8, false, 1, false, false, 0, false) X(8, false, 1, false, false, 1, false)                        \
   X(0, false, 1, false, false, 0, false) X(0, false, 1, false, false, 1, false)                        \
   X(0, true, 1, false, false, 0, false)  X(0, true, 1, false, false, 1, false)                         \
@@ -1181,9 +1189,10 @@ int fused_launch(const float* const* obj_embeds, const int64_t* hw, const int64_
 #undef OVDET_SET_SMEM
   }
   // second epilogue warpgroup (CTA-pair scores-only kernels): OVDET_EPI2 bit 0 = projected mode (the
-  // epilogue is on its critical path: K = 272 per tile), bit 1 = cosine mode
-  static const int epi2_env = []() { const char* e = getenv("OVDET_EPI2"); return e ? atoi(e) : 1; }();
-  const bool epi2 = cg == 2 && mode == 0 && ((proj && (epi2_env & 1)) || (!proj && (epi2_env & 2)));
+  // epilogue is on its critical path: K = 272 per tile), bit 1 = cosine mode, bit 2 = bf16 logits (TMA stores)
+  static const int epi2_env = []() { const char* e = getenv("OVDET_EPI2"); return e ? atoi(e) : 5; }();
+  const bool epi2 = cg == 2 && ((mode == 0 && ((proj && (epi2_env & 1)) || (!proj && (epi2_env & 2)))) ||
+                                (mode == 1 && logits_tma && (epi2_env & 4)));
   // shape variant of this launch
   const int v_kb = cg == 2 ? (proj ? 4 : 8) : ((!in_bf16 && !proj && !split3 && p.kb == 8) ? 8 : 0);
   cudaLaunchConfig_t cfg{};
