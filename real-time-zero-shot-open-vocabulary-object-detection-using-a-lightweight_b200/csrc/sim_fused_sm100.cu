@@ -75,11 +75,15 @@ constexpr int F_MAX_LEVELS = 4;
 // loads issued at an anchor-tile boundary do not queue behind it.  With CG = 2 a stage holds TWO
 // k blocks (two 8 KiB boxes on one barrier), so the single MMA-issuing thread - which now has
 // half the time per k block - synchronises once per 8 MMAs instead of once per 4.
-template <int CG>
+// KPS3 (the projected CTA-pair kernel, K = 4 x 64 + 16): THREE k blocks per stage, three stages of
+// 24 KiB.  With two blocks per stage the 16-wide constant block was a stage of its own - one MMA
+// (64 tensor cycles) behind a full barrier round trip of the issuing thread: dropping that stage in a
+// timing experiment took 13 % off the kernel for 6 % of its MMA work.  Stages are now {0,1,2} {3,const}.
+template <int CG, bool KPS3 = false>
 struct FSmem {
-  static constexpr int kps = CG;                                     // k blocks per text stage
+  static constexpr int kps = KPS3 ? 3 : CG;                          // k blocks per text stage
   static constexpr int b_sub_bytes = (F_BLOCK_N / CG) * F_BLOCK_K * 2;  // one TMA box: [N / CG rows x 64 k]
-  static constexpr int b_stages = OVDET_F_B_STAGES;
+  static constexpr int b_stages = KPS3 ? 3 : OVDET_F_B_STAGES;
   static constexpr int b_stage_bytes = kps * b_sub_bytes;            // 16 KiB
   static constexpr int b_off = 0;
   static constexpr int a_off = b_off + b_stages * b_stage_bytes;                     // 64 KiB
@@ -97,7 +101,8 @@ struct FSmem {
   static constexpr int total = tmem_ptr_off + 16;
   static constexpr int bytes = total + 1024;
 };
-static_assert(FSmem<1>::bytes <= 227 * 1024 && FSmem<2>::bytes <= 227 * 1024, "shared memory budget");
+static_assert(FSmem<1>::bytes <= 227 * 1024 && FSmem<2>::bytes <= 227 * 1024 && FSmem<2, true>::bytes <= 227 * 1024,
+              "shared memory budget");
 
 struct LevelMaps { CUtensorMap m[F_MAX_LEVELS]; };   // activations; (projected) one text operand per level
 
@@ -202,7 +207,7 @@ template <int KB_T, bool SPLIT3, int CG, bool PROJ, bool IN16 = false, int MODE 
 __global__ void __launch_bounds__(EPI2 ? F_THREADS + 128 : F_THREADS, 1)
 sim_fused_kernel(const __grid_constant__ LevelMaps amaps, const __grid_constant__ LevelMaps bmaps,
                  const __grid_constant__ LevelMaps cmaps, const FusedParams p) {
-  using FSmem = ovdet::FSmem<CG>;
+  using FSmem = ovdet::FSmem<CG, (PROJ && CG == 2)>;
   constexpr int F_B_STAGES = FSmem::b_stages;
   constexpr int F_B_STAGE_BYTES = FSmem::b_stage_bytes;
   constexpr int KPS = FSmem::kps;
@@ -1184,7 +1189,7 @@ int fused_launch(const float* const* obj_embeds, const int64_t* hw, const int64_
   if (first_use_on_device(1)) {
 #define OVDET_SET_SMEM(KB, S3, CGV, PR, I16, MD, E2)                                                    \
     OVDET_CUDA_TRY(cudaFuncSetAttribute(sim_fused_kernel<KB, S3, CGV, PR, I16, MD, E2>,                 \
-                                        cudaFuncAttributeMaxDynamicSharedMemorySize, FSmem<CGV>::bytes));
+                                        cudaFuncAttributeMaxDynamicSharedMemorySize, FSmem<CGV, (PR && CGV == 2)>::bytes));
     OVDET_FOR_EACH_FUSED(OVDET_SET_SMEM)
 #undef OVDET_SET_SMEM
   }
@@ -1218,6 +1223,7 @@ int fused_launch(const float* const* obj_embeds, const int64_t* hw, const int64_
   if (!launched && v_kb == KB && (split3 != 0) == S3 && cg == CGV && (proj != 0) == PR &&               \
       (in_bf16 != 0) == I16 && mode == MD && epi2 == E2) {                                              \
     cfg.blockDim = dim3(E2 ? F_THREADS + 128 : F_THREADS);                                              \
+    cfg.dynamicSmemBytes = FSmem<CGV, (PR && CGV == 2)>::bytes;                                         \
     OVDET_CUDA_TRY(cudaLaunchKernelEx(&cfg, sim_fused_kernel<KB, S3, CGV, PR, I16, MD, E2>, maps, bmaps, cmaps, p)); \
     launched = true;                                                                                    \
   }
