@@ -211,6 +211,16 @@ OVDET_API int ovdet_similarity_projected(const float* const* hidden, const int64
 OVDET_API int ovdet_rowmax(const void* logits, int logits_dtype, int64_t rows, int64_t classes, int64_t ldc,
                  float* row_max, int32_t* row_arg, void* stream);
 
+/* E1  `obj_embeddings` of the forward dict: fp32 NCHW conv output of one level -> rows
+ * [row_offset, row_offset + hw) of the anchor-major [batch, rows_per_batch, dim] array (levels
+ * concatenated P3 | P4 | P5 by one call per level).
+ * Replaces: model/yolo_clip.py:208-214 (permute(0,2,3,1).reshape(B,HW,D) per level + torch.cat).
+ *   x   fp32 [batch, dim, hw], element (b,d,a) at x[b*stride_b + d*stride_d + a]
+ *   out fp32 [batch, rows_per_batch, dim] contiguous */
+OVDET_API int ovdet_concat_embeddings(const float* x, int64_t batch, int64_t dim, int64_t hw,
+                                      int64_t stride_b, int64_t stride_d, float* out,
+                                      int64_t rows_per_batch, int64_t row_offset, void* stream);
+
 /* ------------------------------------------------------------------------------------------
  * K3  DFL box decode for all levels + score activation + confidence threshold.
  * Replaces: model/heads/box_head.py:150-218 (decode_boxes; grid of :115-148 is implicit),
@@ -429,8 +439,12 @@ OVDET_API int ovdet_similarity_fused_vp(const void* const* obj_embeds, const int
  * buffer) and advance this rank's counters. */
 OVDET_API int ovdet_vp_signal(void* const* peer_buffers, int world, int rank, int64_t rows, void* stream);
 /* wait until flags[g] >= step for every g, then keys[step & 1] -> scores fp32 / class_ids int32
- * (global class indices) and hand the rows back.  The wait is bounded (timeout_ms, 0 = 2000): on
- * expiry *status (device int32, optional) is set to 1 and the kernel continues with what it has. */
+ * (global class indices) and hand the rows back.  The wait is bounded (timeout_ms, 0 = 2000).  On
+ * expiry NOTHING is unpacked or handed back: scores are set to -inf / class_ids to 0 (K3 / K4 then
+ * yield no detections), a sticky word in the rank's own buffer makes every later call do the same
+ * (a late peer's atomics may still be landing in the key arrays) until ovdet_vp_buffer_init re-arms
+ * the buffer, and *status (int32, optional; device memory or mapped pinned host memory, which the
+ * host can poll without synchronising) is set to 1.  Callers must check status. */
 OVDET_API int ovdet_vp_wait_unpack(void* local_buffer, int world, int64_t rows,
                                    float* scores, int32_t* class_ids, int32_t* status, int timeout_ms,
                                    void* stream);

@@ -288,14 +288,104 @@ def vocabulary_case():
     save("vocab_3cls", matrix=model2.offline_vocabulary.cpu().numpy(), names=np.array(names))
 
 
+def full_forward_case():
+    """The whole boundary against the LIVE reference: ``YOLOCLIP.forward``'s
+    six-key dict (model/yolo_clip.py:102-223) on a batch of two 64x64 images and
+    ``YOLOCLIPDetector.detect`` (inference/detector.py:289-325) on a 48x80 uint8 image.
+
+    Stored: the tensors entering the tail (the neck's per-level maps and its per-image text), the
+    state dicts of the reference's three TextContrastiveHead modules and of its BoxHead, every entry
+    of the forward dict, and the detection records.  The heads are the reference's own classes built
+    with ``hidden_dim=16`` so that their state dicts stay small (the ctor argument exists for that:
+    text_contrastive.py:39-47, box_head.py:38-42); the model, its forward and the detector are the
+    reference's code unchanged."""
+    torch.manual_seed(19)
+    names = ["traffic light", "person", "zebra", "kite", "cup", "dog"]
+    model = YOLOCLIP(backbone_variant="n", num_classes=len(names), offline_mode=True)
+    in_ch = model.backbone.out_channels
+    model.contrastive_heads = torch.nn.ModuleList(
+        [TextContrastiveHead(in_channels=c, embed_dim=512, hidden_dim=16, cls_alpha=1.0, cls_beta=0.0) for c in in_ch])
+    model.box_head = BoxHead(in_channels=in_ch, hidden_dim=16)
+    model.eval()
+    model.offline_vocabulary = torch.randn(len(names), 512)
+    # a random-init network collapses to nearly constant features (scores 1e-8 apart): give every
+    # BatchNorm of the model non-trivial statistics so that anchors differ
+    for mod in [model]:
+        for m in mod.modules():
+            if isinstance(m, torch.nn.BatchNorm2d):
+                m.running_mean.normal_(0, 0.3)
+                m.running_var.uniform_(0.05, 0.3)
+                m.weight.data.uniform_(0.8, 2.0)
+                m.bias.data.normal_(0, 0.5)
+            elif isinstance(m, torch.nn.Conv2d) and m.bias is not None:
+                m.bias.data.normal_(0, 0.1)
+    for branch in model.box_head.box_convs:          # boxes of a few cells instead of exp(8) * stride
+        bias = branch[2].bias.data.view(4, 17)
+        k = torch.arange(17.0)
+        bias[0:2] += -1.2 * k
+        bias[2:4] += -0.9 * (k - 1.5).abs()
+        branch[2].weight.data.mul_(0.3)
+    captured = {}
+    hook = model.neck.register_forward_hook(
+        lambda m, i, o: captured.update(pan=[t.detach().clone() for t in o[0]], text=o[1].detach()))
+    arrays = {"names": np.array(names), "vocabulary": model.offline_vocabulary.numpy()}
+    for l, head in enumerate(model.contrastive_heads):
+        arrays.update({f"sd_head{l}/" + k: v.numpy() for k, v in head.state_dict().items()})
+    arrays.update({"sd_box/" + k: v.numpy() for k, v in model.box_head.state_dict().items()})
+    # ---- forward dict, batch 2 --------------------------------------------------------------------
+    with torch.no_grad():
+        out = model(torch.rand(2, 3, 64, 64).round())       # saturated noise: strong local structure
+    assert list(out.keys()) == ["boxes", "scores", "class_ids", "obj_embeddings", "text_embeddings", "box_preds"]
+    for l, t in enumerate(captured["pan"]):
+        arrays[f"fwd_pan{l}"] = t.numpy()
+    arrays["fwd_text"] = captured["text"].contiguous().numpy()
+    arrays["fwd_text_strides"] = np.array(captured["text"].stride())
+    arrays["fwd_boxes"] = out["boxes"].numpy()
+    arrays["fwd_scores"] = out["scores"].numpy()
+    arrays["fwd_class_ids"] = out["class_ids"].numpy()
+    arrays["fwd_obj_embeddings"] = out["obj_embeddings"].numpy()
+    assert out["text_embeddings"] is captured["text"] or torch.equal(out["text_embeddings"], captured["text"])
+    for l, t in enumerate(out["box_preds"]):
+        arrays[f"fwd_box_preds{l}"] = t.numpy()
+    assert out["class_ids"].dtype == torch.int64
+    # ---- detect(), one image ----------------------------------------------------------------------
+    rng = np.random.default_rng(19)
+    img = (rng.integers(0, 2, (48, 80, 3)) * 255).astype(np.uint8)
+    det = _bare_detector(conf=0.0, iou=0.45, image_size=(64, 64), class_names=names)
+    det.device = "cpu"
+    det.model = model
+    det.use_offline_vocab = True
+    tensor, _, scale = det.preprocess_image(img)
+    with torch.no_grad():
+        probe = np.sort(model(tensor)["scores"][0].numpy())
+    # threshold in the middle of the widest gap between neighbouring scores of the lower half, so
+    # that a 1e-5 score difference cannot move an anchor across it
+    lo, hi = len(probe) // 5, len(probe) // 2
+    g = lo + int(np.argmax(np.diff(probe[lo:hi])))
+    conf = float((probe[g] + probe[g + 1]) / 2)
+    det.conf_threshold = conf
+    dets = det.detect(img)
+    arrays["det_image"] = img
+    arrays["det_tensor"] = tensor.numpy()
+    arrays["det_conf_iou_scale"] = np.array([conf, 0.45, scale], dtype=np.float64)
+    for l, t in enumerate(captured["pan"]):
+        arrays[f"det_pan{l}"] = t.numpy()
+    arrays["det_text"] = captured["text"].contiguous().numpy()
+    arrays["det_box"] = np.array([d["box"] for d in dets], dtype=np.int64).reshape(-1, 4)
+    arrays["det_score"] = np.array([d["score"] for d in dets], dtype=np.float64)
+    arrays["det_class"] = np.array([d["class_id"] for d in dets], dtype=np.int64)
+    arrays["det_name"] = np.array([d["class_name"] for d in dets])
+    hook.remove()
+    print(f"  full forward: scores {out['scores'].min():.3f}..{out['scores'].max():.3f}, conf {conf:.4f}, "
+          f"gap {probe[g + 1] - probe[g]:.2e}, {int((probe > conf).sum())} candidates, {len(dets)} detections of 84 anchors; box span {arrays['det_box'].min()}..{arrays['det_box'].max()}")
+    save("forward_full_64", **arrays)
+
+
 if __name__ == "__main__":
     os.makedirs(OUT, exist_ok=True)
-    similarity_cases()
-    decode_case()
-    nms_cases()
-    postprocess_case()
-    forward_tail_case()
-    preprocess_cases()
-    vocabulary_case()
-    tcsp_case()
-    head_projection_case()
+    only = sys.argv[1:]
+    cases = [similarity_cases, decode_case, nms_cases, postprocess_case, forward_tail_case, preprocess_cases,
+             vocabulary_case, tcsp_case, head_projection_case, full_forward_case]
+    for case in cases:
+        if not only or case.__name__ in only:
+            case()

@@ -20,7 +20,7 @@ OBJ = os.path.join(CSRC, "_obj")
 LIB = os.path.join(PKG_DIR, "libovdet.so")
 INCLUDE = os.path.join(os.path.dirname(PKG_DIR), "include")
 
-SOURCES = ["runtime.cu", "l2norm.cu", "sim_gemm_sm100.cu", "sim_fused_sm100.cu", "rowmax.cu", "decode.cu", "nms.cu", "preprocess.cu", "attention.cu", "step.cu", "vocab_parallel.cu"]
+SOURCES = ["runtime.cu", "l2norm.cu", "sim_gemm_sm100.cu", "sim_fused_sm100.cu", "rowmax.cu", "embeddings.cu", "decode.cu", "nms.cu", "preprocess.cu", "attention.cu", "step.cu", "vocab_parallel.cu"]
 # extra -D definitions for tuning experiments, e.g. OVDET_NVCC_DEFS="-DOVDET_F_A_STAGES=3 -DOVDET_F_B_STAGES=6"
 EXTRA_DEFS = os.environ.get("OVDET_NVCC_DEFS", "").split()
 NVCC_FLAGS = EXTRA_DEFS + [

@@ -5,6 +5,8 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <mutex>
+
 #include "../../include/ovdet.h"
 
 namespace ovdet {
@@ -28,10 +30,22 @@ inline int cuda_fail(cudaError_t e) {
 // Returns OVDET_OK when the current device is compute capability 10.x; cached per device.
 int check_device();
 int sm_count();
-// True the first time it is called for (current device, slot): kernel attributes such as the
-// dynamic shared-memory limit are per device, so they are set once per device, not once per
-// process.  Slots: 0 sim_gemm, 1 sim_fused, 2 nms.  Thread-safe.
-bool first_use_on_device(int slot);
+// Kernel attributes such as the dynamic shared-memory limit are per device: `init` (returning an
+// ovdet_status) runs once per (current device, slot), under a mutex, and the slot is marked done only
+// after it succeeded - a concurrent first caller waits instead of launching before the attribute is
+// set, and a failed attempt is retried by the next call.  Slots: 0 sim_gemm, 1 sim_fused, 2 nms.
+bool first_use_done(int slot);
+void first_use_mark(int slot);
+std::mutex& first_use_mutex();
+template <class F>
+inline int once_per_device(int slot, F&& init) {
+  if (first_use_done(slot)) return OVDET_OK;
+  std::lock_guard<std::mutex> lock(first_use_mutex());
+  if (first_use_done(slot)) return OVDET_OK;
+  const int rc = init();
+  if (rc == OVDET_OK) first_use_mark(slot);
+  return rc;
+}
 
 // sim_fused_sm100.cu: the fused normalise + GEMM + row max kernel behind ovdet_similarity_fused
 // and ovdet_max_sigmoid_attention.

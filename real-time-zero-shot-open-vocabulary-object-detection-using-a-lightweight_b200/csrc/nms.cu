@@ -596,9 +596,10 @@ int ovdet_nms_launch_internal(int pdl, int use_conf, float conf, const float* bo
   p.ws = static_cast<unsigned char*>(workspace);
   p.pow2_cap = next_pow2_cap(anchors);
   p.ws_per_image = WsLayout(p.anchors, p.words, p.pow2_cap).total;
-  if (first_use_on_device(2)) {
-    OVDET_CUDA_TRY(cudaFuncSetAttribute(nms_batched_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, NMS_SMEM_BYTES));
-  }
+  if (int rc = once_per_device(2, []() -> int {
+        OVDET_CUDA_TRY(cudaFuncSetAttribute(nms_batched_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, NMS_SMEM_BYTES));
+        return OVDET_OK;
+      })) return rc;
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3((unsigned)batch);
   cfg.blockDim = dim3(NMS_THREADS);

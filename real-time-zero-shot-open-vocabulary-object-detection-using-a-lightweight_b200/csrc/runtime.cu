@@ -1,6 +1,7 @@
 // Library runtime: version, error strings, device checks.
 #include "common.cuh"
 #include <atomic>
+#include <mutex>
 
 namespace ovdet {
 
@@ -33,12 +34,23 @@ int check_device() {
   return d->status;
 }
 
-bool first_use_on_device(int slot) {
-  static std::atomic<unsigned> seen[64];
+static std::atomic<unsigned> g_first_use_done[64];
+
+bool first_use_done(int slot) {
   int dev = 0;
-  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return true;
-  const unsigned bit = 1u << slot;
-  return (seen[dev].fetch_or(bit) & bit) == 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return false;
+  return (g_first_use_done[dev].load(std::memory_order_acquire) >> slot) & 1u;
+}
+
+void first_use_mark(int slot) {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return;
+  g_first_use_done[dev].fetch_or(1u << slot, std::memory_order_release);
+}
+
+std::mutex& first_use_mutex() {
+  static std::mutex mu;
+  return mu;
 }
 
 int sm_count() {

@@ -1186,13 +1186,14 @@ int fused_launch(const float* const* obj_embeds, const int64_t* hw, const int64_
   X(0, true, 1, false, false, 0, false)  X(0, true, 1, false, false, 1, false)                         \
   X(0, false, 1, true, false, 0, false)                                                                \
   X(0, false, 1, false, true, 0, false)  X(0, false, 1, false, true, 1, false)
-  if (first_use_on_device(1)) {
+  if (int rc = once_per_device(1, []() -> int {
 #define OVDET_SET_SMEM(KB, S3, CGV, PR, I16, MD, E2)                                                    \
-    OVDET_CUDA_TRY(cudaFuncSetAttribute(sim_fused_kernel<KB, S3, CGV, PR, I16, MD, E2>,                 \
-                                        cudaFuncAttributeMaxDynamicSharedMemorySize, FSmem<CGV, (PR && CGV == 2)>::bytes));
-    OVDET_FOR_EACH_FUSED(OVDET_SET_SMEM)
+        OVDET_CUDA_TRY(cudaFuncSetAttribute(sim_fused_kernel<KB, S3, CGV, PR, I16, MD, E2>,             \
+                                            cudaFuncAttributeMaxDynamicSharedMemorySize, FSmem<CGV, (PR && CGV == 2)>::bytes));
+        OVDET_FOR_EACH_FUSED(OVDET_SET_SMEM)
 #undef OVDET_SET_SMEM
-  }
+        return OVDET_OK;
+      })) return rc;
   // second epilogue warpgroup (CTA-pair scores-only kernels): OVDET_EPI2 bit 0 = projected mode (the
   // epilogue is on its critical path: K = 272 per tile), bit 1 = cosine mode, bit 2 = bf16 logits (TMA stores)
   static const int epi2_env = []() { const char* e = getenv("OVDET_EPI2"); return e ? atoi(e) : 5; }();

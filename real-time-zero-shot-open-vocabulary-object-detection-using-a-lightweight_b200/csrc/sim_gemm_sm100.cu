@@ -368,9 +368,10 @@ extern "C" int ovdet_similarity(const void* regions_op, const void* text_op, con
   if (int rc = make_operand_map(&map_a, regions_op, g_batch, g_rows, kop, BLOCK_M)) return rc;
   if (int rc = make_operand_map(&map_b, text_op, text_batched ? batch : 1, classes, kop, p.box_n)) return rc;
 
-  if (first_use_on_device(0)) {
-    OVDET_CUDA_TRY(cudaFuncSetAttribute(sim_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
-  }
+  if (int rc = once_per_device(0, []() -> int {
+        OVDET_CUDA_TRY(cudaFuncSetAttribute(sim_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+        return OVDET_OK;
+      })) return rc;
   const int64_t total_tiles = (int64_t)p.batch * p.m_tiles;
   const int grid = (int)(total_tiles < sm_count() ? total_tiles : sm_count());
   sim_gemm_kernel<<<grid, NUM_THREADS, SMEM_BYTES, as_stream(stream)>>>(map_a, map_b, p);

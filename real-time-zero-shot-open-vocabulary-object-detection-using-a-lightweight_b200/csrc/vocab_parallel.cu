@@ -33,8 +33,9 @@ __host__ __device__ inline size_t vp_flags_offset(long long rows) {
   return ((size_t)rows * 16 + 127) / 128 * 128;            // after keys[2][rows]
 }
 
-// flags block (128 bytes): flags[8] u64, then ctr[2] u64
+// flags block (128 bytes): flags[8] u64, then ctr[2] u64, then the sticky "a wait expired" word
 constexpr int kCtrOffset = 64;
+constexpr int kStickyOffset = 80;
 
 __global__ void vp_signal_kernel(VpTarget t, long long flags_off, int rank) {
   // the similarity kernel of this step has completed (stream order); make its atomics and this
@@ -67,16 +68,24 @@ __device__ __forceinline__ unsigned long long global_timer_ns() {
   return t;
 }
 
+// A timeout is STICKY (a word in the rank's own flags block, so the test costs one L2 read; it is
+// mirrored into `status`, which may be mapped pinned host memory that the host reads without a
+// synchronisation): once a wait has expired - in this block, another block or an earlier step -
+// nothing is unpacked and nothing is handed back.  A late peer's atomics would otherwise land in a
+// key array that was already zeroed for step + 2 and corrupt two steps.  The rows this block owns
+// get the sentinel (-inf, class 0), so that K3 / K4 produce NO detections instead of detections
+// from a partly reduced maximum; the host raises on the status word (VocabParallelHead).
 __global__ void __launch_bounds__(256)
 vp_wait_unpack_kernel(unsigned long long* keys2, const unsigned long long* flags, int world, long long rows,
                       float* __restrict__ scores, int* __restrict__ class_ids,
                       int* status, unsigned long long timeout_ns) {
   __shared__ int s_timeout;
-  if (threadIdx.x == 0) s_timeout = 0;
+  unsigned long long* sticky = const_cast<unsigned long long*>(flags) + kStickyOffset / 8;
+  if (threadIdx.x == 0) s_timeout = __ldcg(sticky) != 0ull;
   const unsigned long long step = __ldcg(flags + kCtrOffset / 8 + 1);
   unsigned long long* keys = keys2 + (long long)(step & 1ull) * rows;
   __syncthreads();
-  if ((int)threadIdx.x < world) {
+  if ((int)threadIdx.x < world && !s_timeout) {
     const unsigned long long t0 = global_timer_ns();
     while (ld_acquire_sys(flags + threadIdx.x) < step) {
       if (global_timer_ns() - t0 > timeout_ns) { s_timeout = 1; break; }
@@ -84,8 +93,19 @@ vp_wait_unpack_kernel(unsigned long long* keys2, const unsigned long long* flags
     }
   }
   __syncthreads();
-  if (s_timeout && threadIdx.x == 0 && status != nullptr) atomicExch(status, 1);
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (s_timeout) {
+    if (threadIdx.x == 0) {
+      *reinterpret_cast<volatile unsigned long long*>(sticky) = 1ull;
+      if (status != nullptr) *reinterpret_cast<volatile int*>(status) = 1;
+      __threadfence_system();
+    }
+    if (i < rows) {
+      scores[i] = -INFINITY;
+      class_ids[i] = 0;
+    }
+    return;
+  }
   if (i >= rows) return;
   // the keys were written by remote (and local) atomics, performed at this GPU's L2: read there
   const unsigned long long key = __ldcg(keys + i);

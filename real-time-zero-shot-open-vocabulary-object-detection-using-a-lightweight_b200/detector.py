@@ -11,6 +11,7 @@ tensors; nothing is computed on the CPU.
 """
 from __future__ import annotations
 
+import dataclasses
 from typing import Dict, List, Optional, Sequence, Tuple, Union
 
 import numpy as np
@@ -153,9 +154,11 @@ class Detector:
                      per_image_text: bool, projections=None) -> HeadPipeline:
         shapes = tuple((e.shape[2], e.shape[3]) for e in obj_embeds)
         proj_key = None if projections is None else tuple(w.data_ptr() for w, _ in projections)
-        key = (obj_embeds[0].shape[0], shapes, num_classes, per_image_text, obj_embeds[0].device, proj_key)
+        dim = self.config.embed_dim if projections is not None else int(obj_embeds[0].shape[1])
+        key = (obj_embeds[0].shape[0], shapes, num_classes, per_image_text, obj_embeds[0].device, proj_key, dim)
         if key not in self._pipelines:
-            self._pipelines[key] = HeadPipeline(key[0], shapes, num_classes, self.config,
+            config = self.config if dim == self.config.embed_dim else dataclasses.replace(self.config, embed_dim=dim)
+            self._pipelines[key] = HeadPipeline(key[0], shapes, num_classes, config,
                                                 device=obj_embeds[0].device,
                                                 per_image_text=per_image_text, projections=projections)
         return self._pipelines[key]
@@ -169,7 +172,9 @@ class Detector:
                 pipe.set_vocabulary(self._vocabulary)
 
     def predict_host(self, obj_embeds: Sequence[torch.Tensor], box_preds: Sequence[torch.Tensor],
-                     chunk: int = 32, projections=None) -> Dict[str, torch.Tensor]:
+                     chunk: int = 32, projections=None,
+                     orig_sizes: Optional[Sequence[Tuple[int, int]]] = None,
+                     scale_factors: Optional[Sequence[float]] = None) -> Dict[str, torch.Tensor]:
         """``predict`` for HOST buffers (pinned CPU tensors, as a serving front-end holds them):
         the batch is cut into chunks; chunk i+1 is copied host->device on a copy stream while
         chunk i runs K1..K4 on the compute stream, and each chunk's detections are copied back
@@ -215,6 +220,12 @@ class Detector:
         for i in range(batch // chunk):
             lo, hi = i * chunk, (i + 1) * chunk
             objs, boxes = st["stage"][i & 1]
+            if orig_sizes is not None:
+                with torch.cuda.stream(comp_s):
+                    pipe.set_geometry(orig_sizes[lo:hi], scale_factors[lo:hi] if scale_factors is not None
+                                      else [1.0] * chunk)
+            else:
+                pipe.clear_geometry()
             with torch.cuda.stream(copy_s):
                 if freed[i & 1] is not None:
                     copy_s.wait_event(freed[i & 1])
@@ -249,7 +260,99 @@ class Detector:
         if orig_sizes is not None:
             pipe.set_geometry(orig_sizes, scale_factors if scale_factors is not None
                               else [1.0] * len(orig_sizes))
+        else:
+            pipe.clear_geometry()       # pipelines are cached per shape: no geometry left over from an earlier call
         return pipe.run(obj_embeds, box_preds, text_embeddings)
+
+
+class YOLOCLIPDetector(Detector):
+    """``YOLOCLIPDetector`` of inference/detector.py:14-117, 289-325 with the reference's
+    constructor arguments and ``detect(image, text_prompts=None) -> List[Dict]``; the call sequence
+    of detect.py:92-125 runs against it unchanged.
+
+    What stays outside (backbone, neck, CLIP, head convolutions are
+    PyTorch/cuDNN code that is not on the path) is the convolutional model itself, so it is
+    injected: ``model`` is a ready ``YOLOCLIP``-shaped module (attributes ``backbone``, ``neck``,
+    ``contrastive_heads``, ``box_head``, ``offline_mode``, ``offline_vocabulary``,
+    ``text_encoder``), or ``model_factory`` builds one from the reference's keyword arguments;
+    with neither, the reference's own class is imported (``yolo_clip_detector`` on ``sys.path``).
+    Everything from the letterbox to the detection records except that model runs in
+    ``libovdet.so``: P1 letterbox -> [model] -> K1+K2 fused similarity -> K3 decode -> K4 NMS ->
+    int-truncated records.  ``precision``: ``"fp32"`` (default, the reference's arithmetic to
+    ~1e-5) or ``"bf16"`` (|dscore| <~ 8e-3)."""
+
+    def __init__(self, model_path: Optional[str] = None, class_names: Optional[List[str]] = None,
+                 vocab_path: Optional[str] = None, device=None, image_size: Tuple[int, int] = (640, 640),
+                 conf_threshold: float = 0.25, iou_threshold: float = 0.45, backbone_variant: str = "n",
+                 clip_model: str = "ViT-B/32", embed_dim: int = 512, *, model: Optional[torch.nn.Module] = None,
+                 model_factory=None, precision: str = "fp32", max_det: int = 0):
+        if device is None:
+            if not torch.cuda.is_available():
+                raise RuntimeError("ovdet: YOLOCLIPDetector needs a CUDA device (no CPU fallback exists)")
+            device = "cuda:0"
+        device = torch.device(device)
+        if device.type != "cuda":
+            raise RuntimeError("ovdet: YOLOCLIPDetector needs a CUDA device (no CPU fallback exists)")
+        if device.index is None:
+            device = torch.device("cuda", torch.cuda.current_device())
+        config = HeadConfig(embed_dim=embed_dim, conf_threshold=conf_threshold, iou_threshold=iou_threshold,
+                            precision=precision, max_det=max_det)
+        super().__init__(class_names=class_names, conf_threshold=conf_threshold, iou_threshold=iou_threshold,
+                         image_size=image_size, device=device, config=config)
+        if model is None:
+            kwargs = dict(backbone_variant=backbone_variant, clip_model=clip_model, embed_dim=embed_dim,
+                          num_classes=len(class_names) if class_names is not None else 80,
+                          offline_mode=vocab_path is not None or class_names is not None)
+            if model_factory is None:
+                try:
+                    from yolo_clip_detector.model.yolo_clip import YOLOCLIP as model_factory
+                except ImportError as exc:
+                    raise RuntimeError("ovdet: pass `model=` / `model_factory=` (the convolutional model is not "
+                                       "part of this library) or put yolo_clip_detector on sys.path") from exc
+            model = model_factory(**kwargs)
+        self.model = model.to(self.device)
+        if model_path is not None:
+            self._load_model(model_path)
+        self.model.eval()
+        self.use_offline_vocab = False
+        if vocab_path is not None:
+            self.load_offline_vocabulary(vocab_path)
+        elif class_names is not None and hasattr(self.model, "set_offline_vocabulary"):
+            self.model.set_offline_vocabulary(class_names)        # needs the model's CLIP text encoder
+            self.use_offline_vocab = True
+        elif getattr(self.model, "offline_mode", False) and getattr(self.model, "offline_vocabulary", None) is not None:
+            self.use_offline_vocab = True                         # an injected model that carries its vocabulary
+        self.feature_fn = self._features
+
+    def _load_model(self, model_path: str) -> None:
+        """inference/detector.py:103-117: a raw state dict or one wrapped as ``model_state_dict``."""
+        checkpoint = torch.load(model_path, map_location=self.device)
+        state = checkpoint["model_state_dict"] if "model_state_dict" in checkpoint else checkpoint
+        self.model.load_state_dict(state)
+
+    def load_offline_vocabulary(self, path: str) -> None:
+        """model/yolo_clip.py:244-263 through ``ovdet.vocabulary``: class names and the ``[C, D]`` matrix
+        of the reference's JSON file; the model's own ``offline_vocabulary`` is set as well."""
+        from .vocabulary import Vocabulary
+        vocab = Vocabulary.load(path)
+        if self.class_names is None:
+            self.class_names = vocab.class_names
+        self.model.offline_mode = True
+        self.model.offline_vocabulary = vocab.embeddings.to(self.device, torch.float32)
+        self.use_offline_vocab = True
+
+    def _features(self, tensor: torch.Tensor, text_prompts=None):
+        """model/yolo_clip.py:121-189 up to the convolution outputs: text embeddings, backbone, neck,
+        the heads' embedding branch and the box head's convolutions."""
+        from .heads import prompt_embeddings
+        model = self.model
+        if not self.use_offline_vocab and text_prompts is None:
+            raise ValueError("Text prompts must be provided in online mode")
+        text = prompt_embeddings(model, tensor.shape[0], None if self.use_offline_vocab else text_prompts)
+        pan_features, text = model.neck(model.backbone(tensor), text)
+        obj_embeds = [head.obj_embed_conv(feat) for feat, head in zip(pan_features, model.contrastive_heads)]
+        box_preds = [conv(feat) for conv, feat in zip(model.box_head.box_convs, pan_features)]
+        return obj_embeds, box_preds, text
 
 
 def _pack_mask(passed: torch.Tensor) -> torch.Tensor:

@@ -4,7 +4,9 @@ shapes / strides / dtypes and state-dict keys, with the arithmetic of the hot pa
 
 * ``TextContrastiveHead``  <- model/heads/text_contrastive.py:32-222
 * ``BoxHead``              <- model/heads/box_head.py:31-218
-* ``head_tail``            <- the tail of YOLOCLIP.forward, model/yolo_clip.py:173-223
+* ``head_tail``            <- the tail of YOLOCLIP.forward, model/yolo_clip.py:173-223, from the conv outputs
+* ``forward_tail``         <- the same tail from the neck's outputs, all six dict keys
+* ``patch_yolo_clip``      <- rebinds an existing YOLOCLIP.forward to ``forward_tail``
 
 The convolution stacks stay in PyTorch/cuDNN (out of
 scope); no parameter or buffer is added, so reference checkpoints load unchanged.
@@ -158,27 +160,180 @@ class BoxHead(nn.Module):
         return boxes
 
 
+def _similarity_levels(obj_embeds: Sequence[torch.Tensor], text_embeddings: torch.Tensor,
+                       cls_alpha: float, cls_beta: float, precision: str, want_logits: bool):
+    """Similarity + class max / argmax of all levels: ``(logits or None, scores, class_ids int32,
+    path)``.  ONE fused launch straight from the fp32 NCHW conv outputs whenever the kernel takes
+    the shape (always for bf16 with TMA-addressable levels; fp32-accurate for any class count at
+    dim <= 512); K1 -> K2 otherwise."""
+    split = precision == "fp32"
+    classes = text_embeddings.shape[-2]
+    levels = [e if e.dtype in (torch.float32, torch.bfloat16) else e.float() for e in obj_embeds]
+    fused = ops.fused_fp32_supported(levels, classes) if split else ops.fused_supported(levels)
+    logits_dtype = torch.float32 if want_logits else None
+    if fused:
+        text_op = ops.text_operand_fp32(text_embeddings.float()) if split else ops.l2norm_text(text_embeddings.float())
+        logits, scores, class_ids = ops.similarity_fused(levels, text_op, cls_alpha, cls_beta,
+                                                         logits_dtype=logits_dtype, want_max=True, fp32=split)
+        return logits, scores, class_ids, "fused_fp32" if split else "fused"
+    levels = [e.float() for e in levels]
+    regions_op, inv_norm = ops.l2norm_regions(levels, split=split)
+    text_op = ops.l2norm_text(text_embeddings.float(), split=split)
+    logits, scores, class_ids = ops.similarity(regions_op, text_op, inv_norm, levels[0].shape[1], cls_alpha,
+                                               cls_beta, split=split, logits_dtype=logits_dtype, want_max=True)
+    return logits, scores, class_ids, "split"
+
+
 def head_tail(obj_embeds: Sequence[torch.Tensor], text_embeddings: torch.Tensor,
               box_preds: Sequence[torch.Tensor], strides: Sequence[int] = (8, 16, 32),
-              cls_alpha: float = 1.0, cls_beta: float = 0.0, precision: str = "bf16",
+              cls_alpha: float = 1.0, cls_beta: float = 0.0, precision: str = "fp32",
               return_logits: bool = False) -> Dict[str, torch.Tensor]:
     """The tail of ``YOLOCLIP.forward`` (model/yolo_clip.py:173-223) from the convolution outputs
-    on: similarity for every level, class max / argmax, level concat, box decode.  All levels
-    go through ONE normalise launch per level, ONE GEMM with the max/argmax fused in the
-    epilogue and ONE decode launch.  Returns the reference's dict keys ``boxes`` / ``scores`` /
+    on: similarity for every level, class max / argmax, level concat, box decode - ONE fused
+    similarity launch (L2 norm + tcgen05 GEMM + class max / argmax reading the NCHW conv outputs
+    in place) and ONE decode launch.  Returns the reference's dict keys ``boxes`` / ``scores`` /
     ``class_ids`` (int64), plus ``logits [B, A, C]`` when asked."""
-    split = precision == "fp32"
-    dim = obj_embeds[0].shape[1]
-    regions_op, inv_norm = ops.l2norm_regions(obj_embeds, split=split)
-    text_op = ops.l2norm_text(text_embeddings, split=split)
-    logits, scores, class_ids = ops.similarity(
-        regions_op, text_op, inv_norm, dim, cls_alpha, cls_beta, split=split,
-        logits_dtype=torch.float32 if return_logits else None, want_max=True)
+    logits, scores, class_ids, _ = _similarity_levels(obj_embeds, text_embeddings, cls_alpha, cls_beta,
+                                                      precision, return_logits)
     boxes, _, _ = ops.decode_filter(box_preds, strides)
     out = {"boxes": boxes, "scores": scores, "class_ids": class_ids.long()}
     if return_logits:
         out["logits"] = logits
     return out
+
+
+class TailOutputs(dict):
+    """The forward dict of ``YOLOCLIP.forward`` (model/yolo_clip.py:216-223) with values that
+    may be produced on first access.  ``obj_embeddings [B, A, D]`` is a 17 MB-per-image transposed
+    copy of the conv outputs that only the trainer reads (train/trainer.py:144-182); inference
+    (inference/detector.py:179-181) reads ``boxes`` / ``scores`` / ``class_ids`` only, so the copy
+    is made when - and if - the key is looked up.  Behaves like the plain dict otherwise (``keys``,
+    ``in``, ``items``, ``**`` unpacking all see six entries)."""
+
+    def __init__(self, eager: Dict, lazy: Dict):
+        super().__init__(eager)
+        self._lazy = dict(lazy)
+        for key in self._lazy:
+            super().__setitem__(key, None)
+
+    def _resolve(self, key):
+        make = self._lazy.pop(key, None)
+        if make is not None:
+            super().__setitem__(key, make())
+
+    def __getitem__(self, key):
+        self._resolve(key)
+        return super().__getitem__(key)
+
+    def get(self, key, default=None):
+        return self[key] if key in self else default
+
+    def __iter__(self):            # a python-level __iter__ keeps dict(x) / {**x} off the C fast path
+        return super().__iter__()
+
+    def items(self):
+        for key in list(self._lazy):
+            self._resolve(key)
+        return super().items()
+
+    def values(self):
+        for key in list(self._lazy):
+            self._resolve(key)
+        return super().values()
+
+    def pop(self, key, *default):
+        self._resolve(key)
+        return super().pop(key, *default)
+
+    def copy(self):
+        return dict(self.items())
+
+
+def forward_tail(pan_features: Sequence[torch.Tensor], text_embeddings: torch.Tensor,
+                 contrastive_heads: Sequence[nn.Module], box_head: nn.Module,
+                 precision: str = "fp32") -> Dict[str, torch.Tensor]:
+    """Drop-in for model/yolo_clip.py:173-223 - everything ``YOLOCLIP.forward`` does after the
+    neck: ``pan_features`` (the neck's per-level maps) and the neck's text embeddings ``[B, C, D]``
+    (any strides: the neck emits ``(D, B*D, 1)``, the offline vocabulary a stride-0 expand) go
+    through the heads' convolution stacks (cuDNN, unchanged), ONE fused similarity launch for all
+    levels (normalise + contraction + class max / argmax) and ONE decode launch.
+
+    ``contrastive_heads`` / ``box_head`` are the model's own modules - the reference's classes or
+    the drop-ins of this file; only their convolution stacks and plain attributes are used.
+    Returns the reference's six keys with its shapes and dtypes: ``boxes [B, A, 4]`` fp32,
+    ``scores [B, A]`` fp32, ``class_ids [B, A]`` int64, ``obj_embeddings [B, A, D]`` fp32,
+    ``text_embeddings`` (as handed in), ``box_preds`` (list of ``[B, 4R, H, W]``)."""
+    assert precision in PRECISIONS
+    assert len(pan_features) == len(contrastive_heads)
+    # yolo_clip.py:177-186 calls head(feat) and drops the second output (the head's own box
+    # branch, dead in the reference): only the embedding branch is evaluated here
+    obj_embeds = [head.obj_embed_conv(feat) if hasattr(head, "obj_embed_conv") else head(feat)[0]
+                  for feat, head in zip(pan_features, contrastive_heads)]
+    # box_head.forward also builds int64 grids that only decode_boxes consumed (box_head.py:115-148)
+    if hasattr(box_head, "box_convs"):
+        box_preds = [conv(feat) for conv, feat in zip(box_head.box_convs, pan_features)]
+    else:
+        box_preds = box_head(list(pan_features))[0]
+    affine = {(float(h.cls_alpha), float(h.cls_beta)) for h in contrastive_heads}
+    if len(affine) == 1:
+        (alpha, beta), = affine
+        _, scores, class_ids, _ = _similarity_levels(obj_embeds, text_embeddings, alpha, beta, precision, False)
+    else:       # per-level affine parameters: one launch per level, concatenated like yolo_clip.py:205-206
+        parts = [_similarity_levels([e], text_embeddings, float(h.cls_alpha), float(h.cls_beta), precision, False)
+                 for e, h in zip(obj_embeds, contrastive_heads)]
+        scores = torch.cat([p[1] for p in parts], dim=1)
+        class_ids = torch.cat([p[2] for p in parts], dim=1)
+    boxes, _, _ = ops.decode_filter(box_preds, box_head.strides)
+    eager = {"boxes": boxes, "scores": scores, "class_ids": class_ids.long()}
+    lazy = {"obj_embeddings": lambda: ops.concat_embeddings([e.float() for e in obj_embeds])}
+    out = TailOutputs(eager, lazy)
+    out["text_embeddings"] = text_embeddings
+    out["box_preds"] = box_preds
+    return out
+
+
+def prompt_embeddings(model: nn.Module, batch: int, text_prompts=None, class_names=None) -> torch.Tensor:
+    """The ``[B, C, D]`` text embeddings ``YOLOCLIP.forward`` builds before the backbone
+    (model/yolo_clip.py:121-165): the offline vocabulary as a stride-0 expand, or the encoder's
+    output for a shared prompt list / one prompt list per image (short lists are zero padded to
+    the longest, a short outer list repeats its last entry)."""
+    if getattr(model, "offline_mode", False):
+        if model.offline_vocabulary is None:
+            if class_names is None:
+                raise ValueError("In offline mode, either offline_vocabulary or class_names must be provided")
+            model.offline_vocabulary = model.vocab_builder.build_online_vocabulary(class_names)
+        return model.offline_vocabulary.unsqueeze(0).expand(batch, -1, -1)
+    if text_prompts is None:
+        raise ValueError("In online mode, text_prompts must be provided")
+    if len(text_prompts) > 0 and isinstance(text_prompts[0], (list, tuple)):
+        if len(text_prompts) == 1 or batch == 1:        # one list serves every image: encode once, stride-0 batch
+            return model.text_encoder(list(text_prompts[0])).unsqueeze(0).expand(batch, -1, -1)
+        per_image = [model.text_encoder(list(text_prompts[min(i, len(text_prompts) - 1)])) for i in range(batch)]
+        rows = max(e.shape[0] for e in per_image)
+        padded = [e if e.shape[0] == rows else torch.cat([e, e.new_zeros(rows - e.shape[0], e.shape[1])])
+                  for e in per_image]
+        return torch.stack(padded)
+    return model.text_encoder(text_prompts).unsqueeze(0).expand(batch, -1, -1)
+
+
+def patch_yolo_clip(model: nn.Module, precision: str = "fp32") -> nn.Module:
+    """Point an existing ``YOLOCLIP`` instance (model/yolo_clip.py:16-263) at the CUDA tail: its
+    ``forward`` keeps the text handling, backbone and neck it has and hands the neck's outputs to
+    ``forward_tail``.  No parameter, buffer or submodule changes, so checkpoints load as before::
+
+        model = YOLOCLIP(...); ovdet.heads.patch_yolo_clip(model)
+    """
+    assert precision in PRECISIONS
+
+    def forward(images, text_prompts=None, class_names=None):
+        text = prompt_embeddings(model, images.shape[0], text_prompts, class_names)
+        features = model.backbone(images)
+        pan_features, updated_text = model.neck(features, text)
+        return forward_tail(pan_features, updated_text, model.contrastive_heads, model.box_head, precision)
+
+    model.forward = forward
+    model.ovdet_precision = precision
+    return model
 
 
 def head_tail_projected(hidden: Sequence[torch.Tensor], projections: Sequence[Tuple[torch.Tensor, Optional[torch.Tensor]]],

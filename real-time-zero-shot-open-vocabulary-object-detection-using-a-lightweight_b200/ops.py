@@ -244,6 +244,31 @@ def rowmax(logits: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
     return out_max.reshape(logits.shape[:-1]), out_arg.reshape(logits.shape[:-1])
 
 
+def concat_embeddings(obj_embeds: Sequence[torch.Tensor], out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """yolo_clip.py:208-214: per level fp32 ``[B, D, H, W]`` -> ``[B, sum HW, D]`` (levels
+    concatenated P3|P4|P5, anchor index ``i * W + j`` inside a level), one launch per level."""
+    first = obj_embeds[0]
+    _require_cuda(first, "obj_embed", torch.float32)
+    batch, dim = first.shape[0], first.shape[1]
+    anchors = sum(e.shape[2] * e.shape[3] for e in obj_embeds)
+    if out is None:
+        out = torch.empty(batch, anchors, dim, device=first.device, dtype=torch.float32)
+    assert out.shape == (batch, anchors, dim) and out.is_contiguous() and out.dtype == torch.float32
+    offset = 0
+    with torch.cuda.device(first.device):
+        for e in obj_embeds:
+            _require_cuda(e, "obj_embed", torch.float32)
+            b, d, h, w = e.shape
+            assert b == batch and d == dim
+            if e.stride(3) != 1 or e.stride(2) != w:
+                e = e.contiguous()
+            check(lib().ovdet_concat_embeddings(e.data_ptr(), b, d, h * w, e.stride(0), e.stride(1),
+                                                out.data_ptr(), anchors, offset, _stream(e)),
+                  "ovdet_concat_embeddings")
+            offset += h * w
+    return out
+
+
 # --------------------------------------------------------------------------------------------
 # K3: DFL decode + activation + confidence threshold
 # --------------------------------------------------------------------------------------------

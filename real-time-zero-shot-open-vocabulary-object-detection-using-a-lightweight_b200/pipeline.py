@@ -138,12 +138,45 @@ class HeadPipeline:
         self.clip_wh.copy_(torch.from_numpy(wh))
         self.use_geometry = True
 
+    def clear_geometry(self) -> None:
+        """Back to "boxes stay in input-image pixels, no clipping" (no ``orig_sizes`` given)."""
+        self.use_geometry = False
+
+    def check_inputs(self, obj_embeds: Sequence[torch.Tensor], box_preds: Sequence[torch.Tensor],
+                     text: Optional[torch.Tensor] = None) -> None:
+        """The planned shapes are what the tensor maps, the decode kernel and the workspaces are
+        sized for: anything else would read or write past an allocation, so it is an error here."""
+        n = len(self.level_shapes)
+        if len(obj_embeds) != n or len(box_preds) != n:
+            raise ValueError(f"ovdet: expected {n} levels, got {len(obj_embeds)} / {len(box_preds)}")
+        dim = self.projections[0][0].shape[1] if self.projections is not None else self.cfg.embed_dim
+        ch = 4 * (self.cfg.reg_max + 1)
+        for l, ((h, w), e, p) in enumerate(zip(self.level_shapes, obj_embeds, box_preds)):
+            if tuple(e.shape) != (self.batch, dim, h, w):
+                raise ValueError(f"ovdet: level {l} embeddings are {tuple(e.shape)}, the pipeline was planned for "
+                                 f"{(self.batch, dim, h, w)}")
+            if tuple(p.shape) != (self.batch, ch, h, w):
+                raise ValueError(f"ovdet: level {l} box_preds are {tuple(p.shape)}, the pipeline was planned for "
+                                 f"{(self.batch, ch, h, w)}")
+            if e.device != self.device or p.device != self.device:
+                raise ValueError(f"ovdet: level {l} tensors live on {e.device} / {p.device}, the pipeline on {self.device}")
+        if text is not None:
+            want_d = self.cfg.embed_dim
+            ok = text.shape[-2:] == (self.num_classes, want_d) and (
+                text.dim() == 2 or (text.dim() == 3 and text.shape[0] in (1, self.batch)))
+            if not ok:
+                raise ValueError(f"ovdet: text embeddings are {tuple(text.shape)}, expected [{self.num_classes}, {want_d}] "
+                                 f"or [{self.batch}, {self.num_classes}, {want_d}]")
+            if self.per_image_text and not (text.dim() == 3 and text.shape[0] == self.batch):
+                raise ValueError("ovdet: this pipeline was planned for per-image text [B, C, D]")
+
     # -- the hot path -----------------------------------------------------------------------
     def run(self, obj_embeds: Sequence[torch.Tensor], box_preds: Sequence[torch.Tensor],
             text: Optional[torch.Tensor] = None, events: Optional[dict] = None) -> ops.NmsResult:
         """One pass of the hot path.  ``events`` (optional dict) receives a pair of CUDA events
         per stage, recorded on the launching stream, for per-kernel timing."""
         cfg = self.cfg
+        self.check_inputs(obj_embeds, box_preds, text)
 
         def mark(name, begin):
             if events is not None:

@@ -158,8 +158,12 @@ class VocabParallelHead:
         self.pipe = HeadPipeline(batch, level_shapes, self.c1 - self.c0, config, device=device)
         self.device = self.pipe.device
         self.rows = batch * self.pipe.anchors
-        self.status = torch.zeros(1, device=self.device, dtype=torch.int32)
+        # sticky status word of the bounded waits, in pinned host memory that the kernels write
+        # through the unified address space: the host reads it without synchronising
+        self.status = torch.zeros(1, dtype=torch.int32).pin_memory()
         self.timeout_ms = 2000
+        self.first_timeout_ms = 30000       # step 1: a peer may still be loading modules / encoding tensor maps
+        self._steps = 0
         self._sim_ws = None
         self.buffer = None
         self.peer_ptrs = None
@@ -242,7 +246,7 @@ class VocabParallelHead:
             if self.exchange == "fused":
                 check(lib().ovdet_vp_wait_unpack(self.buffer.ptr, self.world, self.rows,
                                                  pipe.scores.data_ptr(), pipe.class_ids.data_ptr(),
-                                                 self.status.data_ptr(), self.timeout_ms,
+                                                 self.status.data_ptr(), self._timeout(),
                                                  torch.cuda.current_stream(self.device).cuda_stream),
                       "ovdet_vp_wait_unpack")
             else:
@@ -250,18 +254,56 @@ class VocabParallelHead:
                 self._dist.all_reduce(self._keys, op=self._dist.ReduceOp.MAX, group=self.group)
                 unpack_score_keys(self._keys, pipe.scores, pipe.class_ids)
 
+    def _timeout(self) -> int:
+        t = self.first_timeout_ms if self._steps == 0 else self.timeout_ms
+        self._steps += 1
+        return int(t)
+
+    def raise_if_timed_out(self, synchronize: bool = False) -> None:
+        """A wait on the peers' flags expired in an earlier step (or, with ``synchronize``, in any
+        step enqueued so far): that step and every later one carry NO detections on this rank (the
+        status is sticky and the key arrays are no longer handed back).  Raises; recover with
+        ``reset()`` on every rank."""
+        if synchronize:
+            torch.cuda.synchronize(self.device)
+        if int(self.status[0]) != 0:
+            raise RuntimeError(f"ovdet: rank {self.rank}: a peer did not signal within the exchange timeout; "
+                               "the steps since then returned no detections (VocabParallelHead.reset() on "
+                               "every rank re-arms the exchange)")
+
+    def reset(self) -> None:
+        """Re-arm after a timeout: counters, flags and key arrays back to their initial state.  Every
+        rank must call it (collective when a process group is attached)."""
+        torch.cuda.synchronize(self.device)
+        if self._dist is not None:
+            self._dist.barrier(group=self.group)
+        if self.buffer is not None:
+            with torch.cuda.device(self.device):
+                check(lib().ovdet_vp_buffer_init(self.buffer.ptr, self.rows, self.world,
+                                                 torch.cuda.current_stream(self.device).cuda_stream),
+                      "ovdet_vp_buffer_init")
+            torch.cuda.synchronize(self.device)
+        self.status.zero_()
+        self._steps = 0
+        if self._dist is not None:
+            self._dist.barrier(group=self.group)
+
     def run(self, obj_embeds: Sequence[torch.Tensor], box_preds: Sequence[torch.Tensor]):
         """One pass: sharded similarity + exchange, then K3 / K4 on the merged scores.  Every rank
         returns the same detections.  With the fused exchange the whole step is one C call
         (``ovdet_head_step_vp``) whose arguments never change, so it can also be captured in a CUDA
-        graph (``capture`` / ``replay``)."""
+        graph (``capture`` / ``replay``).  Raises when an EARLIER step's wait expired (read from the
+        pinned status word, no synchronisation); ``raise_if_timed_out(synchronize=True)`` checks
+        the step just enqueued."""
+        self.raise_if_timed_out()
+        self.pipe.check_inputs(obj_embeds, box_preds)
         if self.exchange == "fused" and self.pipe._single_call_ok(box_preds):
             if not ops.fused_supported(obj_embeds) or self.cfg.embed_dim != 512:
                 raise ValueError("ovdet: inputs not addressable by the fused similarity kernel")
             a = self.pipe._fill_step_args(obj_embeds, box_preds)
             with torch.cuda.device(self.device):
                 check(lib().ovdet_head_step_vp(ctypes.byref(a), self.c0, self.peer_ptrs, self.world, self.rank,
-                                               self.status.data_ptr(), self.timeout_ms,
+                                               self.status.data_ptr(), self._timeout(),
                                                torch.cuda.current_stream(self.device).cuda_stream),
                       "ovdet_head_step_vp")
             return self.pipe.result
@@ -284,6 +326,7 @@ class VocabParallelHead:
             self.run(obj_embeds, box_preds)
 
     def replay(self):
+        self.raise_if_timed_out()
         self._graph.replay()
         return self.pipe.result
 
@@ -292,7 +335,8 @@ class VocabParallelHead:
 
     def timed_out(self) -> bool:
         """Host check (synchronises): did a wait on the peers' flags expire?"""
-        return bool(self.status.item())
+        torch.cuda.synchronize(self.device)
+        return bool(int(self.status[0]))
 
     def close(self) -> None:
         if self.buffer is not None:

@@ -352,13 +352,75 @@ def test_predict_vs_oracle(ov, cuda_device, precision):
         np.testing.assert_array_equal(res.classes[i, :k].cpu().numpy(), want[i]["class_ids"])
         np.testing.assert_array_equal(res.boxes[i, :k].cpu().numpy(), want[i]["boxes"])
     assert total > 20                       # the synthetic inputs give NMS real work
-    # (ii) end to end against the pure-oracle path: same kept anchors unless a score sits within
-    # rounding distance of the threshold or an IoU within rounding distance of 0.45
+    # (ii) end to end against the pure-oracle path (oracle scores -> oracle NMS): the kept anchor sets
+    # differ only where a device score sits within its error of the threshold / of a neighbour's score,
+    # or an IoU within rounding distance of 0.45.  Reported per image, bounded per precision.
     pure = ref_port.postprocess_batch(tail, sizes, [1.0] * 4)
-    if precision == "fp32":
-        same = sum(set(res.anchor[i, :int(res.count[i])].tolist()) == set(pure[i]["anchor_idx"].tolist())
-                   for i in range(4))
-        assert same >= 3
+    mism, kept_ref = _index_mismatches(res, pure)
+    print(f"\n[e2e index mismatches, {precision}] per image {mism} of {kept_ref} kept")
+    # fp32: |dscore| ~ 1e-5 - a flip needs two overlapping candidates whose scores are closer than that;
+    # bf16: |dscore| up to 4e-3 reorders near-equal overlapping candidates (planted scores span 0.79-0.87)
+    bound = 0.01 if precision == "fp32" else 0.15
+    assert sum(mism) <= max(1, int(bound * sum(kept_ref))), (mism, kept_ref)
+
+
+def _index_mismatches(res, pure):
+    """Per image: size of the symmetric difference between the device's kept anchor set and the
+    oracle's, and the oracle's kept count."""
+    mism, kept = [], []
+    for i, want in enumerate(pure):
+        got = set(res.anchor[i, :int(res.count[i])].tolist())
+        ref = set(int(a) for a in want["anchor_idx"].tolist())
+        mism.append(len(got ^ ref))
+        kept.append(len(ref))
+    return mism, kept
+
+
+def test_config2_shape_fp32_fused_streaming_vs_oracle(ov, cuda_device):
+    """BASELINE configs[1] at its real per-image size (640^2: 6400 + 1600 + 400 anchors, 80 prompts,
+    fp32-accurate): the fused kernel's streaming three-pass mode over 50 anchor tiles per image of
+    the first level (the 8-slot A ring wraps 19 times per CTA), two images, against the oracle:
+    logits inside the fp32 bar, classes equal, boxes 1e-4, post-processing bit-exact on identical
+    inputs, and the end-to-end kept sets reported."""
+    from ovdet import ops, synth
+    from ovdet.pipeline import HeadConfig, HeadPipeline
+    b, classes, s = 2, 80, 640
+    inp = synth.make_inputs(batch=b, image_size=s, num_classes=classes, seed=11)
+    tail = ref_port.head_tail(inp.obj_embeds, inp.text_batched(), inp.box_preds)
+    shapes = [(s // 8, s // 8), (s // 16, s // 16), (s // 32, s // 32)]
+    pipe = HeadPipeline(b, shapes, classes, HeadConfig(precision="fp32", logits_dtype="fp32"), device=cuda_device)
+    pipe.set_vocabulary(inp.text.to(cuda_device))
+    sizes = [(s, s)] * b
+    pipe.set_geometry(sizes, [1.0] * b)
+    objs = [e.to(cuda_device) for e in inp.obj_embeds]
+    preds = [p.to(cuda_device) for p in inp.box_preds]
+    res = pipe.run(objs, preds)
+    torch.cuda.synchronize()
+    assert pipe.last_path == "fused_fp32"
+    ref_logits = torch.cat([ref_port.compute_similarity(e, inp.text_batched()).flatten(2).transpose(1, 2)
+                            for e in inp.obj_embeds], dim=1)
+    assert_logits_close(pipe.logits, ref_logits, "fp32")
+    assert (pipe.logits.cpu() - ref_logits).abs().max().item() <= 3e-5
+    assert_logits_close(pipe.scores, tail["scores"], "fp32")
+    assert (pipe.class_ids.cpu().long() == tail["class_ids"]).float().mean() >= 0.999
+    torch.testing.assert_close(pipe.boxes.cpu(), tail["boxes"], rtol=1e-4, atol=1e-3)
+    fed = {"boxes": pipe.boxes.cpu(), "scores": pipe.scores.cpu(), "class_ids": pipe.class_ids.cpu().long()}
+    want = ref_port.postprocess_batch(fed, sizes, [1.0] * b)
+    for i in range(b):
+        k = int(res.count[i])
+        assert k == len(want[i]["keep"]) and k > 20
+        np.testing.assert_array_equal(res.keep[i, :k].cpu().numpy(), want[i]["keep"])
+        np.testing.assert_array_equal(res.classes[i, :k].cpu().numpy(), want[i]["class_ids"])
+        np.testing.assert_array_equal(res.boxes[i, :k].cpu().numpy(), want[i]["boxes"])
+    mism, kept_ref = _index_mismatches(res, ref_port.postprocess_batch(tail, sizes, [1.0] * b))
+    print(f"\n[e2e index mismatches, configs[1] shape, fp32] per image {mism} of {kept_ref} kept")
+    assert sum(mism) <= max(1, int(0.01 * sum(kept_ref)))
+    # scores-only launch (what the bench times) == the logits launch
+    pipe2 = HeadPipeline(b, shapes, classes, HeadConfig(precision="fp32"), device=cuda_device)
+    pipe2.set_vocabulary(inp.text.to(cuda_device))
+    pipe2.run(objs, preds)
+    torch.cuda.synchronize()
+    assert pipe2.last_path == "fused_fp32" and torch.equal(pipe2.scores, pipe.scores)
 
 
 def test_full_size_properties(ov, cuda_device):
@@ -872,7 +934,9 @@ def test_vocab_parallel_across_gpus(ov, cuda_device):
 
 
 def test_vocab_parallel_wait_is_bounded(ov, cuda_device):
-    """A rank whose peer never signals does not hang the GPU: the wait expires and is reported."""
+    """A rank whose peer never signals does not hang the GPU: the wait expires, is reported, the
+    step carries NO detections (sentinel scores, nothing unpacked, key arrays not handed back), the
+    condition is sticky, the next run() raises, and reset() re-arms the exchange."""
     from ovdet import synth
     from ovdet.pipeline import HeadConfig
     shapes = [(32, 32), (16, 16), (8, 8)]
@@ -881,12 +945,36 @@ def test_vocab_parallel_wait_is_bounded(ov, cuda_device):
     try:
         for h in heads:
             h.set_vocabulary(x.text)
-            h.timeout_ms = 20
+            h.timeout_ms = h.first_timeout_ms = 20
         heads[0].similarity(x.obj_embeds)
         heads[0].signal()                       # rank 1 never contributes
         heads[0].merge()
+        res = heads[0].finish(x.box_preds)
         torch.cuda.synchronize()
         assert heads[0].timed_out()
+        assert bool(torch.isneginf(heads[0].scores).all()) and int(res.count.sum()) == 0
+        with pytest.raises(RuntimeError, match="did not signal"):
+            heads[0].run(x.obj_embeds, x.box_preds)
+        # sticky: a second merge without a reset unpacks nothing either, even with every flag present
+        heads[1].similarity(x.obj_embeds)
+        heads[1].signal()
+        heads[0].merge()
+        torch.cuda.synchronize()
+        assert bool(torch.isneginf(heads[0].scores).all())
+        for h in heads:
+            h.reset()
+        assert not heads[0].timed_out()
+        for h in heads:
+            h.similarity(x.obj_embeds)
+        for h in heads:
+            h.signal()
+        for h in heads:
+            h.merge()
+            r = h.finish(x.box_preds)
+        torch.cuda.synchronize()
+        assert not heads[0].timed_out() and not heads[1].timed_out()
+        assert torch.equal(heads[0].scores, heads[1].scores) and bool(torch.isfinite(heads[0].scores).all())
+        assert int(r.count.sum()) > 0
     finally:
         for h in heads:
             h.close()
@@ -1256,8 +1344,14 @@ def test_small_launch_class_split(ov, cuda_device, batch, classes):
         assert torch.equal(pipe.scores, want_s)
         assert (pipe.class_ids != want_c).sum().item() <= 2             # exact ties after the affine map only
         assert torch.equal(pipe.result.count, want_n)
-    if getattr(pipe, "_sim_ws", None) is not None:
-        assert int(pipe._sim_ws.sum()) == 0 or True                     # counters are reset by the merging warp
+    if batch == 1:
+        # the split must actually be in use at batch 1, and the contract of ovdet_similarity_fused_ws -
+        # "arrival counters zero on entry, left zero" - holds: the counter block heads the workspace
+        ws = getattr(pipe, "_sim_ws", None)
+        assert ws is not None and ws.numel() > 0
+        tiles = sum((h * w + 127) // 128 for h, w in shapes) * batch
+        counters = ws[:(tiles + 2) * 16].view(torch.int32)
+        assert int(counters.abs().sum()) == 0
 
 
 def test_decode_bf16_box_logits(ov, cuda_device):
