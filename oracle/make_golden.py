@@ -308,17 +308,22 @@ def full_forward_case():
     model.box_head = BoxHead(in_channels=in_ch, hidden_dim=16)
     model.eval()
     model.offline_vocabulary = torch.randn(len(names), 512)
-    # a random-init network collapses to nearly constant features (scores 1e-8 apart): give every
-    # BatchNorm of the model non-trivial statistics so that anchors differ
-    for mod in [model]:
-        for m in mod.modules():
-            if isinstance(m, torch.nn.BatchNorm2d):
-                m.running_mean.normal_(0, 0.3)
-                m.running_var.uniform_(0.05, 0.3)
-                m.weight.data.uniform_(0.8, 2.0)
-                m.bias.data.normal_(0, 0.5)
-            elif isinstance(m, torch.nn.Conv2d) and m.bias is not None:
-                m.bias.data.normal_(0, 0.1)
+    # A random-init network either collapses to nearly constant features (scores 1e-8 apart) or, with
+    # arbitrary BatchNorm statistics, explodes (activations 1e8).  Give every BatchNorm a random affine
+    # part and CALIBRATE its running statistics on seeded inputs (train-mode passes), so that every
+    # layer's activations are O(1) and anchors differ.
+    for m in model.modules():
+        if isinstance(m, torch.nn.BatchNorm2d):
+            m.weight.data.uniform_(0.7, 1.3)
+            m.bias.data.normal_(0, 0.3)
+            m.momentum = 0.2
+        elif isinstance(m, torch.nn.Conv2d) and m.bias is not None:
+            m.bias.data.normal_(0, 0.1)
+    model.train()
+    with torch.no_grad():
+        for _ in range(40):
+            model(torch.rand(4, 3, 64, 64).round())
+    model.eval()
     for branch in model.box_head.box_convs:          # boxes of a few cells instead of exp(8) * stride
         bias = branch[2].bias.data.view(4, 17)
         k = torch.arange(17.0)
