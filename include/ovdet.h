@@ -80,7 +80,9 @@ OVDET_API int ovdet_l2norm_regions(const float* x, int64_t batch, int64_t dim, i
  *
  *   t         fp32 [batch, classes, dim]; element (b,c,d) at t[b*stride_b + c*stride_c + d].
  *             Pass batch=1 for a shared vocabulary (stride-0 expand, model/yolo_clip.py:123).
- *   operand   bf16 [batch, classes, kop], NORMALISED rows t/max(||t||,1e-12); hi/lo as above.
+ *   operand   bf16 [batch, classes, kop], NORMALISED rows t/max(||t||,1e-12); split = 0: kop = dim;
+ *             split = 1: [hi | lo], kop = 2*dim (ovdet_similarity, split recipe); split = 2:
+ *             [hi | lo | hi], kop = 3*dim (the operand of ovdet_similarity_fused_fp32).
  *   inv_norm  optional fp32 [batch, classes] (diagnostics), may be NULL.
  */
 OVDET_API int ovdet_l2norm_text(const float* t, int64_t batch, int64_t classes, int64_t dim,

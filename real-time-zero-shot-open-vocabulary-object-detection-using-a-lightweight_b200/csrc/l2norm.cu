@@ -96,7 +96,9 @@ l2norm_regions_kernel(const float* __restrict__ x, int dim, int hw, int64_t stri
 // ---------------------------------------------------------------------------------------------
 // Text.  One warp per prompt; rows are tiny (D floats) so the second pass re-reads L1/L2.
 // ---------------------------------------------------------------------------------------------
-template <bool SPLIT>
+// SEG 1: [hi]; 2: [hi | lo] (the two-kernel fp32 recipe); 3: [hi | lo | hi], the operand the fused
+// kernel's three-pass mode multiplies against activation blocks laid out [hi | hi | lo].
+template <int SEG>
 __global__ void __launch_bounds__(256)
 l2norm_text_kernel(const float* __restrict__ t, int64_t total_rows, int classes, int dim,
                    int64_t stride_b, int64_t stride_c, __nv_bfloat16* __restrict__ operand,
@@ -117,7 +119,8 @@ l2norm_text_kernel(const float* __restrict__ t, int64_t total_rows, int classes,
     const float f = __fdiv_rn(src[i], denom);
     const __nv_bfloat16 h = __float2bfloat16_rn(f);
     dst[i] = h;
-    if (SPLIT) dst[dim + i] = __float2bfloat16_rn(f - __bfloat162float(h));
+    if (SEG >= 2) dst[dim + i] = __float2bfloat16_rn(f - __bfloat162float(h));
+    if (SEG == 3) dst[2 * dim + i] = h;
   }
 }
 
@@ -188,18 +191,21 @@ extern "C" int ovdet_l2norm_text(const float* t, int64_t batch, int64_t classes,
   using namespace ovdet;
   if (!t || !operand || batch < 0 || classes < 0 || dim <= 0) return OVDET_ERR_INVALID_ARG;
   if (dim % 64 != 0) return OVDET_ERR_UNSUPPORTED_SHAPE;
-  if (kop != dim * (split ? 2 : 1)) return OVDET_ERR_INVALID_ARG;
+  if (split < 0 || split > 2 || kop != dim * (split + 1)) return OVDET_ERR_INVALID_ARG;
   if (int rc = check_device()) return rc;
   const int64_t total = batch * classes;
   if (total == 0) return OVDET_OK;
   auto* op = static_cast<__nv_bfloat16*>(operand);
   const unsigned grid = (unsigned)ceil_div<int64_t>(total, 8);
-  if (split)
-    l2norm_text_kernel<true><<<grid, 256, 0, as_stream(stream)>>>(t, total, (int)classes, (int)dim,
-                                                                  stride_b, stride_c, op, (int)kop, inv_norm);
+  if (split == 2)
+    l2norm_text_kernel<3><<<grid, 256, 0, as_stream(stream)>>>(t, total, (int)classes, (int)dim,
+                                                               stride_b, stride_c, op, (int)kop, inv_norm);
+  else if (split == 1)
+    l2norm_text_kernel<2><<<grid, 256, 0, as_stream(stream)>>>(t, total, (int)classes, (int)dim,
+                                                               stride_b, stride_c, op, (int)kop, inv_norm);
   else
-    l2norm_text_kernel<false><<<grid, 256, 0, as_stream(stream)>>>(t, total, (int)classes, (int)dim,
-                                                                   stride_b, stride_c, op, (int)kop, inv_norm);
+    l2norm_text_kernel<1><<<grid, 256, 0, as_stream(stream)>>>(t, total, (int)classes, (int)dim,
+                                                               stride_b, stride_c, op, (int)kop, inv_norm);
   OVDET_LAUNCH_CHECK();
   return OVDET_OK;
 }

@@ -221,11 +221,14 @@ class Detector:
             lo, hi = i * chunk, (i + 1) * chunk
             objs, boxes = st["stage"][i & 1]
             if orig_sizes is not None:
-                with torch.cuda.stream(comp_s):
-                    pipe.set_geometry(orig_sizes[lo:hi], scale_factors[lo:hi] if scale_factors is not None
-                                      else [1.0] * chunk)
+                geo = (tuple(orig_sizes[lo:hi]), tuple(scale_factors[lo:hi]) if scale_factors is not None else None)
+                if geo != st.get("geo"):          # unchanged geometry (fixed-size serving) is not re-uploaded
+                    with torch.cuda.stream(comp_s):
+                        pipe.set_geometry(geo[0], geo[1] if geo[1] is not None else [1.0] * chunk)
+                    st["geo"] = geo
             else:
                 pipe.clear_geometry()
+                st["geo"] = None
             with torch.cuda.stream(copy_s):
                 if freed[i & 1] is not None:
                     copy_s.wait_event(freed[i & 1])

@@ -75,11 +75,12 @@ def shared_text(text: torch.Tensor) -> bool:
     return text.dim() == 2 or text.shape[0] == 1 or text.stride(0) == 0
 
 
-def l2norm_text(text: torch.Tensor, split: bool = False,
+def l2norm_text(text: torch.Tensor, split=False,
                 operand: Optional[torch.Tensor] = None) -> torch.Tensor:
     """text_contrastive.py:138.  ``text`` is ``[C, D]`` or ``[B, C, D]`` (any batch / row stride,
     as the neck emits it); a shared vocabulary is normalised once.  Returns the normalised
-    bf16 operand ``[Bt, C, kop]`` with Bt = 1 for a shared vocabulary."""
+    bf16 operand ``[Bt, C, kop]`` with Bt = 1 for a shared vocabulary.  ``split``: False ``[hi]``,
+    True ``[hi | lo]`` (two-kernel fp32 recipe), ``3`` ``[hi | lo | hi]`` (fused fp32-accurate mode)."""
     _require_cuda(text, "text_embed", torch.float32)
     if text.dim() == 2:
         text = text.unsqueeze(0)
@@ -88,13 +89,14 @@ def l2norm_text(text: torch.Tensor, split: bool = False,
     if text.stride(2) != 1:
         text = text.contiguous()
     bt, classes, dim = text.shape
-    kop = dim * (2 if split else 1)
+    mode = 2 if split == 3 else int(bool(split))
+    kop = dim * (mode + 1)
     if operand is None:
         operand = torch.empty(bt, classes, kop, device=text.device, dtype=torch.bfloat16)
     assert operand.shape == (bt, classes, kop) and operand.is_contiguous()
     with torch.cuda.device(text.device):
         check(lib().ovdet_l2norm_text(text.data_ptr(), bt, classes, dim, text.stride(0),
-                                      text.stride(1), operand.data_ptr(), kop, int(split), None,
+                                      text.stride(1), operand.data_ptr(), kop, mode, None,
                                       _stream(text)), "ovdet_l2norm_text")
     return operand
 
@@ -163,10 +165,8 @@ def fused_supported(obj_embeds: Sequence[torch.Tensor]) -> bool:
 
 def text_operand_fp32(text: torch.Tensor) -> torch.Tensor:
     """Unit-norm text rows as the ``[hi | lo | hi]`` bf16 operand of ``similarity_fused(fp32=True)``
-    (built from the K1b kernel's ``[hi | lo]`` output; once per vocabulary)."""
-    op = l2norm_text(text, split=True)
-    dim = op.shape[-1] // 2
-    return torch.cat([op, op[..., :dim]], dim=-1).contiguous()
+    (one K1b launch)."""
+    return l2norm_text(text, split=3)
 
 
 def fused_fp32_supported(obj_embeds: Sequence[torch.Tensor], classes: int) -> bool:

@@ -110,6 +110,7 @@ class HeadPipeline:
         self.use_geometry = False
         self._vocab_ready = False
         self.last_path = None              # "fused" | "split": what the previous run() launched
+        self.last_single_call = False      # the previous run() was ONE C call (ovdet_head_step)
         self._step_args = None             # ovdet_head_step_args, filled on first use
         self._parallel_decode = False      # set by capture(): decode forked beside the similarity kernel
         self._side = None
@@ -125,7 +126,7 @@ class HeadPipeline:
         else:
             ops.l2norm_text(text, split=self.split, operand=self.text_op)
             if self.want_fused_fp32:
-                self.text_op3 = torch.cat([self.text_op, self.text_op[..., :self.cfg.embed_dim]], dim=-1).contiguous()
+                self.text_op3 = ops.l2norm_text(text, split=3, operand=self.text_op3)
         self._vocab_ready = True
 
     def set_geometry(self, orig_sizes: Sequence[Tuple[int, int]], scale_factors: Sequence[float]) -> None:
@@ -188,6 +189,7 @@ class HeadPipeline:
                     events[name][1] = ev
 
         self._fork = None
+        self.last_single_call = False
         if self._parallel_decode:
             # fork: decode needs nothing from the similarity kernel once K4 owns the threshold
             main = torch.cuda.current_stream(self.device)
@@ -213,9 +215,10 @@ class HeadPipeline:
                                               dtype=torch.bfloat16)
             ops.l2norm_regions(obj_embeds, split=self.split, operand=self.regions_op, inv_norm=self.inv_norm)
         if self.per_image_text:
-            ops.l2norm_text(text, split=self.split, operand=self.text_op)
-            if fused32:
-                self.text_op3 = torch.cat([self.text_op, self.text_op[..., :cfg.embed_dim]], dim=-1).contiguous()
+            if fused32:         # one K1b launch straight into the [hi | lo | hi] operand, no ATen op in the step
+                self.text_op3 = ops.l2norm_text(text, split=3, operand=self.text_op3)
+            else:
+                ops.l2norm_text(text, split=self.split, operand=self.text_op)
         elif text is not None:
             self.set_vocabulary(text)
         elif not self._vocab_ready:
@@ -255,6 +258,7 @@ class HeadPipeline:
             raise RuntimeError("ovdet: no vocabulary set (call set_vocabulary or pass text)")
         a = self._fill_step_args(obj_embeds, box_preds)
         self.last_path = "fused"
+        self.last_single_call = True
         with torch.cuda.device(self.device):
             _cabi.check(_cabi.lib().ovdet_head_step(ctypes.byref(a),
                                                     torch.cuda.current_stream(self.device).cuda_stream),
