@@ -17,8 +17,25 @@ from typing import Dict, Optional, Sequence, Tuple
 import torch
 
 import ctypes
+import os
 
 from . import _cabi, ops
+
+# NVTX ranges ("tracing / profiling"): one range per step and, on the per-stage
+# launch path, one per kernel stage - what nsys / ncu --nvtx group by.  OVDET_NVTX=0 removes them.
+_NVTX = os.environ.get("OVDET_NVTX", "1") != "0"
+_STAGE_NAMES = {"l2norm": "ovdet.K1 l2norm", "similarity": "ovdet.K2 similarity", "decode": "ovdet.K3 decode",
+                "nms": "ovdet.K4 nms"}
+
+
+def _nvtx_push(name: str) -> None:
+    if _NVTX:
+        torch.cuda.nvtx.range_push(name)
+
+
+def _nvtx_pop() -> None:
+    if _NVTX:
+        torch.cuda.nvtx.range_pop()
 
 
 @dataclass(frozen=True)
@@ -176,10 +193,21 @@ class HeadPipeline:
             text: Optional[torch.Tensor] = None, events: Optional[dict] = None) -> ops.NmsResult:
         """One pass of the hot path.  ``events`` (optional dict) receives a pair of CUDA events
         per stage, recorded on the launching stream, for per-kernel timing."""
+        _nvtx_push("ovdet.head_step")
+        try:
+            return self._run(obj_embeds, box_preds, text, events)
+        finally:
+            _nvtx_pop()
+
+    def _run(self, obj_embeds, box_preds, text, events) -> ops.NmsResult:
         cfg = self.cfg
         self.check_inputs(obj_embeds, box_preds, text)
 
         def mark(name, begin):
+            if begin:
+                _nvtx_push(_STAGE_NAMES.get(name, name))
+            else:
+                _nvtx_pop()
             if events is not None:
                 ev = torch.cuda.Event(enable_timing=True)
                 ev.record()

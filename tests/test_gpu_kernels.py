@@ -462,6 +462,58 @@ def test_full_size_properties(ov, cuda_device):
         assert again.anchor[i, :k].tolist() == list(range(k))
 
 
+@pytest.mark.parametrize("precision,classes", [("bf16", 1203), ("fp32", 80), ("fp32", 1203)])
+def test_per_image_text_bench_shape_vs_oracle(ov, cuda_device, precision, classes):
+    """The reference's real forward hands the head PER-IMAGE text [B, C, D] whose batch is not the
+    outer memory dimension (the neck's I-Pooling output, repvl_pan.py:173-182, strides (D, B*D, 1);
+    yolo_clip.py:171,182): the batched similarity at the bench's per-image shape (640^2, three images
+    so that a CTA pair never straddles two images' text) against the oracle, K1b normalising B*C rows
+    inside the step."""
+    from ovdet import synth
+    from ovdet.pipeline import HeadConfig, HeadPipeline
+    b, s = 3, 640
+    inp = synth.make_inputs(batch=b, image_size=s, num_classes=classes, seed=23)
+    g = torch.Generator().manual_seed(5)
+    text = (inp.text.unsqueeze(1) + 0.05 * torch.randn(classes, b, 512, generator=g)).transpose(0, 1)   # [B, C, D]
+    assert text.stride() == (512, b * 512, 1) and not torch.equal(text[0], text[1])
+    tail = ref_port.head_tail(inp.obj_embeds, text, inp.box_preds)
+    shapes = [(s // 8, s // 8), (s // 16, s // 16), (s // 32, s // 32)]
+    pipe = HeadPipeline(b, shapes, classes, HeadConfig(precision=precision), device=cuda_device, per_image_text=True)
+    sizes = [(s, s)] * b
+    pipe.set_geometry(sizes, [1.0] * b)
+    text_dev = torch.empty(classes, b, 512, device=cuda_device).transpose(0, 1)
+    text_dev.copy_(text)
+    assert text_dev.stride() == (512, b * 512, 1)
+    objs = [e.to(cuda_device) for e in inp.obj_embeds]
+    preds = [p.to(cuda_device) for p in inp.box_preds]
+    res = pipe.run(objs, preds, text=text_dev)
+    torch.cuda.synchronize()
+    if precision == "bf16":
+        assert pipe.last_path == "fused" and pipe.last_single_call
+    elif classes <= 128:
+        assert pipe.last_path == "fused_fp32"
+    assert_logits_close(pipe.scores, tail["scores"], precision)
+    agree = (pipe.class_ids.cpu().long() == tail["class_ids"]).float().mean()
+    assert agree >= (0.999 if precision == "fp32" else 0.97)
+    torch.testing.assert_close(pipe.boxes.cpu(), tail["boxes"], rtol=1e-4, atol=1e-3)
+    fed = {"boxes": pipe.boxes.cpu(), "scores": pipe.scores.cpu(), "class_ids": pipe.class_ids.cpu().long()}
+    want = ref_port.postprocess_batch(fed, sizes, [1.0] * b)
+    for i in range(b):
+        k = int(res.count[i])
+        assert k == len(want[i]["keep"]) and k > 20
+        np.testing.assert_array_equal(res.keep[i, :k].cpu().numpy(), want[i]["keep"])
+        np.testing.assert_array_equal(res.boxes[i, :k].cpu().numpy(), want[i]["boxes"])
+    mism, kept_ref = _index_mismatches(res, ref_port.postprocess_batch(tail, sizes, [1.0] * b))
+    print(f"\n[e2e index mismatches, per-image text, {precision}, C={classes}] per image {mism} of {kept_ref} kept")
+    assert sum(mism) <= max(1, int((0.01 if precision == "fp32" else 0.15) * sum(kept_ref)))
+    # the per-stage launch sequence gives the same bytes as the single C call
+    if precision == "bf16":
+        scores = pipe.scores.clone()
+        pipe.run(objs, preds, text=text_dev, events={})
+        torch.cuda.synchronize()
+        assert torch.equal(pipe.scores, scores)
+
+
 @pytest.mark.parametrize("image_size,classes", [(1280, 1203), (640, 4800)])
 def test_config4_config5_shapes_vs_oracle(ov, cuda_device, image_size, classes):
     """BASELINE configs[3] (1280^2: 33 600 anchors per image - the multi-chunk K4 path and the
