@@ -775,6 +775,70 @@ sim_fused_kernel(const __grid_constant__ LevelMaps amaps, const __grid_constant_
         };
 
         uint32_t ra[32], rb[32];
+        if constexpr (MODE == 1 && EPI2 && !PROJ) {
+          if (n_valid == F_BLOCK_N) {
+            // Hot path of the materialised-logits kernel (full tile, bf16 logits through TMA stores, two
+            // epilogue groups): straight-line over the four 32-column chunks, and - as in the scores-only
+            // hot path below - the accumulator goes back to the MMA warp as soon as its last 32 columns
+            // are in registers; the affine map, the running max / argmax, the packing and the store of
+            // that chunk run after the arrive.  The ncu source page of the generic loop showed ~215-260
+            // issued instructions per chunk against ~150 of arithmetic, on SM sub-partitions whose only
+            // eligible warps are two epilogue warps: this mode is bound by epilogue issue slots.
+            auto emit_chunk = [&](uint32_t (&r)[32], int c) {
+              const int col = n0 + (c << 5);
+#pragma unroll
+              for (int j = 0; j < 32; ++j) r[j] = __float_as_uint(fmaf(scale, __uint_as_float(r[j]), beta));
+              if (want_max) {
+#pragma unroll
+                for (int j = 0; j < 32; ++j) {
+                  const float v = __uint_as_float(r[j]);
+                  const float old = bv[j & 3];
+                  bv[j & 3] = fmaxf(old, v);
+                  if (v > old) bi[j & 3] = col + j;
+                }
+              }
+              if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+              __syncwarp();
+              const uint32_t rowaddr = stage_u32 + lane * 64u;
+              const uint32_t sw = (lane >> 1) & 3u;
+#pragma unroll
+              for (int v = 0; v < 4; ++v)
+                asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::
+                    "r"(rowaddr + (((uint32_t)v ^ sw) << 4)),
+                    "r"(pack_bf16x2(__uint_as_float(r[8 * v + 0]), __uint_as_float(r[8 * v + 1]))),
+                    "r"(pack_bf16x2(__uint_as_float(r[8 * v + 2]), __uint_as_float(r[8 * v + 3]))),
+                    "r"(pack_bf16x2(__uint_as_float(r[8 * v + 4]), __uint_as_float(r[8 * v + 5]))),
+                    "r"(pack_bf16x2(__uint_as_float(r[8 * v + 6]), __uint_as_float(r[8 * v + 7]))) : "memory");
+              asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+              __syncwarp();
+              if (lane == 0 && tc.rows > lg * 32) {
+                asm volatile(
+                    "cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%1, %2, %3}], [%4];"
+                    :: "l"(&cmaps.m[tc.level]), "r"(col), "r"(tc.m0 + lg * 32), "r"(tc.b), "r"(stage_u32) : "memory");
+                asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+              }
+            };
+            ptx::tmem_ld_32x32(t_row, ra);
+            ptx::tmem_ld_wait();
+            ptx::tmem_ld_32x32(t_row + 32u, rb);
+            emit_chunk(ra, 0);
+            ptx::tmem_ld_wait();
+            ptx::tmem_ld_32x32(t_row + 64u, ra);
+            emit_chunk(rb, 1);
+            ptx::tmem_ld_wait();
+            ptx::tmem_ld_32x32(t_row + 96u, rb);
+            emit_chunk(ra, 2);
+            ptx::tmem_ld_wait();
+            ptx::tc_fence_before();
+            __syncwarp();
+            if (lane == 0) {
+              if constexpr (CG == 2) ptx::mbar_arrive_cluster(lead_t_empty0 + 8u * as);
+              else ptx::mbar_arrive(t_empty0 + 8u * as);
+            }
+            emit_chunk(rb, 3);
+            continue;
+          }
+        }
         if (raw_mode && n_valid == F_BLOCK_N) {
           // Hot path (full tile, no logits): straight-line, and the accumulator is handed back to
           // the MMA warp as soon as its last 32 columns are in registers - the compare work on
