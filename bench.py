@@ -70,6 +70,8 @@ def static_config(args, n_gpus):
     return {"workload": workload_name(batch) + (PROJECTED_NOTE if args.projected else ""),
             "global_batch": batch * n_gpus, "anchors": anchors, "classes": NUM_CLASSES, "embed_dim": EMBED_DIM,
             "precision": ("bf16 operands, fp32 accumulate, fused class max/argmax" if args.precision == "bf16"
+                          else "fp16 operands (per-row power-of-two scaling), fp32 accumulate, |dlogit| <~ 1e-4"
+                          if args.precision == "fp16"
                           else "three bf16 passes over hi/lo operand halves (|dlogit| ~ 1e-5), fp32 accumulate"),
             "text": ("per-image [B, C, 512], strides (512, B*512, 1) as the neck emits it, normalised every step"
                      if args.per_image_text else "shared vocabulary [C, 512], re-normalised every step"),
@@ -528,7 +530,7 @@ def run_ours(args):
                       "note": "kept anchor sets: device path vs oracle scores -> oracle NMS on the first images of "
                               "this run's batch (symmetric difference); differences need two overlapping "
                               "candidates whose scores are closer than the similarity error "
-                              f"({'~1e-5' if args.precision == 'fp32' else '<= 4e-3, bf16'})"}
+                              f"({{'fp32': '~1e-5', 'fp16': '<= 1e-4, fp16', 'bf16': '<= 4e-3, bf16'}}[args.precision])"}
         step()
         t0 = time.perf_counter()
         reps = 0
@@ -548,9 +550,13 @@ def run_ours(args):
         fused = timed_path in ("fused", "fused_fp32")
         k1b = 0 if proj or (step_text is None) else 1                          # text rows, every step
         launches = (3 if (fused or proj) else len(shapes) + 3) + k1b
+        if args.precision == "fp16" and fused:
+            timed_path = "fused_fp16"
         kernel = ("sim_fused_kernel, projected mode (1x1 projection folded: hidden fp32 NCHW in, quadratic-form "
                   "norm, tcgen05 GEMM K = 272, class max/argmax)" if proj else
                   "sim_fused_kernel, fp32-accurate three-pass mode" if timed_path == "fused_fp32" else
+                  "sim_fused_kernel, fp16 operand tier (K1+K2: fp32 NCHW in, row scaling, L2 norm, tcgen05 GEMM, class "
+                  "max/argmax)" if timed_path == "fused_fp16" else
                   "sim_fused_kernel (K1+K2: fp32 NCHW in, L2 norm, tcgen05 GEMM, class max/argmax)" if fused
                   else "sim_gemm_kernel (K2)")
         if proj:
@@ -603,7 +609,8 @@ def run_ours(args):
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": n_gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": elapsed_ms / args.steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None,
-            "dtype": "bf16" if args.precision == "bf16" else "bf16x3 (fp32-accurate hi/lo split)", "data": "synthetic",
+            "dtype": {"bf16": "bf16", "fp16": "fp16", "fp32": "bf16x3 (fp32-accurate hi/lo split)"}[args.precision],
+            "data": "synthetic",
             "config": static_config(args, n_gpus),
             "observed": {"path": timed_path, "timed_through": "ovdet_head_step (one C call, PDL)" if single_call
                          else "per-stage C calls", "mean_candidates_per_image": cand, "mean_kept_per_image": kept,
@@ -765,8 +772,9 @@ def main():
     ap.add_argument("--logits", default="none", choices=["none", "bf16", "fp32"],
                     help="also materialise the [B, A, C] logits (the reference's compute_similarity output); "
                          "default: class max/argmax fused in the GEMM epilogue only")
-    ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"],
-                    help="bf16 = the metric's configuration; fp32 = three-pass hi/lo recipe (BASELINE configs[1])")
+    ap.add_argument("--precision", default="bf16", choices=["bf16", "fp16", "fp32"],
+                    help="bf16 = the metric's configuration; fp16 = one pass with fp16 operands (|dlogit| <~ 1e-4, same "
+                         "tensor rate); fp32 = three-pass hi/lo recipe (BASELINE configs[1])")
     ap.add_argument("--image-size", type=int, default=IMAGE_SIZE,
                     help="default 640 (the metric's configuration); 1280 = BASELINE configs[3]")
     ap.add_argument("--classes", type=int, default=NUM_CLASSES,

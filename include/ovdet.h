@@ -82,7 +82,8 @@ OVDET_API int ovdet_l2norm_regions(const float* x, int64_t batch, int64_t dim, i
  *             Pass batch=1 for a shared vocabulary (stride-0 expand, model/yolo_clip.py:123).
  *   operand   bf16 [batch, classes, kop], NORMALISED rows t/max(||t||,1e-12); split = 0: kop = dim;
  *             split = 1: [hi | lo], kop = 2*dim (ovdet_similarity, split recipe); split = 2:
- *             [hi | lo | hi], kop = 3*dim (the operand of ovdet_similarity_fused_fp32).
+ *             [hi | lo | hi], kop = 3*dim (the operand of ovdet_similarity_fused_fp32); split = 3:
+ *             one FP16 segment holding 16 x the unit row, kop = dim (ovdet_similarity_fused_fp16).
  *   inv_norm  optional fp32 [batch, classes] (diagnostics), may be NULL.
  */
 OVDET_API int ovdet_l2norm_text(const float* t, int64_t batch, int64_t classes, int64_t dim,
@@ -179,6 +180,22 @@ OVDET_API int ovdet_similarity_fused_fp32(const float* const* obj_embeds, const 
                                           const int64_t* stride_b, const int64_t* stride_d,
                                           int num_levels, int64_t batch, int64_t dim,
                                           const void* text_op3, int64_t classes, int text_batched,
+                                          float alpha, float beta, void* logits, int logits_dtype,
+                                          int64_t ldc, float* row_max, int32_t* row_arg,
+                                          float* inv_norm, void* stream);
+
+/* The same kernel with FP16 tensor-core operands instead of bf16 (the "fp16" precision tier): one
+ * pass at the bf16 rate, 11-bit significands: |dlogit| ~ 1e-5 (max ~6e-5) at unit-norm scale against
+ * ~4e-3 for bf16 and ~3e-5 for the three-pass fp32-accurate mode.  Every anchor row is scaled by a
+ * power of two taken from its first 64 channels before the fp16 rounding (cosine similarity is
+ * scale-invariant), so activations of any magnitude are accepted; a row whose later channels exceed
+ * 8000 x the largest of its first 64 saturates at +-65504.  dim must be 512, fp32 activations.
+ *   text_op16  fp16 [text_batch, classes, dim] from ovdet_l2norm_text(split = 3)
+ * Other arguments as ovdet_similarity_fused. */
+OVDET_API int ovdet_similarity_fused_fp16(const float* const* obj_embeds, const int64_t* hw,
+                                          const int64_t* stride_b, const int64_t* stride_d,
+                                          int num_levels, int64_t batch, int64_t dim,
+                                          const void* text_op16, int64_t classes, int text_batched,
                                           float alpha, float beta, void* logits, int logits_dtype,
                                           int64_t ldc, float* row_max, int32_t* row_arg,
                                           float* inv_norm, void* stream);
@@ -369,7 +386,7 @@ typedef struct ovdet_head_step_args {
   const void* box_preds[4];        /* fp32 or bf16 (box_dtype) [batch, 4 * bins, h, w] per level */
   int32_t heights[4], widths[4], strides[4];
   int64_t emb_stride_b[4], emb_stride_d[4], box_stride_b[4];
-  const void* text_op;             /* bf16 [text_batch, classes, dim], unit-norm rows */
+  const void* text_op;             /* bf16 [text_batch, classes, dim], unit-norm rows (fp16 x 16 with text_fp16) */
   int32_t text_batched;
   int32_t activation;              /* ovdet_activation */
   int32_t class_aware, topk;
@@ -390,6 +407,10 @@ typedef struct ovdet_head_step_args {
   void* workspace; size_t workspace_bytes;           /* K4: ovdet_nms_workspace_bytes */
   void* sim_workspace; size_t sim_workspace_bytes;   /* optional, ZEROED once by the caller:
                                                         ovdet_similarity_split_workspace_bytes */
+  int32_t text_fp16;               /* 1: text_op is the fp16 operand of ovdet_l2norm_text(split = 3) and the
+                                      similarity runs with fp16 tensor-core operands (ovdet_similarity_fused_fp16);
+                                      fp32 activations, dim = 512 */
+  int32_t reserved;
 } ovdet_head_step_args;
 
 OVDET_API int ovdet_head_step(const ovdet_head_step_args* args, void* stream);

@@ -36,6 +36,7 @@ class HeadStepArgs(ctypes.Structure):
         ("out_anchor", c_void_p), ("out_keep", c_void_p), ("out_count", c_void_p),
         ("out_candidates", c_void_p), ("workspace", c_void_p), ("workspace_bytes", c_size_t),
         ("sim_workspace", c_void_p), ("sim_workspace_bytes", c_size_t),
+        ("text_fp16", c_int32), ("reserved", c_int32),
     ]
 
 
@@ -66,6 +67,10 @@ PROTOTYPES = {
                                               c_int, c_float, c_float, c_void_p, c_int, c_int64,
                                               c_void_p, c_void_p, c_void_p, c_void_p]),
     "ovdet_similarity_fused_fp32": (c_int, [POINTER(c_void_p), POINTER(c_int64), POINTER(c_int64),
+                                            POINTER(c_int64), c_int, c_int64, c_int64, c_void_p, c_int64,
+                                            c_int, c_float, c_float, c_void_p, c_int, c_int64,
+                                            c_void_p, c_void_p, c_void_p, c_void_p]),
+    "ovdet_similarity_fused_fp16": (c_int, [POINTER(c_void_p), POINTER(c_int64), POINTER(c_int64),
                                             POINTER(c_int64), c_int, c_int64, c_int64, c_void_p, c_int64,
                                             c_int, c_float, c_float, c_void_p, c_int, c_int64,
                                             c_void_p, c_void_p, c_void_p, c_void_p]),

@@ -63,7 +63,7 @@ int fused_launch(const float* const* obj_embeds, const int64_t* hw, const int64_
                  int normalize, int split3, float alpha, float beta, void* logits, int logits_dtype,
                  int64_t ldc, float* row_max, int32_t* row_arg, float* inv_norm, void* stream,
                  int in_bf16 = 0, void* split_ws = nullptr, size_t split_ws_bytes = 0,
-                 const VpTarget* vp = nullptr);
+                 const VpTarget* vp = nullptr, int f16_operands = 0);
 
 inline cudaStream_t as_stream(void* s) { return reinterpret_cast<cudaStream_t>(s); }
 
@@ -92,6 +92,13 @@ __device__ __forceinline__ uint4 ld_stream_u32x4(const uint4* p) {
 __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
   __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);   // .x = lo (low 16 bits), .y = hi
   return *reinterpret_cast<uint32_t*>(&v);
+}
+
+// two floats -> packed fp16 pair (.x = lo in the low 16 bits), round to nearest, finite saturation
+__device__ __forceinline__ uint32_t pack_f16x2_sat(float lo, float hi) {
+  uint32_t v;
+  asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(v) : "f"(hi), "f"(lo));
+  return v;
 }
 
 // float -> uint32 whose unsigned order equals the float order (-inf < ... < +inf).

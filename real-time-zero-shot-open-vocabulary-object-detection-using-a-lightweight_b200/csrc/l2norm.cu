@@ -7,6 +7,7 @@
 //            write fp32 inv_norm [B, A]
 //   text:    one warp per prompt row, normalised before rounding.
 #include "common.cuh"
+#include <cuda_fp16.h>
 
 namespace ovdet {
 
@@ -98,6 +99,9 @@ l2norm_regions_kernel(const float* __restrict__ x, int dim, int hw, int64_t stri
 // ---------------------------------------------------------------------------------------------
 // SEG 1: [hi]; 2: [hi | lo] (the two-kernel fp32 recipe); 3: [hi | lo | hi], the operand the fused
 // kernel's three-pass mode multiplies against activation blocks laid out [hi | hi | lo].
+// SEG 0: ONE fp16 segment holding 16 x the unit row (the fused kernel's fp16 tier: fp16 keeps 11
+// significant bits down to 6e-5, so the unit rows - typical element 0.04 - are lifted by 2^4; the
+// factor comes back out in the kernel's row scale).
 template <int SEG>
 __global__ void __launch_bounds__(256)
 l2norm_text_kernel(const float* __restrict__ t, int64_t total_rows, int classes, int dim,
@@ -117,6 +121,10 @@ l2norm_text_kernel(const float* __restrict__ t, int64_t total_rows, int classes,
   __nv_bfloat16* dst = operand + row * kop;
   for (int i = lane; i < dim; i += 32) {
     const float f = __fdiv_rn(src[i], denom);
+    if (SEG == 0) {
+      reinterpret_cast<__half*>(dst)[i] = __float2half_rn(f * 16.0f);
+      continue;
+    }
     const __nv_bfloat16 h = __float2bfloat16_rn(f);
     dst[i] = h;
     if (SEG >= 2) dst[dim + i] = __float2bfloat16_rn(f - __bfloat162float(h));
@@ -191,13 +199,16 @@ extern "C" int ovdet_l2norm_text(const float* t, int64_t batch, int64_t classes,
   using namespace ovdet;
   if (!t || !operand || batch < 0 || classes < 0 || dim <= 0) return OVDET_ERR_INVALID_ARG;
   if (dim % 64 != 0) return OVDET_ERR_UNSUPPORTED_SHAPE;
-  if (split < 0 || split > 2 || kop != dim * (split + 1)) return OVDET_ERR_INVALID_ARG;
+  if (split < 0 || split > 3 || kop != dim * (split == 3 ? 1 : split + 1)) return OVDET_ERR_INVALID_ARG;
   if (int rc = check_device()) return rc;
   const int64_t total = batch * classes;
   if (total == 0) return OVDET_OK;
   auto* op = static_cast<__nv_bfloat16*>(operand);
   const unsigned grid = (unsigned)ceil_div<int64_t>(total, 8);
-  if (split == 2)
+  if (split == 3)
+    l2norm_text_kernel<0><<<grid, 256, 0, as_stream(stream)>>>(t, total, (int)classes, (int)dim,
+                                                               stride_b, stride_c, op, (int)kop, inv_norm);
+  else if (split == 2)
     l2norm_text_kernel<3><<<grid, 256, 0, as_stream(stream)>>>(t, total, (int)classes, (int)dim,
                                                                stride_b, stride_c, op, (int)kop, inv_norm);
   else if (split == 1)

@@ -203,7 +203,15 @@ __device__ __forceinline__ TileCoord decode_tile(const FusedParams& p, int tile)
 // buffer per warp): a SECOND epilogue warpgroup (warps 12-15, 512 threads).  Group e drains the N tiles whose accumulator stage is e, so the two stages are
 // emptied concurrently; the groups' partial (max, argmax, q) of a row meet in shared memory at the
 // end of the anchor tile and group 0 emits.
-template <int KB_T, bool SPLIT3, int CG, bool PROJ, bool IN16 = false, int MODE = 0, bool EPI2 = false>
+// F16OP (the "fp16" precision tier, CTA pairs, dim = 512): both operands are fp16 instead of bf16 - the
+// same tensor rate with 11-bit significands, |dlogit| ~ 1e-5 (max ~6e-5 over 10^7 logits) against
+// ~4e-3 for bf16.  fp16 has a narrow exponent range, so every anchor row is scaled by a power of two s
+// chosen from its first 64 channels (their sampled maximum lands in [4, 8)); the sum of squares is
+// taken over the scaled values and cos = <s x, t> / ||s x|| is unchanged.  Rows whose later channels
+// exceed 8000 x that maximum saturate at +-65504 (finite).  The text operand carries the unit rows
+// times 16 (ovdet_l2norm_text, split = 3); the 1/16 goes into the row scale.
+template <int KB_T, bool SPLIT3, int CG, bool PROJ, bool IN16 = false, int MODE = 0, bool EPI2 = false,
+          bool F16OP = false>
 __global__ void __launch_bounds__(EPI2 ? F_THREADS + 128 : F_THREADS, 1)
 sim_fused_kernel(const __grid_constant__ LevelMaps amaps, const __grid_constant__ LevelMaps bmaps,
                  const __grid_constant__ LevelMaps cmaps, const FusedParams p) {
@@ -215,6 +223,7 @@ sim_fused_kernel(const __grid_constant__ LevelMaps amaps, const __grid_constant_
   static_assert(CG == 1 || KB_T > 0, "CTA pairs need a compile-time k-block count");
   static_assert(!(PROJ && SPLIT3), "the projected mode is a single bf16 pass");
   static_assert(!EPI2 || MODE != 2, "two epilogue groups: not for the key exchange");
+  static_assert(!F16OP || (!SPLIT3 && !PROJ && !IN16), "fp16 operands: the plain cosine similarity from fp32 input");
   // cluster rank: 0 = leader (issues the MMAs, owns the barriers the pair synchronises on)
   const uint32_t rank = CG == 2 ? ptx::cluster_ctarank() : 0u;
   const int pair0 = blockIdx.x / CG, pair_stride = gridDim.x / CG;
@@ -353,7 +362,8 @@ sim_fused_kernel(const __grid_constant__ LevelMaps amaps, const __grid_constant_
       const int nt_b = (w % NSPLIT) * NT / NSPLIT, nt_e = (w % NSPLIT + 1) * NT / NSPLIT;
       for (int nt = nt_b; nt < nt_e; ++nt, ++g) {
         const int n_size = ntile_nsize(nt);
-        const uint32_t idesc = ptx::umma_idesc_bf16_f32(F_BLOCK_M * CG, (uint32_t)n_size);
+        const uint32_t idesc = F16OP ? ptx::umma_idesc_f16_f32(F_BLOCK_M * CG, (uint32_t)n_size)
+                                     : ptx::umma_idesc_bf16_f32(F_BLOCK_M * CG, (uint32_t)n_size);
         const uint32_t as = g & 1u;
         const bool first_nt = nt == nt_b, last_nt = nt == nt_e - 1;
         const uint32_t it0 = g * (uint32_t)NSTAGE;
@@ -470,6 +480,7 @@ sim_fused_kernel(const __grid_constant__ LevelMaps amaps, const __grid_constant_
       (void)nt_b; (void)nt_e;
       const TileCoord tc = decode_tile(p, tile);
       float ss0 = 0.f, ss1 = 0.f, ss2 = 0.f, ss3 = 0.f;
+      float row_scale = 1.0f;                          // F16OP: power of two applied before the fp16 rounding
       // block `t` of the A region: wait until the previous tile's MMAs have read it, store, publish
       auto publish = [&](int i, const uint32_t (&regs)[32]) {
         const int t = a_slot(lt, i);
@@ -496,14 +507,26 @@ sim_fused_kernel(const __grid_constant__ LevelMaps amaps, const __grid_constant_
         };
         uint32_t packed[32];
         uint32_t packed_lo[32];                            // dead (eliminated) unless SPLIT3
+        if constexpr (F16OP) {
+          if (kb == 0) {
+            // the row's power-of-two scale from eight samples of its first block: 2^(2 - exponent of the
+            // largest), i.e. that sample lands in [4, 8); zero / denormal rows keep 1
+            float m = 0.f;
+#pragma unroll
+            for (int k = 0; k < 64; k += 8) m = fmaxf(m, fabsf(ldx(k)));
+            const uint32_t e = (__float_as_uint(m) >> 23) & 0xffu;
+            row_scale = e >= 2u ? __uint_as_float((256u - e) << 23) : 1.0f;
+          }
+        }
 #pragma unroll
         for (int k = 0; k < 64; k += 4) {
-          const float x0 = ldx(k + 0), x1 = ldx(k + 1);
-          const float x2 = ldx(k + 2), x3 = ldx(k + 3);
+          float x0 = ldx(k + 0), x1 = ldx(k + 1);
+          float x2 = ldx(k + 2), x3 = ldx(k + 3);
+          if constexpr (F16OP) { x0 *= row_scale; x1 *= row_scale; x2 *= row_scale; x3 *= row_scale; }
           ss0 = fmaf(x0, x0, ss0); ss1 = fmaf(x1, x1, ss1);
           ss2 = fmaf(x2, x2, ss2); ss3 = fmaf(x3, x3, ss3);
-          packed[(k >> 1) + 0] = pack_bf16x2(x0, x1);
-          packed[(k >> 1) + 1] = pack_bf16x2(x2, x3);
+          packed[(k >> 1) + 0] = F16OP ? pack_f16x2_sat(x0, x1) : pack_bf16x2(x0, x1);
+          packed[(k >> 1) + 1] = F16OP ? pack_f16x2_sat(x2, x3) : pack_bf16x2(x2, x3);
           if constexpr (SPLIT3) {
             const uint32_t h01 = packed[(k >> 1) + 0], h23 = packed[(k >> 1) + 1];
             packed_lo[(k >> 1) + 0] = pack_bf16x2(x0 - __uint_as_float(h01 << 16),
@@ -522,9 +545,15 @@ sim_fused_kernel(const __grid_constant__ LevelMaps amaps, const __grid_constant_
           publish(kb, packed);
         }
       }
-      const float inv = 1.0f / fmaxf(sqrtf((ss0 + ss1) + (ss2 + ss3)), 1e-12f);
+      float inv = 1.0f / fmaxf(sqrtf((ss0 + ss1) + (ss2 + ss3)), 1e-12f);
       const int slot = lt % 3;
-      norm_s[slot * F_BLOCK_M + arow] = inv;
+      if constexpr (F16OP) {
+        // ||x|| = ||s x|| / s; the accumulators hold <s x, 16 t>: the row factor is 1 / (16 s max(||x||, eps))
+        inv = 1.0f / fmaxf(sqrtf((ss0 + ss1) + (ss2 + ss3)) / row_scale, 1e-12f);
+        norm_s[slot * F_BLOCK_M + arow] = inv / (16.0f * row_scale);
+      } else {
+        norm_s[slot * F_BLOCK_M + arow] = inv;
+      }
       if (!PROJ && p.inv_norm != nullptr && arow < tc.rows) p.inv_norm[tc.out_row0 + arow] = inv;
       __syncwarp();
       if (lane == 0) ptx::mbar_arrive(n_ready0 + 8u * slot);
@@ -1083,8 +1112,9 @@ int fused_launch(const float* const* obj_embeds, const int64_t* hw, const int64_
                  const void* text_op, const void* const* level_ops, int64_t classes, int text_batched,
                  int normalize, int split3, float alpha, float beta, void* logits, int logits_dtype,
                  int64_t ldc, float* row_max, int32_t* row_arg, float* inv_norm, void* stream,
-                 int in_bf16, void* split_ws, size_t split_ws_bytes, const VpTarget* vp) {
+                 int in_bf16, void* split_ws, size_t split_ws_bytes, const VpTarget* vp, int f16_operands) {
   const int proj = level_ops != nullptr;
+  if (f16_operands && (proj || split3 || in_bf16 || vp || !normalize)) return OVDET_ERR_INVALID_ARG;
   if (vp) {                                         // vocabulary-parallel: keys instead of row_max / row_arg
     if (proj || split3 || logits || row_max || row_arg || alpha < 0.f) return OVDET_ERR_INVALID_ARG;
     if (vp->world < 1 || vp->world > OVDET_MAX_PEERS || vp->class_offset < 0 || !vp->step) return OVDET_ERR_INVALID_ARG;
@@ -1238,21 +1268,24 @@ int fused_launch(const float* const* obj_embeds, const int64_t* hw, const int64_
 
   // every (shape variant, epilogue mode) instantiation the dispatch below can pick
   const int mode = vp ? 2 : (logits ? 1 : 0);
+  if (f16_operands && cg != 2) return OVDET_ERR_UNSUPPORTED_SHAPE;   // fp16 tier: the dim = 512 CTA-pair kernel only
   if (vp && cg != 2) return OVDET_ERR_UNSUPPORTED_SHAPE;      // key exchange: the dim = 512 CTA-pair kernel only
 #define OVDET_FOR_EACH_FUSED(X)                                                                        \
-  X(8, false, 2, false, false, 0, false) X(8, false, 2, false, false, 1, false) X(8, false, 2, false, false, 2, false) \
-  X(8, false, 2, false, true, 0, false)  X(8, false, 2, false, true, 1, false)  X(8, false, 2, false, true, 2, false)  \
-  X(4, false, 2, true, false, 0, false)                                                                \
-  X(8, false, 2, false, false, 0, true)  X(8, false, 2, false, true, 0, true)  X(4, false, 2, true, false, 0, true)     \
-  X(8, false, 2, false, false, 1, true)  X(8, false, 2, false, true, 1, true)                           \
-  X(8, false, 1, false, false, 0, false) X(8, false, 1, false, false, 1, false)                        \
-  X(0, false, 1, false, false, 0, false) X(0, false, 1, false, false, 1, false)                        \
-  X(0, true, 1, false, false, 0, false)  X(0, true, 1, false, false, 1, false)                         \
-  X(0, false, 1, true, false, 0, false)                                                                \
-  X(0, false, 1, false, true, 0, false)  X(0, false, 1, false, true, 1, false)
+  X(8, false, 2, false, false, 0, false, false) X(8, false, 2, false, false, 1, false, false) X(8, false, 2, false, false, 2, false, false) \
+  X(8, false, 2, false, true, 0, false, false)  X(8, false, 2, false, true, 1, false, false)  X(8, false, 2, false, true, 2, false, false)  \
+  X(4, false, 2, true, false, 0, false, false)                                                                \
+  X(8, false, 2, false, false, 0, true, false)  X(8, false, 2, false, true, 0, true, false)  X(4, false, 2, true, false, 0, true, false)     \
+  X(8, false, 2, false, false, 1, true, false)  X(8, false, 2, false, true, 1, true, false)                           \
+  X(8, false, 1, false, false, 0, false, false) X(8, false, 1, false, false, 1, false, false)                        \
+  X(0, false, 1, false, false, 0, false, false) X(0, false, 1, false, false, 1, false, false)                        \
+  X(0, true, 1, false, false, 0, false, false)  X(0, true, 1, false, false, 1, false, false)                         \
+  X(0, false, 1, true, false, 0, false, false)                                                                \
+  X(0, false, 1, false, true, 0, false, false)  X(0, false, 1, false, true, 1, false, false)  \
+  X(8, false, 2, false, false, 0, false, true) X(8, false, 2, false, false, 1, false, true)            \
+  X(8, false, 2, false, false, 1, true, true)
   if (int rc = once_per_device(1, []() -> int {
-#define OVDET_SET_SMEM(KB, S3, CGV, PR, I16, MD, E2)                                                    \
-        OVDET_CUDA_TRY(cudaFuncSetAttribute(sim_fused_kernel<KB, S3, CGV, PR, I16, MD, E2>,             \
+#define OVDET_SET_SMEM(KB, S3, CGV, PR, I16, MD, E2, F16)                                                  \
+        OVDET_CUDA_TRY(cudaFuncSetAttribute(sim_fused_kernel<KB, S3, CGV, PR, I16, MD, E2, F16>,        \
                                             cudaFuncAttributeMaxDynamicSharedMemorySize, FSmem<CGV, (PR && CGV == 2)>::bytes));
         OVDET_FOR_EACH_FUSED(OVDET_SET_SMEM)
 #undef OVDET_SET_SMEM
@@ -1262,7 +1295,8 @@ int fused_launch(const float* const* obj_embeds, const int64_t* hw, const int64_
   // epilogue is on its critical path: K = 272 per tile), bit 1 = cosine mode, bit 2 = bf16 logits (TMA stores)
   static const int epi2_env = []() { const char* e = getenv("OVDET_EPI2"); return e ? atoi(e) : 5; }();
   const bool epi2 = cg == 2 && ((mode == 0 && ((proj && (epi2_env & 1)) || (!proj && (epi2_env & 2)))) ||
-                                (mode == 1 && logits_tma && (epi2_env & 4)));
+                                (mode == 1 && logits_tma && (epi2_env & 4))) &&
+                    !(f16_operands && mode == 0);
   // shape variant of this launch
   const int v_kb = cg == 2 ? (proj ? 4 : 8) : ((!in_bf16 && !proj && !split3 && p.kb == 8) ? 8 : 0);
   cudaLaunchConfig_t cfg{};
@@ -1284,12 +1318,12 @@ int fused_launch(const float* const* obj_embeds, const int64_t* hw, const int64_
     cfg.dynamicSmemBytes = FSmem<1>::bytes;
   }
   bool launched = false;
-#define OVDET_TRY_LAUNCH(KB, S3, CGV, PR, I16, MD, E2)                                                  \
+#define OVDET_TRY_LAUNCH(KB, S3, CGV, PR, I16, MD, E2, F16)                                                \
   if (!launched && v_kb == KB && (split3 != 0) == S3 && cg == CGV && (proj != 0) == PR &&               \
-      (in_bf16 != 0) == I16 && mode == MD && epi2 == E2) {                                              \
+      (in_bf16 != 0) == I16 && mode == MD && epi2 == E2 && (f16_operands != 0) == F16) {                                            \
     cfg.blockDim = dim3(E2 ? F_THREADS + 128 : F_THREADS);                                              \
     cfg.dynamicSmemBytes = FSmem<CGV, (PR && CGV == 2)>::bytes;                                         \
-    OVDET_CUDA_TRY(cudaLaunchKernelEx(&cfg, sim_fused_kernel<KB, S3, CGV, PR, I16, MD, E2>, maps, bmaps, cmaps, p)); \
+    OVDET_CUDA_TRY(cudaLaunchKernelEx(&cfg, sim_fused_kernel<KB, S3, CGV, PR, I16, MD, E2, F16>, maps, bmaps, cmaps, p)); \
     launched = true;                                                                                    \
   }
   OVDET_FOR_EACH_FUSED(OVDET_TRY_LAUNCH)
@@ -1373,4 +1407,17 @@ extern "C" int ovdet_similarity_projected(const float* const* hidden, const int6
   return ovdet::fused_launch(hidden, hw, stride_b, stride_d, num_levels, batch, hidden_dim, nullptr, level_ops,
                              classes, text_batched, /*normalize=*/1, /*split3=*/0, alpha, beta, nullptr,
                              OVDET_F32, classes, row_max, row_arg, inv_norm, stream, 0, nullptr, 0);
+}
+
+extern "C" int ovdet_similarity_fused_fp16(const float* const* obj_embeds, const int64_t* hw,
+                                           const int64_t* stride_b, const int64_t* stride_d,
+                                           int num_levels, int64_t batch, int64_t dim,
+                                           const void* text_op16, int64_t classes, int text_batched,
+                                           float alpha, float beta, void* logits, int logits_dtype,
+                                           int64_t ldc, float* row_max, int32_t* row_arg,
+                                           float* inv_norm, void* stream) {
+  if (dim != 512) return OVDET_ERR_UNSUPPORTED_SHAPE;      // the CTA-pair kernel's shape
+  return ovdet::fused_launch(obj_embeds, hw, stride_b, stride_d, num_levels, batch, dim, text_op16, nullptr,
+                             classes, text_batched, /*normalize=*/1, /*split3=*/0, alpha, beta, logits,
+                             logits_dtype, ldc, row_max, row_arg, inv_norm, stream, 0, nullptr, 0, nullptr, 1);
 }

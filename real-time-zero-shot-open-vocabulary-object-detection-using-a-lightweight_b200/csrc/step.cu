@@ -15,10 +15,19 @@ extern "C" int ovdet_head_step(const ovdet_head_step_args* a, void* stream) {
     hw[l] = (int64_t)a->heights[l] * a->widths[l];
     anchors += hw[l];
   }
-  int rc = ovdet_similarity_fused_ws(reinterpret_cast<const float* const*>(a->obj_embeds), hw, a->emb_stride_b,
+  int rc;
+  if (a->text_fp16) {
+    if (a->embed_dtype != OVDET_F32) return OVDET_ERR_UNSUPPORTED_SHAPE;
+    rc = ovdet_similarity_fused_fp16(reinterpret_cast<const float* const*>(a->obj_embeds), hw, a->emb_stride_b,
                                      a->emb_stride_d, a->num_levels, a->batch, a->dim, a->text_op, a->classes,
-                                     a->text_batched, a->alpha, a->beta, a->scores, a->class_ids, a->inv_norm,
-                                     a->sim_workspace, a->sim_workspace_bytes, a->embed_dtype, stream);
+                                     a->text_batched, a->alpha, a->beta, nullptr, OVDET_F32, a->classes, a->scores,
+                                     a->class_ids, a->inv_norm, stream);
+  } else {
+    rc = ovdet_similarity_fused_ws(reinterpret_cast<const float* const*>(a->obj_embeds), hw, a->emb_stride_b,
+                                   a->emb_stride_d, a->num_levels, a->batch, a->dim, a->text_op, a->classes,
+                                   a->text_batched, a->alpha, a->beta, a->scores, a->class_ids, a->inv_norm,
+                                   a->sim_workspace, a->sim_workspace_bytes, a->embed_dtype, stream);
+  }
   if (rc != OVDET_OK) return rc;
   // K3 and K4 are launched with programmatic stream serialization: their CTAs may be scheduled while
   // the preceding kernel drains (K3 decodes the boxes beside the similarity kernel's tail and waits

@@ -281,14 +281,15 @@ class YOLOCLIPDetector(Detector):
     with neither, the reference's own class is imported (``yolo_clip_detector`` on ``sys.path``).
     Everything from the letterbox to the detection records except that model runs in
     ``libovdet.so``: P1 letterbox -> [model] -> K1+K2 fused similarity -> K3 decode -> K4 NMS ->
-    int-truncated records.  ``precision``: ``"fp32"`` (default, the reference's arithmetic to
-    ~1e-5) or ``"bf16"`` (|dscore| <~ 8e-3)."""
+    int-truncated records.  ``precision``: ``"auto"`` (default: every score within 1e-4 of the
+    reference's fp32 arithmetic - the fused three-pass mode up to 128 prompts, the fp16 tensor-core tier
+    above), ``"fp32"``, ``"fp16"`` or ``"bf16"`` (|dscore| <~ 8e-3)."""
 
     def __init__(self, model_path: Optional[str] = None, class_names: Optional[List[str]] = None,
                  vocab_path: Optional[str] = None, device=None, image_size: Tuple[int, int] = (640, 640),
                  conf_threshold: float = 0.25, iou_threshold: float = 0.45, backbone_variant: str = "n",
                  clip_model: str = "ViT-B/32", embed_dim: int = 512, *, model: Optional[torch.nn.Module] = None,
-                 model_factory=None, precision: str = "fp32", max_det: int = 0):
+                 model_factory=None, precision: str = "auto", max_det: int = 0):
         if device is None:
             if not torch.cuda.is_available():
                 raise RuntimeError("ovdet: YOLOCLIPDetector needs a CUDA device (no CPU fallback exists)")

@@ -20,7 +20,7 @@ import torch.nn as nn
 
 from . import ops
 
-PRECISIONS = ("fp32", "bf16")
+PRECISIONS = ("fp32", "bf16", "fp16", "auto")
 
 
 class ConvBlock(nn.Module):
@@ -59,8 +59,8 @@ def _init_like_reference(module: nn.Module) -> None:
 class TextContrastiveHead(nn.Module):
     """Region/text contrastive head.  ``precision`` selects the tensor-core recipe of
     ``compute_similarity``: ``"fp32"`` (default; three bf16 passes over hi/lo operand halves,
-    |dlogit| ~ 1e-5) or ``"bf16"`` (one pass, |dlogit| <~ 8e-3).  It is a plain attribute, not
-    a parameter or buffer."""
+    |dlogit| ~ 1e-5), ``"fp16"`` (one pass with fp16 operands, |dlogit| <~ 1e-4, embed_dim 512) or
+    ``"bf16"`` (one pass, |dlogit| <~ 8e-3).  It is a plain attribute, not a parameter or buffer."""
 
     def __init__(self, in_channels: int, embed_dim: int = 512, hidden_dim: int = 256,
                  reg_max: int = 16, cls_alpha: float = 1.0, cls_beta: float = 0.0,
@@ -99,8 +99,13 @@ class TextContrastiveHead(nn.Module):
         (the same transposed view, with the same strides, the reference returns)."""
         b, d, h, w = obj_embed.shape
         c = text_embed.shape[-2]
-        split = self.precision == "fp32"
         level = [obj_embed.float()]
+        if self.precision == "fp16" and ops.fused_fp16_supported(level):
+            text_op = ops.l2norm_text(text_embed.float(), split="fp16")
+            logits, _, _ = ops.similarity_fused(level, text_op, self.cls_alpha, self.cls_beta,
+                                                logits_dtype=torch.float32, want_max=False)
+            return logits.transpose(1, 2).reshape(b, c, h, w)
+        split = self.precision != "bf16"        # "fp16" outside its shapes: the three-pass recipe
         # one fused launch (L2 norm + similarity, fp32 NCHW read in place) when the shape allows:
         # bf16 always, fp32-accurate for a single class tile; else K1 -> K2
         if d % 64 == 0 and d <= 512 and (ops.fused_fp32_supported(level, c) if split else ops.fused_supported(level)):
@@ -166,16 +171,22 @@ def _similarity_levels(obj_embeds: Sequence[torch.Tensor], text_embeddings: torc
     path)``.  ONE fused launch straight from the fp32 NCHW conv outputs whenever the kernel takes
     the shape (always for bf16 with TMA-addressable levels; fp32-accurate for any class count at
     dim <= 512); K1 -> K2 otherwise."""
-    split = precision == "fp32"
     classes = text_embeddings.shape[-2]
     levels = [e if e.dtype in (torch.float32, torch.bfloat16) else e.float() for e in obj_embeds]
+    if precision == "auto":             # inside the fp32 bar at the best speed the shape allows
+        precision = ("fp32" if ops.fused_fp32_supported(levels, classes) or want_logits else
+                     "fp16" if ops.fused_fp16_supported(levels) else "fp32")
+    if precision == "fp16" and not ops.fused_fp16_supported(levels):
+        precision = "fp32"              # shapes outside the fp16 tier: the (more accurate) three-pass recipe
+    split = precision == "fp32"
     fused = ops.fused_fp32_supported(levels, classes) if split else ops.fused_supported(levels)
     logits_dtype = torch.float32 if want_logits else None
     if fused:
-        text_op = ops.text_operand_fp32(text_embeddings.float()) if split else ops.l2norm_text(text_embeddings.float())
+        text_op = (ops.text_operand_fp32(text_embeddings.float()) if split else
+                   ops.l2norm_text(text_embeddings.float(), split="fp16" if precision == "fp16" else False))
         logits, scores, class_ids = ops.similarity_fused(levels, text_op, cls_alpha, cls_beta,
                                                          logits_dtype=logits_dtype, want_max=True, fp32=split)
-        return logits, scores, class_ids, "fused_fp32" if split else "fused"
+        return logits, scores, class_ids, "fused_fp32" if split else ("fused_fp16" if precision == "fp16" else "fused")
     levels = [e.float() for e in levels]
     regions_op, inv_norm = ops.l2norm_regions(levels, split=split)
     text_op = ops.l2norm_text(text_embeddings.float(), split=split)
@@ -186,7 +197,7 @@ def _similarity_levels(obj_embeds: Sequence[torch.Tensor], text_embeddings: torc
 
 def head_tail(obj_embeds: Sequence[torch.Tensor], text_embeddings: torch.Tensor,
               box_preds: Sequence[torch.Tensor], strides: Sequence[int] = (8, 16, 32),
-              cls_alpha: float = 1.0, cls_beta: float = 0.0, precision: str = "fp32",
+              cls_alpha: float = 1.0, cls_beta: float = 0.0, precision: str = "auto",
               return_logits: bool = False) -> Dict[str, torch.Tensor]:
     """The tail of ``YOLOCLIP.forward`` (model/yolo_clip.py:173-223) from the convolution outputs
     on: similarity for every level, class max / argmax, level concat, box decode - ONE fused
@@ -251,7 +262,7 @@ class TailOutputs(dict):
 
 def forward_tail(pan_features: Sequence[torch.Tensor], text_embeddings: torch.Tensor,
                  contrastive_heads: Sequence[nn.Module], box_head: nn.Module,
-                 precision: str = "fp32") -> Dict[str, torch.Tensor]:
+                 precision: str = "auto") -> Dict[str, torch.Tensor]:
     """Drop-in for model/yolo_clip.py:173-223 - everything ``YOLOCLIP.forward`` does after the
     neck: ``pan_features`` (the neck's per-level maps) and the neck's text embeddings ``[B, C, D]``
     (any strides: the neck emits ``(D, B*D, 1)``, the offline vocabulary a stride-0 expand) go
@@ -262,7 +273,11 @@ def forward_tail(pan_features: Sequence[torch.Tensor], text_embeddings: torch.Te
     the drop-ins of this file; only their convolution stacks and plain attributes are used.
     Returns the reference's six keys with its shapes and dtypes: ``boxes [B, A, 4]`` fp32,
     ``scores [B, A]`` fp32, ``class_ids [B, A]`` int64, ``obj_embeddings [B, A, D]`` fp32,
-    ``text_embeddings`` (as handed in), ``box_preds`` (list of ``[B, 4R, H, W]``)."""
+    ``text_embeddings`` (as handed in), ``box_preds`` (list of ``[B, 4R, H, W]``).
+
+    ``precision``: ``"auto"`` (default) keeps every score within 1e-4 of the reference's fp32 arithmetic
+    at the best speed the shape allows - the fused three-pass mode up to 128 prompts, the fp16 tensor-core
+    tier (one pass, bf16 speed) above; ``"fp32"`` / ``"fp16"`` / ``"bf16"`` force a recipe."""
     assert precision in PRECISIONS
     assert len(pan_features) == len(contrastive_heads)
     # yolo_clip.py:177-186 calls head(feat) and drops the second output (the head's own box
@@ -316,7 +331,7 @@ def prompt_embeddings(model: nn.Module, batch: int, text_prompts=None, class_nam
     return model.text_encoder(text_prompts).unsqueeze(0).expand(batch, -1, -1)
 
 
-def patch_yolo_clip(model: nn.Module, precision: str = "fp32") -> nn.Module:
+def patch_yolo_clip(model: nn.Module, precision: str = "auto") -> nn.Module:
     """Point an existing ``YOLOCLIP`` instance (model/yolo_clip.py:16-263) at the CUDA tail: its
     ``forward`` keeps the text handling, backbone and neck it has and hands the neck's outputs to
     ``forward_tail``.  No parameter, buffer or submodule changes, so checkpoints load as before::

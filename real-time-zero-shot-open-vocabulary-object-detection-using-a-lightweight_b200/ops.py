@@ -80,7 +80,8 @@ def l2norm_text(text: torch.Tensor, split=False,
     """text_contrastive.py:138.  ``text`` is ``[C, D]`` or ``[B, C, D]`` (any batch / row stride,
     as the neck emits it); a shared vocabulary is normalised once.  Returns the normalised
     bf16 operand ``[Bt, C, kop]`` with Bt = 1 for a shared vocabulary.  ``split``: False ``[hi]``,
-    True ``[hi | lo]`` (two-kernel fp32 recipe), ``3`` ``[hi | lo | hi]`` (fused fp32-accurate mode)."""
+    True ``[hi | lo]`` (two-kernel fp32 recipe), ``3`` ``[hi | lo | hi]`` (fused fp32-accurate mode),
+    ``"fp16"``: ONE float16 segment holding 16 x the unit rows (the fp16 tier of ``similarity_fused``)."""
     _require_cuda(text, "text_embed", torch.float32)
     if text.dim() == 2:
         text = text.unsqueeze(0)
@@ -89,11 +90,15 @@ def l2norm_text(text: torch.Tensor, split=False,
     if text.stride(2) != 1:
         text = text.contiguous()
     bt, classes, dim = text.shape
-    mode = 2 if split == 3 else int(bool(split))
-    kop = dim * (mode + 1)
+    f16 = isinstance(split, str)
+    if f16 and split != "fp16":
+        raise ValueError("ovdet: split is False, True, 3 or 'fp16'")
+    mode = 3 if f16 else (2 if split == 3 else int(bool(split)))
+    kop = dim if f16 else dim * (mode + 1)
+    op_dtype = torch.float16 if f16 else torch.bfloat16
     if operand is None:
-        operand = torch.empty(bt, classes, kop, device=text.device, dtype=torch.bfloat16)
-    assert operand.shape == (bt, classes, kop) and operand.is_contiguous()
+        operand = torch.empty(bt, classes, kop, device=text.device, dtype=op_dtype)
+    assert operand.shape == (bt, classes, kop) and operand.is_contiguous() and operand.dtype == op_dtype
     with torch.cuda.device(text.device):
         check(lib().ovdet_l2norm_text(text.data_ptr(), bt, classes, dim, text.stride(0),
                                       text.stride(1), operand.data_ptr(), kop, mode, None,
@@ -169,6 +174,12 @@ def text_operand_fp32(text: torch.Tensor) -> torch.Tensor:
     return l2norm_text(text, split=3)
 
 
+def fused_fp16_supported(obj_embeds: Sequence[torch.Tensor]) -> bool:
+    """Shapes of the fp16 tier: the CTA-pair kernel (dim = 512), fp32 activations, TMA-addressable levels."""
+    return (fused_supported(obj_embeds) and obj_embeds[0].shape[1] == 512 and
+            obj_embeds[0].dtype == torch.float32)
+
+
 def fused_fp32_supported(obj_embeds: Sequence[torch.Tensor], classes: int) -> bool:
     """Shapes of the fused fp32-accurate kernel: TMA-addressable levels and a single class tile
     (or an embedding of at most 128 values)."""
@@ -181,12 +192,16 @@ def similarity_fused(obj_embeds: Sequence[torch.Tensor], text_op: torch.Tensor, 
                      row_max: Optional[torch.Tensor] = None, row_arg: Optional[torch.Tensor] = None,
                      inv_norm: Optional[torch.Tensor] = None, want_arg: bool = True, fp32: bool = False):
     """text_contrastive.py:134-147 for all levels + yolo_clip.py:198-206 in one launch, reading
-    the fp32 NCHW ``obj_embeds`` directly.  ``text_op`` comes from ``l2norm_text(split=False)``.
-    Returns ``(logits [B, A, C] or None, row_max, row_arg)``; ``want_arg=False`` skips the
-    argmax (scores only)."""
+    the fp32 NCHW ``obj_embeds`` directly.  ``text_op`` comes from ``l2norm_text(split=False)`` - or
+    from ``l2norm_text(split="fp16")``: a float16 operand selects the fp16 tensor-core tier (same speed,
+    |dlogit| ~ 1e-5 instead of ~4e-3).  Returns ``(logits [B, A, C] or None, row_max, row_arg)``;
+    ``want_arg=False`` skips the argmax (scores only)."""
     first = obj_embeds[0]
     _require_cuda(first, "obj_embed")
-    _require_cuda(text_op, "text_op", torch.bfloat16)
+    f16 = text_op.dtype == torch.float16
+    _require_cuda(text_op, "text_op", torch.float16 if f16 else torch.bfloat16)
+    if f16 and (fp32 or not fused_fp16_supported(obj_embeds)):
+        raise ValueError("ovdet: the fp16 tier takes fp32 activations with dim = 512 (and is not the three-pass mode)")
     in16 = first.dtype == torch.bfloat16
     if in16 and fp32:
         raise ValueError("ovdet: the fp32-accurate mode takes fp32 activations")
@@ -217,7 +232,7 @@ def similarity_fused(obj_embeds: Sequence[torch.Tensor], text_op: torch.Tensor, 
     hw = (ctypes.c_int64 * n)(*[e.shape[2] * e.shape[3] for e in obj_embeds])
     sb = (ctypes.c_int64 * n)(*[e.stride(0) for e in obj_embeds])
     sd = (ctypes.c_int64 * n)(*[e.stride(1) for e in obj_embeds])
-    entry = (lib().ovdet_similarity_fused_fp32 if fp32 else
+    entry = (lib().ovdet_similarity_fused_fp32 if fp32 else lib().ovdet_similarity_fused_fp16 if f16 else
              lib().ovdet_similarity_fused_bf16in if in16 else lib().ovdet_similarity_fused)
     with torch.cuda.device(dev):
         check(entry(ptrs, hw, sb, sd, n, batch, dim, text_op.data_ptr(),

@@ -50,13 +50,35 @@ class HeadConfig:
     cls_beta: float = 0.0
     conf_threshold: float = 0.25
     iou_threshold: float = 0.45
-    precision: str = "bf16"            # "bf16": one tensor-core pass; "fp32": 3-pass hi/lo split
+    # "auto" (default): inside the fp32 bar of the reference's arithmetic (|dlogit| <= 1e-4) at the best speed
+    #         the shape allows - "fp32" where its fused streaming mode applies (<= 128 classes), else "fp16"
+    #         (embed_dim 512, H*W multiples of 4), else "fp32" through the two-kernel path;
+    # "bf16": one tensor-core pass, |dlogit| <~ 8e-3 (the BASELINE metric's configuration; opt-in);
+    # "fp16": one pass at the same rate with fp16 operands and per-row power-of-two scaling, |dlogit| <~ 1e-4
+    #         (embed_dim 512, fp32 activations, TMA-addressable levels);
+    # "fp32": three bf16 passes over hi/lo operand halves, |dlogit| <~ 3e-5
+    precision: str = "auto"
     logits_dtype: Optional[str] = None  # None: fused max only; "bf16" / "fp32": also materialise
     activation: str = "none"           # reference applies no activation to the scores
     topk: int = 0                      # 0 = every survivor goes to NMS (reference)
     class_aware: bool = False          # reference NMS is class-agnostic
     max_det: int = 0                   # 0 = capacity for every anchor (reference has no cap)
     fused: bool = True                 # bf16 only: K1+K2 in one kernel when the inputs allow it
+
+
+def resolve_precision(config: "HeadConfig", level_shapes, num_classes: int, projected: bool = False) -> str:
+    """What ``precision="auto"`` means for a problem shape (see ``HeadConfig``)."""
+    if config.precision != "auto":
+        return config.precision
+    if projected:
+        return "bf16"                       # the projected similarity is a single bf16 pass by construction
+    d = config.embed_dim
+    tma_ok = all((h * w) % 4 == 0 for h, w in level_shapes) and len(level_shapes) <= 4
+    if config.fused and tma_ok and d % 64 == 0 and d <= 512 and (num_classes <= 128 or d <= 128):
+        return "fp32"                       # fused streaming three-pass mode: one launch, ~1e-5
+    if config.fused and tma_ok and d == 512 and config.logits_dtype != "fp32":
+        return "fp16"
+    return "fp32"
 
 
 class HeadPipeline:
@@ -74,10 +96,18 @@ class HeadPipeline:
         self.num_classes = num_classes
         self.device = torch.device(device)
         self.per_image_text = per_image_text
+        if config.precision not in ("auto", "bf16", "fp16", "fp32"):
+            raise ValueError("ovdet: precision is 'auto', 'bf16', 'fp16' or 'fp32'")
+        if config.precision == "auto":
+            import dataclasses
+            config = dataclasses.replace(config, precision=resolve_precision(
+                config, level_shapes, num_classes, projected=projections is not None))
+            self.cfg = config
         self.split = config.precision == "fp32"
+        self.f16 = config.precision == "fp16"
         self.projections = None
         if projections is not None:
-            if self.split:
+            if self.split or self.f16:
                 raise ValueError("ovdet: the projected similarity is a bf16 path")
             self.projections = [(w.detach().to(device, torch.float32),
                                  None if b is None else b.detach().to(device, torch.float32))
@@ -87,6 +117,8 @@ class HeadPipeline:
         d, a, dev = config.embed_dim, self.anchors, self.device
         kop = d * (2 if self.split else 1)
         self.want_fused = config.fused and not self.split and d % 64 == 0 and d <= 512
+        if self.f16 and not (config.fused and d == 512):
+            raise ValueError("ovdet: precision 'fp16' is a mode of the fused CTA-pair kernel (embed_dim 512)")
         # fp32 precision with a single class tile: the fused kernel's streaming three-pass mode
         self.want_fused_fp32 = (config.fused and self.split and d % 64 == 0 and d <= 512 and
                                 (num_classes <= 128 or d <= 128))
@@ -95,7 +127,7 @@ class HeadPipeline:
         self.regions_op = None             # bf16 operand of the two-kernel path, allocated on first use
         self.inv_norm = torch.empty(batch, a, device=dev, dtype=torch.float32)
         self.text_op = torch.empty(batch if per_image_text else 1, num_classes, kop, device=dev,
-                                   dtype=torch.bfloat16)
+                                   dtype=torch.float16 if self.f16 else torch.bfloat16)
         self.scores = torch.empty(batch, a, device=dev, dtype=torch.float32)
         self.class_ids = torch.empty(batch, a, device=dev, dtype=torch.int32)
         self.logits = None
@@ -141,10 +173,13 @@ class HeadPipeline:
         if self.projections is not None:
             self.level_ops = [ops.project_vocabulary(text, w, b) for w, b in self.projections]
         else:
-            ops.l2norm_text(text, split=self.split, operand=self.text_op)
+            ops.l2norm_text(text, split=self._text_mode(), operand=self.text_op)
             if self.want_fused_fp32:
                 self.text_op3 = ops.l2norm_text(text, split=3, operand=self.text_op3)
         self._vocab_ready = True
+
+    def _text_mode(self):
+        return "fp16" if self.f16 else self.split
 
     def set_geometry(self, orig_sizes: Sequence[Tuple[int, int]], scale_factors: Sequence[float]) -> None:
         """Per-image ``(orig_h, orig_w)`` and letterbox scale (detector.py:193-202).  The scale
@@ -231,10 +266,14 @@ class HeadPipeline:
         if self.projections is not None:
             return self._run_projected(obj_embeds, box_preds, text, mark)
         if (events is None and self.want_fused and self.logits is None and not self._parallel_decode
-                and ops.fused_supported(obj_embeds) and self._single_call_ok(box_preds)):
+                and ops.fused_supported(obj_embeds) and self._single_call_ok(box_preds)
+                and (not self.f16 or ops.fused_fp16_supported(obj_embeds))):
             return self._run_single_call(obj_embeds, box_preds, text)
         fused = self.want_fused and ops.fused_supported(obj_embeds)
         fused32 = self.want_fused_fp32 and ops.fused_supported(obj_embeds)
+        if self.f16 and not (fused and ops.fused_fp16_supported(obj_embeds)):
+            raise ValueError("ovdet: precision 'fp16' needs fp32 activations with TMA-addressable levels "
+                             "(H*W and strides multiples of 4); use 'fp32' or 'bf16' for this input")
         self.last_path = "fused" if fused else ("fused_fp32" if fused32 else "split")
         mark("l2norm", True)
         if not fused and not fused32:
@@ -246,7 +285,7 @@ class HeadPipeline:
             if fused32:         # one K1b launch straight into the [hi | lo | hi] operand, no ATen op in the step
                 self.text_op3 = ops.l2norm_text(text, split=3, operand=self.text_op3)
             else:
-                ops.l2norm_text(text, split=self.split, operand=self.text_op)
+                ops.l2norm_text(text, split=self._text_mode(), operand=self.text_op)
         elif text is not None:
             self.set_vocabulary(text)
         elif not self._vocab_ready:
@@ -279,7 +318,7 @@ class HeadPipeline:
     def _run_single_call(self, obj_embeds, box_preds, text) -> ops.NmsResult:
         cfg = self.cfg
         if self.per_image_text:
-            ops.l2norm_text(text, split=False, operand=self.text_op)
+            ops.l2norm_text(text, split=self._text_mode(), operand=self.text_op)
         elif text is not None:
             self.set_vocabulary(text)
         elif not self._vocab_ready:
@@ -308,6 +347,7 @@ class HeadPipeline:
                 a.heights[l], a.widths[l], a.strides[l] = h, w, int(cfg.strides[l])
             a.text_op = self.text_op.data_ptr()
             a.text_batched = int(self.per_image_text and self.batch > 1)
+            a.text_fp16 = int(self.f16)
             a.activation = {"none": _cabi.ACT_NONE, "sigmoid": _cabi.ACT_SIGMOID}[cfg.activation]
             a.class_aware, a.topk = int(cfg.class_aware), int(cfg.topk)
             a.alpha, a.beta, a.conf, a.iou_thr = cfg.cls_alpha, cfg.cls_beta, cfg.conf_threshold, cfg.iou_threshold

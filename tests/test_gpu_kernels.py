@@ -1286,6 +1286,89 @@ def test_similarity_fused_fp32_streaming(ov, cuda_device, classes, batched, dim)
     assert (a0 == rarg).float().mean().item() >= 0.999
 
 
+FP16_ABS = 1e-4          # the fp16 tier: |dlogit| at alpha = 1 (measured max ~6e-5 over 10^7 logits, rms ~1e-5)
+
+
+@pytest.mark.parametrize("classes,batched", [(80, False), (1203, False), (300, True)])
+def test_similarity_fused_fp16_tier_vs_oracle(ov, cuda_device, classes, batched):
+    """The fp16 tensor-core tier (one pass, fp16 operands, per-row power-of-two scaling): logits against
+    the oracle inside the north_star's fp32 bar (1e-3 relative) and inside 1e-4 absolute - two orders
+    below the bf16 tier - for activations of any magnitude: levels scaled by 1e-6 and 3e4, a zero
+    vector, a row whose first 64 channels are all zero, ragged anchor tiles."""
+    from ovdet import ops
+    torch.manual_seed(classes)
+    b, dim = 3, 512
+    shapes = [(20, 20), (10, 12), (4, 5)]
+    scales = [1.0, 1e-6, 3e4]
+    embs = [torch.randn(b, dim, h, w) * sc for (h, w), sc in zip(shapes, scales)]
+    embs[0][1, :, 2, 3] = 0.0                       # zero vector: eps clamp, score = beta
+    embs[0][2, :64, 5, 5] = 0.0                     # first block all zero: scale falls back to 1
+    embs[1][0, :8, 1, 1] *= 1e-3                    # sampled channels much smaller than the rest of the row
+    text = torch.randn(b, classes, dim) if batched else torch.randn(classes, dim).unsqueeze(0).expand(b, -1, -1)
+    alpha, beta = 1.0, 0.03
+    ref = torch.cat([ref_port.compute_similarity(e, text, alpha, beta).flatten(2).transpose(1, 2)
+                     for e in embs], dim=1)
+    dev_embs = [e.to(cuda_device) for e in embs]
+    top = ops.l2norm_text(text.to(cuda_device) if batched else text[0].to(cuda_device), split="fp16")
+    assert top.dtype == torch.float16 and top.shape[-1] == dim
+    logits, rmax, rarg = ops.similarity_fused(dev_embs, top, alpha, beta, logits_dtype=torch.float32, want_max=True)
+    torch.cuda.synchronize()
+    err = (logits.cpu() - ref).abs()
+    print(f"\n[fp16 tier, C={classes}] max |dlogit| {err.max():.2e}, rms {err.pow(2).mean().sqrt():.2e}")
+    assert err.max() / ref.abs().max() <= FP32_REL          # north_star: within 1e-3 relative
+    assert err.max() <= FP16_ABS
+    m, a = logits.max(dim=-1)
+    assert torch.equal(rmax, m) and torch.equal(rarg.long(), a)
+    assert (rarg.cpu().long() == ref.argmax(dim=-1)).float().mean() >= 0.995
+    _, m0, a0 = ops.similarity_fused(dev_embs, top, alpha, beta, logits_dtype=None, want_max=True)
+    assert (m0 - rmax).abs().max().item() <= 1e-6 and (a0 == rarg).float().mean().item() >= 0.999
+    # bf16 logits out of the fp16 product (TMA-store epilogue, two epilogue groups)
+    lb = torch.empty(b, logits.shape[1], (classes + 7) // 8 * 8, device=cuda_device, dtype=torch.bfloat16)[..., :classes]
+    ops.similarity_fused(dev_embs, top, alpha, beta, logits=lb, want_max=True)
+    torch.cuda.synchronize()
+    assert (lb.float() - logits).abs().max().item() <= 4e-3
+
+
+def test_pipeline_fp16_tier_bench_shape_vs_oracle(ov, cuda_device):
+    """precision="fp16" through HeadPipeline at the bench's per-image shape (640^2, 1203 prompts): the
+    single C call and the per-stage launches agree byte for byte, scores inside 1e-4 of the oracle,
+    classes equal outside near-ties, post-processing bit-exact on identical inputs, kept sets reported."""
+    from ovdet import synth
+    from ovdet.pipeline import HeadConfig, HeadPipeline
+    b, classes, s = 2, 1203, 640
+    inp = synth.make_inputs(batch=b, image_size=s, num_classes=classes, seed=31)
+    tail = ref_port.head_tail(inp.obj_embeds, inp.text_batched(), inp.box_preds)
+    shapes = [(s // 8, s // 8), (s // 16, s // 16), (s // 32, s // 32)]
+    pipe = HeadPipeline(b, shapes, classes, HeadConfig(precision="fp16"), device=cuda_device)
+    pipe.set_vocabulary(inp.text.to(cuda_device))
+    sizes = [(s, s)] * b
+    pipe.set_geometry(sizes, [1.0] * b)
+    objs = [e.to(cuda_device) for e in inp.obj_embeds]
+    preds = [p.to(cuda_device) for p in inp.box_preds]
+    res = pipe.run(objs, preds)
+    torch.cuda.synchronize()
+    assert pipe.last_path == "fused" and pipe.last_single_call
+    err = (pipe.scores.cpu() - tail["scores"]).abs().max().item()
+    print(f"\n[fp16 tier pipeline] max |dscore| {err:.2e}")
+    assert err <= FP16_ABS
+    assert (pipe.class_ids.cpu().long() == tail["class_ids"]).float().mean() >= 0.998
+    fed = {"boxes": pipe.boxes.cpu(), "scores": pipe.scores.cpu(), "class_ids": pipe.class_ids.cpu().long()}
+    want = ref_port.postprocess_batch(fed, sizes, [1.0] * b)
+    for i in range(b):
+        k = int(res.count[i])
+        assert k == len(want[i]["keep"]) and k > 20
+        np.testing.assert_array_equal(res.keep[i, :k].cpu().numpy(), want[i]["keep"])
+    mism, kept_ref = _index_mismatches(res, ref_port.postprocess_batch(tail, sizes, [1.0] * b))
+    print(f"[e2e index mismatches, fp16 tier] per image {mism} of {kept_ref} kept")
+    assert sum(mism) <= max(1, int(0.02 * sum(kept_ref)))
+    scores = pipe.scores.clone()
+    pipe.run(objs, preds, events={})
+    torch.cuda.synchronize()
+    assert torch.equal(pipe.scores, scores)
+    with pytest.raises(ValueError, match="fp16"):
+        HeadPipeline(b, shapes, classes, HeadConfig(precision="fp16", embed_dim=256), device=cuda_device)
+
+
 def test_fused_modes_are_deterministic_under_load(ov, cuda_device):
     """Race detector of last resort (compute-sanitizer is closed on this pool): every mode of the
     fused kernel - CTA-pair cosine, projected, streaming fp32, attention - run 12 times on the same
