@@ -52,11 +52,18 @@ constexpr int F_BLOCK_M = 128;
 constexpr int F_BLOCK_N = 128;
 constexpr int F_BLOCK_K = 64;
 constexpr int F_MAX_KB = 8;                       // dim <= 512: A fills 256 TMEM columns
+constexpr int F_MAX_SLOTS = 12;                   // slots of the A ring (BN64: 12 x 32 columns)
+#ifndef OVDET_F_BN64
+#define OVDET_F_BN64 0                           // CTA-pair cosine kernels: 64-class N tiles, 12-slot A ring (see BN64)
+#endif
 #ifndef OVDET_F_A_STAGES
 #define OVDET_F_A_STAGES 4
 #endif
 #ifndef OVDET_F_B_STAGES
 #define OVDET_F_B_STAGES 4
+#endif
+#ifndef OVDET_F_AHEAD2
+#define OVDET_F_AHEAD2 1                         // converter publishes blocks late (see AHEAD2 in the kernel); 2: at most two
 #endif
 constexpr int F_A_STAGES = OVDET_F_A_STAGES;      // fp32 activation ring (tuning: -DOVDET_F_A_STAGES=n)
 constexpr int F_A_STAGE_BYTES = F_BLOCK_K * F_BLOCK_M * 4;     // 32 KiB fp32 [k][anchor]
@@ -79,10 +86,13 @@ constexpr int F_MAX_LEVELS = 4;
 // 24 KiB.  With two blocks per stage the 16-wide constant block was a stage of its own - one MMA
 // (64 tensor cycles) behind a full barrier round trip of the issuing thread: dropping that stage in a
 // timing experiment took 13 % off the kernel for 6 % of its MMA work.  Stages are now {0,1,2} {3,const}.
-template <int CG, bool KPS3 = false>
+// BN64 (the dim = 512 CTA-pair cosine kernels): N tiles of 64 classes - a text box is [32 rows x 64 k] =
+// 4 KiB and a stage holds FOUR k blocks (16 MMAs of 32 cycles per barrier round trip).
+template <int CG, bool KPS3 = false, bool BN64 = false>
 struct FSmem {
-  static constexpr int kps = KPS3 ? 3 : CG;                          // k blocks per text stage
-  static constexpr int b_sub_bytes = (F_BLOCK_N / CG) * F_BLOCK_K * 2;  // one TMA box: [N / CG rows x 64 k]
+  static constexpr int bn = BN64 ? 64 : F_BLOCK_N;                   // classes per N tile
+  static constexpr int kps = KPS3 ? 3 : (BN64 ? 4 : CG);             // k blocks per text stage
+  static constexpr int b_sub_bytes = (bn / CG) * F_BLOCK_K * 2;      // one TMA box: [N / CG rows x 64 k]
   static constexpr int b_stages = KPS3 ? 3 : OVDET_F_B_STAGES;
   static constexpr int b_stage_bytes = kps * b_sub_bytes;            // 16 KiB
   static constexpr int b_off = 0;
@@ -96,12 +106,13 @@ struct FSmem {
   static constexpr int xbuf_bytes = 2 * 3 * F_BLOCK_M * 4;
   static constexpr int bar_off = xbuf_off + xbuf_bytes;
   // b_full, b_empty, as_full, as_empty, a_ready, a_free, tmem_full, tmem_empty, norm_ready
-  static constexpr int num_bars = 2 * b_stages + 2 * F_A_STAGES + 2 * F_MAX_KB + 2 + 2 + 3;
+  static constexpr int num_bars = 2 * b_stages + 2 * F_A_STAGES + 2 * F_MAX_SLOTS + 2 + 2 + 3;
   static constexpr int tmem_ptr_off = bar_off + num_bars * 8;
   static constexpr int total = tmem_ptr_off + 16;
   static constexpr int bytes = total + 1024;
 };
-static_assert(FSmem<1>::bytes <= 227 * 1024 && FSmem<2>::bytes <= 227 * 1024 && FSmem<2, true>::bytes <= 227 * 1024,
+static_assert(FSmem<1>::bytes <= 227 * 1024 && FSmem<2>::bytes <= 227 * 1024 && FSmem<2, true>::bytes <= 227 * 1024 &&
+              FSmem<2, false, true>::bytes <= 227 * 1024,
               "shared memory budget");
 
 struct LevelMaps { CUtensorMap m[F_MAX_LEVELS]; };   // activations; (projected) one text operand per level
@@ -151,7 +162,17 @@ struct FusedParams {
   const unsigned long long* vp_step;              // this rank's counter: the step being contributed to
   unsigned long long* vp_keys[OVDET_MAX_PEERS];   // keys[2][vp_rows] of every rank (peer-mapped)
   int dbg;
+  unsigned long long* trace;       // OVDET_TRACE builds only: per-role clock stamps of CTA 0 (tools/trace_fused.py)
 };
+#ifdef OVDET_TRACE
+#define OVDET_TR(role, tag)                                                                       \
+  do {                                                                                            \
+    if (p.trace != nullptr && blockIdx.x == 0 && lane == 0 && tr_n < 32768)                       \
+      p.trace[(role) * 32768 + tr_n++] = ((unsigned long long)(tag) << 48) | ((unsigned long long)clock64() & 0xFFFFFFFFFFFFull); \
+  } while (0)
+#else
+#define OVDET_TR(role, tag) do { } while (0)
+#endif
 
 // With CG == 2 the two CTAs of a pair take tiles 2i and 2i+1; `mt` is then rounded up to an even
 // count per (level, image) when the text is per-image, so that a pair never straddles two images
@@ -215,7 +236,17 @@ template <int KB_T, bool SPLIT3, int CG, bool PROJ, bool IN16 = false, int MODE 
 __global__ void __launch_bounds__(EPI2 ? F_THREADS + 128 : F_THREADS, 1)
 sim_fused_kernel(const __grid_constant__ LevelMaps amaps, const __grid_constant__ LevelMaps bmaps,
                  const __grid_constant__ LevelMaps cmaps, const FusedParams p) {
-  using FSmem = ovdet::FSmem<CG, (PROJ && CG == 2)>;
+  // BN64: N tiles of 64 classes.  Tensor memory then holds two 64-column accumulators and a TWELVE-slot A
+  // ring (12 x 32 columns = 1.5 anchor tiles) instead of two 128-column accumulators and exactly one tile:
+  // the first four blocks of the next anchor tile are converted and stored while the current tile is still
+  // being multiplied, and the other four go into slots the last N tile releases in its FIRST half.  With
+  // the 8-slot ring every block of the next tile had to wait for the last N tile's MMAs on the same slot
+  // and the converter - ~550 cycles per block against 256 cycles of MMAs - left the tensor pipe idle for
+  // ~2800 cycles per anchor tile (tools/trace_fused.py, profiles/r2_trace_*.txt).
+  constexpr bool BN64 = CG == 2 && !PROJ && !SPLIT3 && KB_T == 8 && OVDET_F_BN64;
+  constexpr int BN = BN64 ? 64 : F_BLOCK_N;
+  constexpr int A_COL = BN64 ? 2 * BN : F_A_COL;                   // first column of the A ring
+  using FSmem = ovdet::FSmem<CG, (PROJ && CG == 2), BN64>;
   constexpr int F_B_STAGES = FSmem::b_stages;
   constexpr int F_B_STAGE_BYTES = FSmem::b_stage_bytes;
   constexpr int KPS = FSmem::kps;
@@ -243,8 +274,8 @@ sim_fused_kernel(const __grid_constant__ LevelMaps amaps, const __grid_constant_
   const uint32_t b_empty0 = bars + 8u * bi_;     bi_ += F_B_STAGES;
   const uint32_t as_full0 = bars + 8u * bi_;     bi_ += F_A_STAGES;
   const uint32_t as_empty0 = bars + 8u * bi_;    bi_ += F_A_STAGES;
-  const uint32_t a_ready0 = bars + 8u * bi_;     bi_ += F_MAX_KB;
-  const uint32_t a_free0 = bars + 8u * bi_;      bi_ += F_MAX_KB;
+  const uint32_t a_ready0 = bars + 8u * bi_;     bi_ += F_MAX_SLOTS;
+  const uint32_t a_free0 = bars + 8u * bi_;      bi_ += F_MAX_SLOTS;
   const uint32_t t_full0 = bars + 8u * bi_;      bi_ += 2;
   const uint32_t t_empty0 = bars + 8u * bi_;     bi_ += 2;
   const uint32_t n_ready0 = bars + 8u * bi_;
@@ -252,13 +283,16 @@ sim_fused_kernel(const __grid_constant__ LevelMaps amaps, const __grid_constant_
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
+#ifdef OVDET_TRACE
+  int tr_n = 0;
+#endif
 
   if (warp == 0 && lane == 0) {
     for (int l = 0; l < p.levels; ++l) { ptx::prefetch_tmap(&amaps.m[l]); ptx::prefetch_tmap(&bmaps.m[PROJ ? l : 0]); }
     for (int s = 0; s < F_B_STAGES; ++s) { ptx::mbar_init(b_full0 + 8u * s, 1); ptx::mbar_init(b_empty0 + 8u * s, 1); }
     for (int s = 0; s < F_A_STAGES; ++s) { ptx::mbar_init(as_full0 + 8u * s, 1); ptx::mbar_init(as_empty0 + 8u * s, 4); }
     // a_ready / t_empty collect the converter / epilogue warps of BOTH CTAs on the leader
-    for (int k = 0; k < F_MAX_KB; ++k) { ptx::mbar_init(a_ready0 + 8u * k, 4 * CG);
+    for (int k = 0; k < F_MAX_SLOTS; ++k) { ptx::mbar_init(a_ready0 + 8u * k, 4 * CG);
       // projected: the epilogue warps read x' back from the A region, so they release it too
       ptx::mbar_init(a_free0 + 8u * k, PROJ ? (EPI2 ? 9 : 5) : 1); }
     for (int s = 0; s < 2; ++s) { ptx::mbar_init(t_full0 + 8u * s, 1); ptx::mbar_init(t_empty0 + 8u * s, 4 * CG); }
@@ -294,7 +328,8 @@ sim_fused_kernel(const __grid_constant__ LevelMaps amaps, const __grid_constant_
   // slot i for the whole anchor tile.  Streaming (SPLIT3 with more than 8 blocks, one N tile only):
   // R = 8 and block i of tile lt takes slot (lt * KB_A + i) % 8 - every block is consumed exactly
   // once, so its slot is handed back as soon as its MMAs retire.
-  const int R = (SPLIT3 && KB_A > F_MAX_KB) ? F_MAX_KB : KB_A;
+  // BN64: R = 12 > KB_A = 8: block i of tile lt takes slot (8 lt + i) % 12 for the tile's lifetime.
+  const int R = BN64 ? F_MAX_SLOTS : ((SPLIT3 && KB_A > F_MAX_KB) ? F_MAX_KB : KB_A);
   auto a_slot = [&](uint32_t lt_, int i) { return (int)((lt_ * (uint32_t)KB_A + (uint32_t)i) % (uint32_t)R); };
   auto a_phase = [&](uint32_t lt_, int i) { return ((lt_ * (uint32_t)KB_A + (uint32_t)i) / (uint32_t)R) & 1u; };
   // SPLIT3 visits the blocks input-block-major: i = 3 * j + part, parts (hi, hi, lo) against the
@@ -304,10 +339,10 @@ sim_fused_kernel(const __grid_constant__ LevelMaps amaps, const __grid_constant_
   const int NT = p.n_tiles;
   const int NG = PROJ ? p.ng_tiles : 0;
   // N tile nt of an anchor tile: first operand row, MMA N (multiple of 16), valid columns
-  auto ntile_row0 = [&](int nt) { return nt < NG ? p.cpad + nt * F_BLOCK_N : (nt - NG) * F_BLOCK_N; };
+  auto ntile_row0 = [&](int nt) { return nt < NG ? p.cpad + nt * BN : (nt - NG) * BN; };
   auto ntile_valid = [&](int nt) {
-    const int n = nt < NG ? p.kop - nt * F_BLOCK_N : p.classes - (nt - NG) * F_BLOCK_N;
-    return n >= F_BLOCK_N ? F_BLOCK_N : n;
+    const int n = nt < NG ? p.kop - nt * BN : p.classes - (nt - NG) * BN;
+    return n >= BN ? BN : n;
   };
   auto ntile_nsize = [&](int nt) { return (ntile_valid(nt) + 15) & ~15; };
 
@@ -369,8 +404,10 @@ sim_fused_kernel(const __grid_constant__ LevelMaps amaps, const __grid_constant_
         const uint32_t it0 = g * (uint32_t)NSTAGE;
         // peek at the first text stage while waiting for the accumulator to drain
         bool ready = ptx::mbar_try_wait(b_full0 + 8u * (it0 % F_B_STAGES), (it0 / F_B_STAGES) & 1u);
+        OVDET_TR(0, 1);
         ptx::mbar_wait(t_empty0 + 8u * as, ((g >> 1) & 1u) ^ 1u);
-        const uint32_t d_tmem = tmem_u + (uint32_t)F_ACC_COL + as * (uint32_t)F_BLOCK_N;
+        OVDET_TR(0, 2);
+        const uint32_t d_tmem = tmem_u + (uint32_t)F_ACC_COL + as * (uint32_t)BN;
 #pragma unroll
         for (int sb = 0; sb < NSTAGE; ++sb) {
           const uint32_t it = it0 + (uint32_t)sb;
@@ -380,8 +417,10 @@ sim_fused_kernel(const __grid_constant__ LevelMaps amaps, const __grid_constant_
             for (int j = 0; j < KPS; ++j)
               if (sb * KPS + j < KB_A)
                 ptx::mbar_wait(a_ready0 + 8u * a_slot(lt, sb * KPS + j), a_phase(lt, sb * KPS + j));
+            OVDET_TR(0, 3);
           }
           ptx::mbar_wait_if_not(ready, b_full0 + 8u * s, ph);
+          OVDET_TR(0, 4);
           ptx::tc_fence_after();
           if (sb + 1 < NSTAGE)                                           // hide the next wait's latency
             ready = ptx::mbar_try_wait(b_full0 + 8u * ((it + 1) % F_B_STAGES), ((it + 1) / F_B_STAGES) & 1u);
@@ -391,7 +430,7 @@ sim_fused_kernel(const __grid_constant__ LevelMaps amaps, const __grid_constant_
               const int kb = sb * KPS + j;
               if (kb < KB) {
                 const uint64_t b_desc = ptx::umma_desc_k_sw128(smem_b_u + s * F_B_STAGE_BYTES + j * F_B_SUB_BYTES);
-                const uint32_t a_tmem = tmem_u + (uint32_t)(F_A_COL + (kb < KB_A ? a_slot(lt, kb) : kb) * 32);
+                const uint32_t a_tmem = tmem_u + (uint32_t)(A_COL + (kb < KB_A ? a_slot(lt, kb) : kb) * 32);
                 // projected: the last block is the 16-wide constant block of x' = [x, 1]
                 const int ksteps = (PROJ && kb == KB - 1) ? 1 : F_BLOCK_K / 16;
 #pragma unroll
@@ -411,6 +450,7 @@ sim_fused_kernel(const __grid_constant__ LevelMaps amaps, const __grid_constant_
         }
         if (ptx::elect_one()) ptx::umma_commit_cg<CG>(t_full0 + 8u * as);
         __syncwarp();
+        OVDET_TR(0, 5);
       }
     }
   } else if (warp == 2) {
@@ -428,6 +468,7 @@ sim_fused_kernel(const __grid_constant__ LevelMaps amaps, const __grid_constant_
         const uint32_t s = ia % F_A_STAGES;
         const uint32_t ph = (ia / F_A_STAGES) & 1u;
         ptx::mbar_wait_lazy(as_empty0 + 8u * s, ph ^ 1u, lazy_ns);
+        OVDET_TR(4, 30);
         ptx::mbar_arrive_expect_tx_if(issue, as_full0 + 8u * s, IN16 ? F_A_STAGE_BYTES / 2 : F_A_STAGE_BYTES);
         ptx::tma_load_3d_if(issue, smem_a + s * F_A_STAGE_BYTES, map, as_full0 + 8u * s, tc.m0,
                             kb * F_BLOCK_K, tc.b);
@@ -469,11 +510,41 @@ sim_fused_kernel(const __grid_constant__ LevelMaps amaps, const __grid_constant_
 #pragma unroll
       for (int i = 0; i < 32; ++i) one[i] = 0u;
       one[0] = 0x00003F80u;                           // bf16 pair (1.0, 0.0)
-      ptx::tmem_st_32x32(tmem_base + ((uint32_t)(lg * 32) << 16) + (uint32_t)(F_A_COL + KB_IN * 32), one);
+      ptx::tmem_st_32x32(tmem_base + ((uint32_t)(lg * 32) << 16) + (uint32_t)(A_COL + KB_IN * 32), one);
       ptx::tmem_st_wait();
       ptx::tc_fence_before();
     }
+    // AHEAD2 (the resident dim = 512 cosine kernels): converted blocks are published TWO blocks late, so
+    // that at an anchor-tile boundary - where block kb of the A region is only released by the last N
+    // tile's MMAs - two blocks of the next tile are already sitting in registers and the conversion of
+    // block kb + 2 overlaps the wait for block kb's release.  The clock-stamp trace (tools/trace_fused.py)
+    // showed the MMA warp waiting ~3800 cycles per anchor tile for converted blocks: a block takes the
+    // converter ~550 cycles (the 32 KiB fp32 read alone is 256 cycles of shared-memory bandwidth) against
+    // 256 cycles of MMAs, and with one block in flight those 550 cycles were serial, eight times over.
+    constexpr bool AHEAD2 = !SPLIT3 && !PROJ && KB_T == 8 && OVDET_F_AHEAD2;
+    // blocks held in registers: two, or three where the kernel has the registers (384 threads, no second
+    // epilogue group): every block held is one ~550-cycle conversion less in the boundary's serial chain
+    constexpr int AH = !AHEAD2 ? 1 : ((EPI2 || OVDET_F_AHEAD2 == 2) ? 2 : 3);
+    uint32_t held[AH][32];                             // AHEAD2: blocks converted but not yet published
     uint32_t ia = 0, lt = 0;
+    // block `i` of the A region for anchor tile lt_: wait until the previous tile's MMAs have read it,
+    // store, publish
+    auto publish_at = [&](uint32_t lt_, int i, const uint32_t (&regs)[32], bool peeked) {
+      const int t = a_slot(lt_, i);
+      if (warp == 4) OVDET_TR(1, 12);
+      if (!peeked) ptx::mbar_wait_lazy(a_free0 + 8u * t, a_phase(lt_, i) ^ 1u, lazy_ns >> 1);
+      if (warp == 4) OVDET_TR(1, 13);
+      ptx::tc_fence_after();
+      ptx::tmem_st_32x32(tmem_base + ((uint32_t)(lg * 32) << 16) + (uint32_t)(A_COL + t * 32), regs);
+      ptx::tmem_st_wait();
+      ptx::tc_fence_before();
+      __syncwarp();
+      if (lane == 0) {
+        if constexpr (CG == 2) ptx::mbar_arrive_cluster(lead_a_ready0 + 8u * t);
+        else ptx::mbar_arrive(a_ready0 + 8u * t);
+      }
+      if (warp == 4) OVDET_TR(1, 14);
+    };
     for (int w = pair0; w < total_work; w += pair_stride, ++lt) {
       const int tile = (w / NSPLIT) * CG + (int)rank;
       const int nt_b = (w % NSPLIT) * NT / NSPLIT, nt_e = (w % NSPLIT + 1) * NT / NSPLIT;
@@ -481,31 +552,31 @@ sim_fused_kernel(const __grid_constant__ LevelMaps amaps, const __grid_constant_
       const TileCoord tc = decode_tile(p, tile);
       float ss0 = 0.f, ss1 = 0.f, ss2 = 0.f, ss3 = 0.f;
       float row_scale = 1.0f;                          // F16OP: power of two applied before the fp16 rounding
-      // block `t` of the A region: wait until the previous tile's MMAs have read it, store, publish
-      auto publish = [&](int i, const uint32_t (&regs)[32]) {
-        const int t = a_slot(lt, i);
-        ptx::mbar_wait_lazy(a_free0 + 8u * t, a_phase(lt, i) ^ 1u, lazy_ns >> 1);
-        ptx::tc_fence_after();
-        ptx::tmem_st_32x32(tmem_base + ((uint32_t)(lg * 32) << 16) + (uint32_t)(F_A_COL + t * 32), regs);
-        ptx::tmem_st_wait();
-        ptx::tc_fence_before();
-        __syncwarp();
-        if (lane == 0) {
-          if constexpr (CG == 2) ptx::mbar_arrive_cluster(lead_a_ready0 + 8u * t);
-          else ptx::mbar_arrive(a_ready0 + 8u * t);
-        }
-      };
+      auto publish = [&](int i, const uint32_t (&regs)[32]) { publish_at(lt, i, regs, false); };
 #pragma unroll
       for (int kb = 0; kb < KB_IN; ++kb, ++ia) {
         const uint32_t s = ia % F_A_STAGES;
-        ptx::mbar_wait_lazy(as_full0 + 8u * s, (ia / F_A_STAGES) & 1u, lazy_ns >> 1);
+        if (warp == 4) OVDET_TR(1, 10);
+        if constexpr (AHEAD2) {
+          // the register buffer this block converts into still holds the block two positions back.  Both
+          // barriers are polled before either result is needed: a try_wait on a completed barrier still
+          // takes ~100-150 cycles, and back to back those latencies were a third of the per-block chain.
+          bool freed = true;
+          if (kb >= AH) freed = ptx::mbar_try_wait(a_free0 + 8u * a_slot(lt, kb - AH), a_phase(lt, kb - AH) ^ 1u);
+          const bool landed = ptx::mbar_try_wait(as_full0 + 8u * s, (ia / F_A_STAGES) & 1u);
+          if (kb >= AH) publish_at(lt, kb - AH, held[kb % AH], freed);
+          if (!landed) ptx::mbar_wait_lazy(as_full0 + 8u * s, (ia / F_A_STAGES) & 1u, lazy_ns >> 1);
+        } else {
+          ptx::mbar_wait_lazy(as_full0 + 8u * s, (ia / F_A_STAGES) & 1u, lazy_ns >> 1);
+        }
+        if (warp == 4) OVDET_TR(1, 11);
         const float* col = a_stage_ptr + s * (F_A_STAGE_BYTES / 4) + arow;
         const __nv_bfloat16* col16 = reinterpret_cast<const __nv_bfloat16*>(a_stage_ptr + s * (F_A_STAGE_BYTES / 4)) + arow;
         auto ldx = [&](int k) -> float {
           if constexpr (IN16) return __bfloat162float(col16[k * F_BLOCK_M]);
           else return col[k * F_BLOCK_M];
         };
-        uint32_t packed[32];
+        uint32_t (&packed)[32] = held[kb % AH];
         uint32_t packed_lo[32];                            // dead (eliminated) unless SPLIT3
         if constexpr (F16OP) {
           if (kb == 0) {
@@ -541,9 +612,13 @@ sim_fused_kernel(const __grid_constant__ LevelMaps amaps, const __grid_constant_
           publish(3 * kb, packed);
           publish(3 * kb + 1, packed);
           publish(3 * kb + 2, packed_lo);
-        } else {
+        } else if constexpr (!AHEAD2) {
           publish(kb, packed);
         }
+      }
+      if constexpr (AHEAD2) {                          // the tile's last blocks
+#pragma unroll
+        for (int kb = KB_IN - AH; kb < KB_IN; ++kb) publish_at(lt, kb, held[kb % AH], false);
       }
       float inv = 1.0f / fmaxf(sqrtf((ss0 + ss1) + (ss2 + ss3)), 1e-12f);
       const int slot = lt % 3;
@@ -616,19 +691,21 @@ sim_fused_kernel(const __grid_constant__ LevelMaps amaps, const __grid_constant_
       bool a_released = false;
       for (int nt = nt_b; nt < nt_e; ++nt, ++acc_it) {
         if (EPI2 && (int)(acc_it & 1u) != eg) continue;
-        const int n0 = (nt - NG) * F_BLOCK_N;          // first class of a class tile
+        const int n0 = (nt - NG) * BN;                 // first class of a class tile
         const int n_valid = ntile_valid(nt);
         const int nchunks = (n_valid + 31) >> 5;
         const int as = acc_it & 1;
+        if ((warp & 3) == 0) OVDET_TR(2 + eg, 20);
         ptx::mbar_wait(t_full0 + 8u * as, (acc_it >> 1) & 1u);
+        if ((warp & 3) == 0) OVDET_TR(2 + eg, 21);
         ptx::tc_fence_after();
-        const uint32_t t_row = tmem_base + ((uint32_t)(lg * 32) << 16) + (uint32_t)(F_ACC_COL + as * F_BLOCK_N);
+        const uint32_t t_row = tmem_base + ((uint32_t)(lg * 32) << 16) + (uint32_t)(F_ACC_COL + as * BN);
         if (PROJ && nt < NG) {
           // G' tile: q += sum_j acc_j * x'_j, x' (bf16 pairs) read back from the A region
-          const uint32_t a_row = tmem_base + ((uint32_t)(lg * 32) << 16) + (uint32_t)F_A_COL;
+          const uint32_t a_row = tmem_base + ((uint32_t)(lg * 32) << 16) + (uint32_t)A_COL;
           uint32_t acc[32], xa[16];
           for (int c = 0; c < nchunks; ++c) {
-            const int j0 = nt * F_BLOCK_N + (c << 5);                  // k index of the chunk's first column
+            const int j0 = nt * BN + (c << 5);                         // k index of the chunk's first column
             ptx::tmem_ld_32x32(t_row + (uint32_t)(c << 5), acc);
             ptx::tmem_ld_32x32_x16(a_row + (uint32_t)(j0 >> 1), xa);
             ptx::tmem_ld_wait();
@@ -805,7 +882,7 @@ sim_fused_kernel(const __grid_constant__ LevelMaps amaps, const __grid_constant_
 
         uint32_t ra[32], rb[32];
         if constexpr (MODE == 1 && EPI2 && !PROJ) {
-          if (n_valid == F_BLOCK_N) {
+          if (n_valid == BN) {
             // Hot path of the materialised-logits kernel (full tile, bf16 logits through TMA stores, two
             // epilogue groups): straight-line over the four 32-column chunks, and - as in the scores-only
             // hot path below - the accumulator goes back to the MMA warp as soon as its last 32 columns
@@ -852,23 +929,25 @@ sim_fused_kernel(const __grid_constant__ LevelMaps amaps, const __grid_constant_
             ptx::tmem_ld_32x32(t_row + 32u, rb);
             emit_chunk(ra, 0);
             ptx::tmem_ld_wait();
-            ptx::tmem_ld_32x32(t_row + 64u, ra);
-            emit_chunk(rb, 1);
-            ptx::tmem_ld_wait();
-            ptx::tmem_ld_32x32(t_row + 96u, rb);
-            emit_chunk(ra, 2);
-            ptx::tmem_ld_wait();
+            if constexpr (BN == 128) {
+              ptx::tmem_ld_32x32(t_row + 64u, ra);
+              emit_chunk(rb, 1);
+              ptx::tmem_ld_wait();
+              ptx::tmem_ld_32x32(t_row + 96u, rb);
+              emit_chunk(ra, 2);
+              ptx::tmem_ld_wait();
+            }
             ptx::tc_fence_before();
             __syncwarp();
             if (lane == 0) {
               if constexpr (CG == 2) ptx::mbar_arrive_cluster(lead_t_empty0 + 8u * as);
               else ptx::mbar_arrive(t_empty0 + 8u * as);
             }
-            emit_chunk(rb, 3);
+            emit_chunk(rb, BN / 32 - 1);
             continue;
           }
         }
-        if (raw_mode && n_valid == F_BLOCK_N) {
+        if (raw_mode && n_valid == BN) {
           // Hot path (full tile, no logits): straight-line, and the accumulator is handed back to
           // the MMA warp as soon as its last 32 columns are in registers - the compare work on
           // that chunk runs after the arrive, off the MMA -> epilogue -> MMA critical chain.
@@ -903,19 +982,23 @@ sim_fused_kernel(const __grid_constant__ LevelMaps amaps, const __grid_constant_
           ptx::tmem_ld_32x32(t_row + 32u, rb);
           scan(ra, n0);
           ptx::tmem_ld_wait();
-          ptx::tmem_ld_32x32(t_row + 64u, ra);
-          scan(rb, n0 + 32);
-          ptx::tmem_ld_wait();
-          ptx::tmem_ld_32x32(t_row + 96u, rb);
-          scan(ra, n0 + 64);
-          ptx::tmem_ld_wait();
+          if constexpr (BN == 128) {
+            ptx::tmem_ld_32x32(t_row + 64u, ra);
+            scan(rb, n0 + 32);
+            ptx::tmem_ld_wait();
+            ptx::tmem_ld_32x32(t_row + 96u, rb);
+            scan(ra, n0 + 64);
+            ptx::tmem_ld_wait();
+          }
           ptx::tc_fence_before();
           __syncwarp();
           if (lane == 0) {
             if constexpr (CG == 2) ptx::mbar_arrive_cluster(lead_t_empty0 + 8u * as);
             else ptx::mbar_arrive(t_empty0 + 8u * as);
           }
-          scan(rb, n0 + 96);
+          if ((warp & 3) == 0) OVDET_TR(2 + eg, 22);
+          scan(rb, n0 + BN - 32);
+          if ((warp & 3) == 0) OVDET_TR(2 + eg, 23);
           continue;
         }
         ptx::tmem_ld_32x32(t_row, ra);
@@ -1182,13 +1265,15 @@ int fused_launch(const float* const* obj_embeds, const int64_t* hw, const int64_
   }
   for (int l = num_levels; l < F_MAX_LEVELS; ++l) maps.m[l] = maps.m[0];
   const int64_t kop = proj ? (int64_t)kb_in * F_BLOCK_K + 16 : (int64_t)kb * F_BLOCK_K;
+  // classes per N tile of this launch (kernel: BN)
+  const int bn = (cg == 2 && !proj && !split3 && OVDET_F_BN64) ? 64 : F_BLOCK_N;
   const int64_t cpad = ceil_div<int64_t>(classes, F_BLOCK_N) * F_BLOCK_N;
   const int64_t op_rows = proj ? cpad + kop : classes;
   for (int l = 0; l < (proj ? num_levels : 1); ++l) {
     const int64_t tb = text_batched ? batch : 1;
     cuuint64_t dims[3] = {(cuuint64_t)kop, (cuuint64_t)op_rows, (cuuint64_t)tb};
     cuuint64_t strides[2] = {(cuuint64_t)kop * 2, (cuuint64_t)op_rows * (cuuint64_t)kop * 2};
-    cuuint32_t box[3] = {(cuuint32_t)F_BLOCK_K, (cuuint32_t)(F_BLOCK_N / cg), 1};
+    cuuint32_t box[3] = {(cuuint32_t)F_BLOCK_K, (cuuint32_t)(bn / cg), 1};
     const void* op = proj ? level_ops[l] : text_op;
     CUresult r = encode3(enc, &bmaps.m[l], CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, op, dims, strides, box,
                          CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B);
@@ -1227,7 +1312,7 @@ int fused_launch(const float* const* obj_embeds, const int64_t* hw, const int64_
   p.ng_tiles = proj ? (int)ceil_div<int64_t>(kop, F_BLOCK_N) : 0;
   p.cpad = (int)cpad;
   p.kop = (int)kop;
-  p.n_tiles = (int)ceil_div<int64_t>(classes, F_BLOCK_N) + p.ng_tiles;
+  p.n_tiles = (int)ceil_div<int64_t>(classes, bn) + p.ng_tiles;
   p.text_batched = text_batched ? 1 : 0;
   p.alpha = alpha;
   p.beta = beta;
@@ -1265,6 +1350,10 @@ int fused_launch(const float* const* obj_embeds, const int64_t* hw, const int64_
   // epilogue, 16 / 32 back-off of the non-critical waits off / 256 ns
   static const int dbg_env = []() { const char* e = getenv("OVDET_DBG"); return e ? atoi(e) : 0; }();
   p.dbg = dbg_env;
+#ifdef OVDET_TRACE
+  static const unsigned long long trace_env = []() { const char* e = getenv("OVDET_TRACE_PTR"); return e ? strtoull(e, nullptr, 0) : 0ull; }();
+  p.trace = reinterpret_cast<unsigned long long*>(trace_env);
+#endif
 
   // every (shape variant, epilogue mode) instantiation the dispatch below can pick
   const int mode = vp ? 2 : (logits ? 1 : 0);
@@ -1286,7 +1375,8 @@ int fused_launch(const float* const* obj_embeds, const int64_t* hw, const int64_
   if (int rc = once_per_device(1, []() -> int {
 #define OVDET_SET_SMEM(KB, S3, CGV, PR, I16, MD, E2, F16)                                                  \
         OVDET_CUDA_TRY(cudaFuncSetAttribute(sim_fused_kernel<KB, S3, CGV, PR, I16, MD, E2, F16>,        \
-                                            cudaFuncAttributeMaxDynamicSharedMemorySize, FSmem<CGV, (PR && CGV == 2)>::bytes));
+                                            cudaFuncAttributeMaxDynamicSharedMemorySize,                   \
+                                            FSmem<CGV, (PR && CGV == 2), (CGV == 2 && !PR && !S3 && KB == 8 && OVDET_F_BN64)>::bytes));
         OVDET_FOR_EACH_FUSED(OVDET_SET_SMEM)
 #undef OVDET_SET_SMEM
         return OVDET_OK;
@@ -1322,7 +1412,7 @@ int fused_launch(const float* const* obj_embeds, const int64_t* hw, const int64_
   if (!launched && v_kb == KB && (split3 != 0) == S3 && cg == CGV && (proj != 0) == PR &&               \
       (in_bf16 != 0) == I16 && mode == MD && epi2 == E2 && (f16_operands != 0) == F16) {                                            \
     cfg.blockDim = dim3(E2 ? F_THREADS + 128 : F_THREADS);                                              \
-    cfg.dynamicSmemBytes = FSmem<CGV, (PR && CGV == 2)>::bytes;                                         \
+    cfg.dynamicSmemBytes = FSmem<CGV, (PR && CGV == 2), (CGV == 2 && !PR && !S3 && KB == 8 && OVDET_F_BN64)>::bytes; \
     OVDET_CUDA_TRY(cudaLaunchKernelEx(&cfg, sim_fused_kernel<KB, S3, CGV, PR, I16, MD, E2, F16>, maps, bmaps, cmaps, p)); \
     launched = true;                                                                                    \
   }

@@ -51,8 +51,9 @@ class HeadConfig:
     conf_threshold: float = 0.25
     iou_threshold: float = 0.45
     # "auto" (default): inside the fp32 bar of the reference's arithmetic (|dlogit| <= 1e-4) at the best speed
-    #         the shape allows - "fp32" where its fused streaming mode applies (<= 128 classes), else "fp16"
-    #         (embed_dim 512, H*W multiples of 4), else "fp32" through the two-kernel path;
+    #         the shape allows - "fp16" for embed_dim 512 with TMA-addressable levels (one tensor-core pass;
+    #         at 80 prompts 0.22 ms against 0.35 ms for the three-pass mode, batch 64), else "fp32" (the fused
+    #         streaming three-pass mode up to 128 classes, the two-kernel path above);
     # "bf16": one tensor-core pass, |dlogit| <~ 8e-3 (the BASELINE metric's configuration; opt-in);
     # "fp16": one pass at the same rate with fp16 operands and per-row power-of-two scaling, |dlogit| <~ 1e-4
     #         (embed_dim 512, fp32 activations, TMA-addressable levels);
@@ -74,11 +75,9 @@ def resolve_precision(config: "HeadConfig", level_shapes, num_classes: int, proj
         return "bf16"                       # the projected similarity is a single bf16 pass by construction
     d = config.embed_dim
     tma_ok = all((h * w) % 4 == 0 for h, w in level_shapes) and len(level_shapes) <= 4
-    if config.fused and tma_ok and d % 64 == 0 and d <= 512 and (num_classes <= 128 or d <= 128):
-        return "fp32"                       # fused streaming three-pass mode: one launch, ~1e-5
     if config.fused and tma_ok and d == 512 and config.logits_dtype != "fp32":
-        return "fp16"
-    return "fp32"
+        return "fp16"                       # one pass of the CTA-pair kernel, ~1e-5 (max 7e-5)
+    return "fp32"                           # three passes: fused streaming mode (<= 128 classes) or K1 -> K2
 
 
 class HeadPipeline:

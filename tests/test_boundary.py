@@ -263,7 +263,9 @@ def test_yoloclip_detector_detect_vs_live_reference(fx, cuda_device, exact_convs
     assert [r["box"] for r in records] == fx["det_box"].tolist()
     assert [r["class_id"] for r in records] == fx["det_class"].tolist()
     assert [r["class_name"] for r in records] == [str(n) for n in fx["det_name"]]
-    np.testing.assert_allclose([r["score"] for r in records], fx["det_score"], rtol=0, atol=2e-5)
+    # precision "auto" = the fp16 operand tier at embed_dim 512: |dlogit| <= 1e-4 (measured max 7e-5 over 1e7
+    # logits), ten times inside north_star's 1e-3 relative bar at these score magnitudes
+    np.testing.assert_allclose([r["score"] for r in records], fx["det_score"], rtol=0, atol=1e-4)
     assert all(isinstance(r["score"], float) and isinstance(r["class_id"], int) for r in records)
     # second call: cached pipeline, same answer; a path on disk goes through cv2.imread like the reference
     assert det.detect(image) == records
