@@ -321,7 +321,8 @@ sim_fused_kernel(const __grid_constant__ LevelMaps amaps, const __grid_constant_
   const uint32_t lead_b_full0 = CG == 2 ? ptx::map_to_cta(b_full0, 0) : b_full0;
   const uint32_t lead_a_ready0 = CG == 2 ? ptx::map_to_cta(a_ready0, 0) : a_ready0;
   const uint32_t lead_t_empty0 = CG == 2 ? ptx::map_to_cta(t_empty0, 0) : t_empty0;
-  const int KB_IN = KB_T ? KB_T : p.kb_in;                       // fp32 input blocks per anchor tile
+  // (KB_T counts the blocks the MMA walks: with SPLIT3 three per input block)
+  const int KB_IN = KB_T ? (SPLIT3 ? KB_T / 3 : KB_T) : p.kb_in;  // fp32 input blocks per anchor tile
   const int KB = PROJ ? KB_IN + 1 : (KB_T ? KB_T : p.kb);        // k blocks the MMA walks
   const int KB_A = PROJ ? KB_IN : KB;                            // A blocks rewritten per anchor tile
   // The A region is a ring of R slots of 32 columns.  Resident modes: R = KB_A, block i lives in
@@ -381,7 +382,7 @@ sim_fused_kernel(const __grid_constant__ LevelMaps amaps, const __grid_constant_
             for (int j = 0; j < KPS; ++j)
               if (j < subs)
                 ptx::tma_load_3d_pair_if(issue, smem_b + s * F_B_STAGE_BYTES + j * F_B_SUB_BYTES, bmap,
-                                         lead_b_full0 + 8u * s, (sb * KPS + j) * F_BLOCK_K,
+                                         lead_b_full0 + 8u * s, b_kblock(sb * KPS + j) * F_BLOCK_K,
                                          row0 + (int)rank * n_half, tb);
           }
         }
@@ -1225,7 +1226,12 @@ int fused_launch(const float* const* obj_embeds, const int64_t* hw, const int64_
   // CTA pairs (cta_group::2) for the dim = 512 similarity and the hidden = 256 projected one;
   // OVDET_FUSED_CG=1 forces single CTAs
   static const int cg_env = []() { const char* e = getenv("OVDET_FUSED_CG"); return e ? atoi(e) : 2; }();
-  const int cg = (cg_env == 2 && !split3 && ((!proj && kb == 8) || (proj && kb_in == 4))) ? 2 : 1;
+  // ... and for the attention row's small resident shapes (hidden <= 128: 1-2 k blocks, 3 or 6 with the
+  // three-pass recipe; scores only): there the text tile is re-read from L2 once per anchor tile for very
+  // little MMA work, which is the L2 -> SM bound CTA pairs halve
+  const bool small_pair = !proj && !logits && !vp && !in_bf16 && !f16_operands && row_max && !row_arg &&
+                          ((!split3 && (kb == 1 || kb == 2)) || (split3 && (kb == 3 || kb == 6)));
+  const int cg = (cg_env == 2 && ((!split3 && ((!proj && kb == 8) || (proj && kb_in == 4))) || small_pair)) ? 2 : 1;
   EncodeTiledFn enc = nullptr;
   FusedParams p{};
   LevelMaps maps, bmaps, cmaps;
@@ -1371,7 +1377,9 @@ int fused_launch(const float* const* obj_embeds, const int64_t* hw, const int64_
   X(0, false, 1, true, false, 0, false, false)                                                                \
   X(0, false, 1, false, true, 0, false, false)  X(0, false, 1, false, true, 1, false, false)  \
   X(8, false, 2, false, false, 0, false, true) X(8, false, 2, false, false, 1, false, true)            \
-  X(8, false, 2, false, false, 1, true, true)
+  X(8, false, 2, false, false, 1, true, true)                                                          \
+  X(1, false, 2, false, false, 0, false, false) X(2, false, 2, false, false, 0, false, false)          \
+  X(3, true, 2, false, false, 0, false, false)  X(6, true, 2, false, false, 0, false, false)
   if (int rc = once_per_device(1, []() -> int {
 #define OVDET_SET_SMEM(KB, S3, CGV, PR, I16, MD, E2, F16)                                                  \
         OVDET_CUDA_TRY(cudaFuncSetAttribute(sim_fused_kernel<KB, S3, CGV, PR, I16, MD, E2, F16>,        \
@@ -1384,11 +1392,12 @@ int fused_launch(const float* const* obj_embeds, const int64_t* hw, const int64_
   // second epilogue warpgroup (CTA-pair scores-only kernels): OVDET_EPI2 bit 0 = projected mode (the
   // epilogue is on its critical path: K = 272 per tile), bit 1 = cosine mode, bit 2 = bf16 logits (TMA stores)
   static const int epi2_env = []() { const char* e = getenv("OVDET_EPI2"); return e ? atoi(e) : 5; }();
-  const bool epi2 = cg == 2 && ((mode == 0 && ((proj && (epi2_env & 1)) || (!proj && (epi2_env & 2)))) ||
+  // (measured and dropped: a second group for the attention row's CTA-pair kernels - 0.140 vs 0.136 ms at P3)
+  const bool epi2 = cg == 2 && ((mode == 0 && ((proj && (epi2_env & 1)) || (!proj && kb == 8 && (epi2_env & 2)))) ||
                                 (mode == 1 && logits_tma && (epi2_env & 4))) &&
                     !(f16_operands && mode == 0);
   // shape variant of this launch
-  const int v_kb = cg == 2 ? (proj ? 4 : 8) : ((!in_bf16 && !proj && !split3 && p.kb == 8) ? 8 : 0);
+  const int v_kb = cg == 2 ? (proj ? 4 : p.kb) : ((!in_bf16 && !proj && !split3 && p.kb == 8) ? 8 : 0);
   cudaLaunchConfig_t cfg{};
   cudaLaunchAttribute attr[1];
   cfg.blockDim = dim3(F_THREADS);
