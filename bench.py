@@ -162,11 +162,14 @@ def measured_peaks():
     return {"tflops": 1400.0, "tflops_burst": 1590.0, "hbm_gbs": 6650.0, "source": "fallback"}
 
 
+NCU_CAPTURE = "r2_ncu_full_main_b256.json"     # ncu --set full of `bench.py --profile` at the current build
+
+
 def ncu_traffic(kernel_substr: str, batch: int):
     """DRAM bytes per launch (dram__bytes_read.sum + dram__bytes_write.sum) of the dominant kernel
     from the committed `ncu --set full` capture of this same workload (profiles/, batch 256);
     None when the run's shape differs from the captured one."""
-    path = os.path.join(ROOT, "profiles", "r1_ncu_full_pipeline_b256_v7.json")
+    path = os.path.join(ROOT, "profiles", NCU_CAPTURE)
     if batch != 256 or (IMAGE_SIZE, NUM_CLASSES) != (640, 1203) or not os.path.exists(path):
         return None
     scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
@@ -601,7 +604,7 @@ def run_ours(args):
         roofline["frac_of_nominal"] = roofline["achieved"] / (2250.0 if roofline["bound"] == "tensor" else 8000.0)
         plain = not proj and not args.per_image_text and args.logits == "none"
         roofline.update({"traffic": ncu_traffic("sim_fused" if fused else "sim_gemm", batch) if plain else None,
-                         "traffic_source": "profiles/r1_ncu_full_pipeline_b256_v7.json (ncu --set full, bytes per launch)",
+                         "traffic_source": f"profiles/{NCU_CAPTURE} (ncu --set full, bytes per launch)",
                          "algorithmic_bytes": alg_bytes, "algorithmic_flops": flops,
                          "ms_per_launch": stages["similarity"],
                          "ms_per_launch_source": "CUDA events around the kernel in the per-stage pass (same steps, "

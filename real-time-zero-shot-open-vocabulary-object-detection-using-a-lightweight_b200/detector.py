@@ -71,12 +71,17 @@ class Detector:
         scores = _to_device(outputs["scores"], dev, torch.float32)
         classes = _to_device(outputs["class_ids"], dev, torch.int32)
         batch = scores.shape[0]
-        if activation == "sigmoid":
-            scores = torch.sigmoid(scores)
-        mask = _pack_mask(scores > self.conf_threshold)
         scale = torch.from_numpy(np.asarray([np.float32(s) for s in scale_factors], dtype=np.float32)).to(dev)
         wh = torch.tensor([[float(w), float(h)] for (h, w) in orig_sizes], dtype=torch.float32, device=dev)
         assert scale.numel() == batch and wh.shape[0] == batch
+        if activation == "none" and scores.shape[1] <= 65536:
+            # the reference's case: K4 evaluates `scores > conf` itself (detector.py:184), no mask tensor
+            return ops.nms_batched(boxes, scores, classes, None, scale=scale, clip_wh=wh,
+                                   iou_thr=self.iou_threshold, class_aware=class_aware, topk=topk,
+                                   max_det=max_det, conf=self.conf_threshold)
+        if activation == "sigmoid":
+            scores = torch.sigmoid(scores)
+        mask = _pack_mask(scores > self.conf_threshold)
         return ops.nms_batched(boxes, scores, classes, mask, scale=scale, clip_wh=wh,
                                iou_thr=self.iou_threshold, class_aware=class_aware, topk=topk,
                                max_det=max_det)
