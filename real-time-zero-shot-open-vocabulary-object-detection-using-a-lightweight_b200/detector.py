@@ -287,8 +287,8 @@ class YOLOCLIPDetector(Detector):
     Everything from the letterbox to the detection records except that model runs in
     ``libovdet.so``: P1 letterbox -> [model] -> K1+K2 fused similarity -> K3 decode -> K4 NMS ->
     int-truncated records.  ``precision``: ``"auto"`` (default: every score within 1e-4 of the
-    reference's fp32 arithmetic - the fused three-pass mode up to 128 prompts, the fp16 tensor-core tier
-    above), ``"fp32"``, ``"fp16"`` or ``"bf16"`` (|dscore| <~ 8e-3)."""
+    reference's fp32 arithmetic - the fp16 tensor-core tier at embed_dim 512, the three-pass recipe
+    otherwise), ``"fp32"``, ``"fp16"`` or ``"bf16"`` (|dscore| <~ 8e-3)."""
 
     def __init__(self, model_path: Optional[str] = None, class_names: Optional[List[str]] = None,
                  vocab_path: Optional[str] = None, device=None, image_size: Tuple[int, int] = (640, 640),

@@ -174,8 +174,9 @@ def _similarity_levels(obj_embeds: Sequence[torch.Tensor], text_embeddings: torc
     classes = text_embeddings.shape[-2]
     levels = [e if e.dtype in (torch.float32, torch.bfloat16) else e.float() for e in obj_embeds]
     if precision == "auto":             # inside the fp32 bar at the best speed the shape allows
-        precision = ("fp32" if ops.fused_fp32_supported(levels, classes) or want_logits else
-                     "fp16" if ops.fused_fp16_supported(levels) else "fp32")
+        # (the same rule as pipeline.resolve_precision: the fp16 tier - one tensor-core pass, |dlogit| <= 1e-4 -
+        # wherever its kernel takes the shape; the three-pass recipe otherwise and for fp32 logits)
+        precision = "fp16" if (ops.fused_fp16_supported(levels) and not want_logits) else "fp32"
     if precision == "fp16" and not ops.fused_fp16_supported(levels):
         precision = "fp32"              # shapes outside the fp16 tier: the (more accurate) three-pass recipe
     split = precision == "fp32"
@@ -276,8 +277,9 @@ def forward_tail(pan_features: Sequence[torch.Tensor], text_embeddings: torch.Te
     ``text_embeddings`` (as handed in), ``box_preds`` (list of ``[B, 4R, H, W]``).
 
     ``precision``: ``"auto"`` (default) keeps every score within 1e-4 of the reference's fp32 arithmetic
-    at the best speed the shape allows - the fused three-pass mode up to 128 prompts, the fp16 tensor-core
-    tier (one pass, bf16 speed) above; ``"fp32"`` / ``"fp16"`` / ``"bf16"`` force a recipe."""
+    at the best speed the shape allows - the fp16 tensor-core tier (one pass, bf16 speed) at embed_dim 512
+    with TMA-addressable levels, the three-pass recipe otherwise; ``"fp32"`` / ``"fp16"`` / ``"bf16"`` force
+    a recipe."""
     assert precision in PRECISIONS
     assert len(pan_features) == len(contrastive_heads)
     # yolo_clip.py:177-186 calls head(feat) and drops the second output (the head's own box
