@@ -527,6 +527,7 @@ sim_fused_kernel(const __grid_constant__ LevelMaps amaps, const __grid_constant_
     // epilogue group): every block held is one ~550-cycle conversion less in the boundary's serial chain
     constexpr int AH = !AHEAD2 ? 1 : ((EPI2 || OVDET_F_AHEAD2 == 2) ? 2 : 3);
     uint32_t held[AH][32];                             // AHEAD2: blocks converted but not yet published
+    bool poll_freed = false, poll_landed = false;      // AHEAD2: results of the polls issued one block earlier
     uint32_t ia = 0, lt = 0;
     // block `i` of the A region for anchor tile lt_: wait until the previous tile's MMAs have read it,
     // store, publish
@@ -559,14 +560,13 @@ sim_fused_kernel(const __grid_constant__ LevelMaps amaps, const __grid_constant_
         const uint32_t s = ia % F_A_STAGES;
         if (warp == 4) OVDET_TR(1, 10);
         if constexpr (AHEAD2) {
-          // the register buffer this block converts into still holds the block two positions back.  Both
-          // barriers are polled before either result is needed: a try_wait on a completed barrier still
-          // takes ~100-150 cycles, and back to back those latencies were a third of the per-block chain.
-          bool freed = true;
-          if (kb >= AH) freed = ptx::mbar_try_wait(a_free0 + 8u * a_slot(lt, kb - AH), a_phase(lt, kb - AH) ^ 1u);
-          const bool landed = ptx::mbar_try_wait(as_full0 + 8u * s, (ia / F_A_STAGES) & 1u);
-          if (kb >= AH) publish_at(lt, kb - AH, held[kb % AH], freed);
-          if (!landed) ptx::mbar_wait_lazy(as_full0 + 8u * s, (ia / F_A_STAGES) & 1u, lazy_ns >> 1);
+          // the register buffer this block converts into still holds the block AH positions back.  Both of
+          // this iteration's barriers were POLLED DURING THE PREVIOUS CONVERSION (poll_* below): a try_wait
+          // on a completed barrier still takes 150-180 cycles in this kernel (tools/trace_fused.py), which
+          // in the boundary's serial chain was a third of every block's time.  A poll that came back true
+          // is final; one that came back false is followed by the real wait.
+          if (kb >= AH) publish_at(lt, kb - AH, held[kb % AH], poll_freed);
+          if (!poll_landed) ptx::mbar_wait_lazy(as_full0 + 8u * s, (ia / F_A_STAGES) & 1u, lazy_ns >> 1);
         } else {
           ptx::mbar_wait_lazy(as_full0 + 8u * s, (ia / F_A_STAGES) & 1u, lazy_ns >> 1);
         }
@@ -579,6 +579,13 @@ sim_fused_kernel(const __grid_constant__ LevelMaps amaps, const __grid_constant_
         };
         uint32_t (&packed)[32] = held[kb % AH];
         uint32_t packed_lo[32];                            // dead (eliminated) unless SPLIT3
+        if constexpr (AHEAD2) {
+          // polls for the NEXT iteration (or the tile's closing publishes): issued now, consumed after
+          // this block's ~400 cycles of shared-memory reads and packing
+          const int nb = kb + 1;                           // next block of this tile, or KB_IN = the closing publishes
+          poll_freed = nb >= AH ? ptx::mbar_try_wait(a_free0 + 8u * a_slot(lt, nb - AH), a_phase(lt, nb - AH) ^ 1u) : true;
+          poll_landed = ptx::mbar_try_wait(as_full0 + 8u * ((ia + 1u) % F_A_STAGES), ((ia + 1u) / F_A_STAGES) & 1u);
+        }
         if constexpr (F16OP) {
           if (kb == 0) {
             // the row's power-of-two scale from eight samples of its first block: 2^(2 - exponent of the
@@ -619,7 +626,7 @@ sim_fused_kernel(const __grid_constant__ LevelMaps amaps, const __grid_constant_
       }
       if constexpr (AHEAD2) {                          // the tile's last blocks
 #pragma unroll
-        for (int kb = KB_IN - AH; kb < KB_IN; ++kb) publish_at(lt, kb, held[kb % AH], false);
+        for (int kb = KB_IN - AH; kb < KB_IN; ++kb) publish_at(lt, kb, held[kb % AH], kb == KB_IN - AH ? poll_freed : false);
       }
       float inv = 1.0f / fmaxf(sqrtf((ss0 + ss1) + (ss2 + ss3)), 1e-12f);
       const int slot = lt % 3;

@@ -179,6 +179,10 @@ def _check_forward_dict(out, fx, text, precision):
     if precision == "fp32":
         assert err <= 1e-3 * ref_scores.abs().max().item(), err        # north_star: 1e-3 relative
         assert err <= 2e-5, err                                       # what the three-pass product measures
+    elif precision == "auto":
+        # the default: the fp16 operand tier at embed_dim 512 - still inside north_star's fp32 bar
+        assert err <= 1e-3 * ref_scores.abs().max().item(), err
+        assert err <= 1e-4, err
     else:
         assert err <= 8e-3, err                                       # bf16 bar, stated separately
     ids = out["class_ids"].cpu()
@@ -186,6 +190,10 @@ def _check_forward_dict(out, fx, text, precision):
     ref_ids = torch.from_numpy(fx["fwd_class_ids"])
     if precision == "fp32":
         assert torch.equal(ids, ref_ids)
+    elif precision == "auto":
+        # an argmax may only differ where the reference's own top two classes are closer than the error bar
+        diff = ids != ref_ids
+        assert diff.float().mean() <= 0.01, diff.float().mean()
     else:
         assert (ids == ref_ids).float().mean() >= 0.9
     torch.testing.assert_close(out["boxes"].cpu(), torch.from_numpy(fx["fwd_boxes"]), rtol=1e-4, atol=1e-3)
@@ -223,7 +231,12 @@ def test_patch_yolo_clip_forward_vs_live_reference(fx, cuda_device, exact_convs)
     """INTEGRATION.md route A: the two-line patch of an existing model object."""
     from ovdet.heads import patch_yolo_clip
     model, pan, text = _replay_model(fx, "fwd", cuda_device)
-    patch_yolo_clip(model)
+    patch_yolo_clip(model)                                  # precision="auto"
+    assert model.ovdet_precision == "auto"
+    with torch.no_grad():
+        out = model(torch.zeros(2, 3, 64, 64, device=cuda_device))
+    _check_forward_dict(out, fx, text, "auto")
+    patch_yolo_clip(model, precision="fp32")                # the three-pass recipe: the tight bar, equal class ids
     with torch.no_grad():
         out = model(torch.zeros(2, 3, 64, 64, device=cuda_device))
     _check_forward_dict(out, fx, text, "fp32")
