@@ -132,6 +132,58 @@ l2norm_text_kernel(const float* __restrict__ t, int64_t total_rows, int classes,
   }
 }
 
+// The same for rows of 128 * nv floats (nv <= 8) that start 16-byte aligned: the row is read ONCE with
+// 16-byte loads (4 * nv per lane, kept in registers) and written with 8-byte stores.  This is the
+// per-image-text case (text [B, C, 512] from the neck, model/repvl_pan.py:173-182: batch * classes =
+// 308 k rows per step at the benchmark's shape), where the scalar kernel above - two passes over the
+// row, 4-byte loads, 2-byte stores - ran at 0.6 of the HBM bandwidth.
+template <int SEG>
+__global__ void __launch_bounds__(256)
+l2norm_text_vec_kernel(const float* __restrict__ t, int64_t total_rows, int classes, int nv,
+                       int64_t stride_b, int64_t stride_c, __nv_bfloat16* __restrict__ operand,
+                       int kop, float* __restrict__ inv_norm) {
+  const int64_t row = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (row >= total_rows) return;
+  const int64_t b = row / classes, c = row % classes;
+  const float4* src = reinterpret_cast<const float4*>(t + b * stride_b + c * stride_c) + lane;
+  const int dim = nv * 128;
+  float4 v[8];
+  float ss = 0.f;
+#pragma unroll
+  for (int j = 0; j < 8; ++j)
+    if (j < nv) v[j] = ld_stream_f32x4(src + 32 * j);
+#pragma unroll
+  for (int j = 0; j < 8; ++j)
+    if (j < nv) {
+      ss = fmaf(v[j].x, v[j].x, ss); ss = fmaf(v[j].y, v[j].y, ss);
+      ss = fmaf(v[j].z, v[j].z, ss); ss = fmaf(v[j].w, v[j].w, ss);
+    }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
+  const float denom = fmaxf(sqrtf(ss), 1e-12f);
+  if (inv_norm != nullptr && lane == 0) inv_norm[row] = 1.0f / denom;
+  __nv_bfloat16* dst = operand + row * kop + 4 * lane;
+#pragma unroll
+  for (int j = 0; j < 8; ++j)
+    if (j < nv) {
+      const float f0 = __fdiv_rn(v[j].x, denom), f1 = __fdiv_rn(v[j].y, denom);
+      const float f2 = __fdiv_rn(v[j].z, denom), f3 = __fdiv_rn(v[j].w, denom);
+      if (SEG == 0) {
+        *reinterpret_cast<uint2*>(dst + 128 * j) = make_uint2(pack_f16x2_sat(f0 * 16.0f, f1 * 16.0f),
+                                                              pack_f16x2_sat(f2 * 16.0f, f3 * 16.0f));
+        continue;
+      }
+      const uint32_t h01 = pack_bf16x2(f0, f1), h23 = pack_bf16x2(f2, f3);
+      *reinterpret_cast<uint2*>(dst + 128 * j) = make_uint2(h01, h23);
+      if (SEG >= 2)
+        *reinterpret_cast<uint2*>(dst + dim + 128 * j) =
+            make_uint2(pack_bf16x2(f0 - __uint_as_float(h01 << 16), f1 - __uint_as_float(h01 & 0xffff0000u)),
+                       pack_bf16x2(f2 - __uint_as_float(h23 << 16), f3 - __uint_as_float(h23 & 0xffff0000u)));
+      if (SEG == 3) *reinterpret_cast<uint2*>(dst + 2 * dim + 128 * j) = make_uint2(h01, h23);
+    }
+}
+
 // Raw (un-normalised) text rows -> bf16 operand, zero padded to `dpad` columns per segment.
 // segments == 1: [hi]; segments == 3: [hi | lo | hi] with lo = bf16(x - hi), the layout the
 // three-pass (fp32-accurate) mode of the fused kernel multiplies against [hi | hi | lo].
@@ -205,6 +257,18 @@ extern "C" int ovdet_l2norm_text(const float* t, int64_t batch, int64_t classes,
   if (total == 0) return OVDET_OK;
   auto* op = static_cast<__nv_bfloat16*>(operand);
   const unsigned grid = (unsigned)ceil_div<int64_t>(total, 8);
+  // rows of 128 * nv floats, 16-byte aligned (and 8-byte aligned operand rows): the vectorised kernel
+  if (dim % 128 == 0 && dim <= 1024 && !((uintptr_t)t & 15) && !(stride_b & 3) && !(stride_c & 3) &&
+      !((uintptr_t)operand & 7) && !(kop & 3)) {
+    const int nv = (int)(dim / 128);
+    auto s_ = as_stream(stream);
+    if (split == 3) l2norm_text_vec_kernel<0><<<grid, 256, 0, s_>>>(t, total, (int)classes, nv, stride_b, stride_c, op, (int)kop, inv_norm);
+    else if (split == 2) l2norm_text_vec_kernel<3><<<grid, 256, 0, s_>>>(t, total, (int)classes, nv, stride_b, stride_c, op, (int)kop, inv_norm);
+    else if (split == 1) l2norm_text_vec_kernel<2><<<grid, 256, 0, s_>>>(t, total, (int)classes, nv, stride_b, stride_c, op, (int)kop, inv_norm);
+    else l2norm_text_vec_kernel<1><<<grid, 256, 0, s_>>>(t, total, (int)classes, nv, stride_b, stride_c, op, (int)kop, inv_norm);
+    OVDET_LAUNCH_CHECK();
+    return OVDET_OK;
+  }
   if (split == 3)
     l2norm_text_kernel<0><<<grid, 256, 0, as_stream(stream)>>>(t, total, (int)classes, (int)dim,
                                                                stride_b, stride_c, op, (int)kop, inv_norm);
