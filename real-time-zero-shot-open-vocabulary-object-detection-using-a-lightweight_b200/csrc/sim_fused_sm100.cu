@@ -53,6 +53,9 @@ constexpr int F_BLOCK_N = 128;
 constexpr int F_BLOCK_K = 64;
 constexpr int F_MAX_KB = 8;                       // dim <= 512: A fills 256 TMEM columns
 constexpr int F_MAX_SLOTS = 12;                   // slots of the A ring (BN64: 12 x 32 columns)
+#ifndef OVDET_F_CONV8
+#define OVDET_F_CONV8 1                          // eight converter warps, half a k block each (see CONV8 in the kernel)
+#endif
 #ifndef OVDET_F_BN64
 #define OVDET_F_BN64 0                           // CTA-pair cosine kernels: 64-class N tiles, 12-slot A ring (see BN64)
 #endif
@@ -101,7 +104,7 @@ struct FSmem {
   static constexpr int epi_warp_bytes = 32 * F_VPITCH * 4;           // 4608: fp32 staging, or two 2 KiB TMA-store buffers
   static constexpr int epi_bytes = 4 * epi_warp_bytes;
   static constexpr int norm_off = epi_off + epi_bytes;
-  static constexpr int norm_bytes = 3 * F_BLOCK_M * 4;
+  static constexpr int norm_bytes = 3 * 3 * F_BLOCK_M * 4;           // 3 tiles in flight x (two partial sums of squares, row scale)
   static constexpr int xbuf_off = norm_off + norm_bytes;              // EPI2: group 1's partial rows, two parities
   static constexpr int xbuf_bytes = 2 * 3 * F_BLOCK_M * 4;
   static constexpr int bar_off = xbuf_off + xbuf_bytes;
@@ -232,8 +235,8 @@ __device__ __forceinline__ TileCoord decode_tile(const FusedParams& p, int tile)
 // exceed 8000 x that maximum saturate at +-65504 (finite).  The text operand carries the unit rows
 // times 16 (ovdet_l2norm_text, split = 3); the 1/16 goes into the row scale.
 template <int KB_T, bool SPLIT3, int CG, bool PROJ, bool IN16 = false, int MODE = 0, bool EPI2 = false,
-          bool F16OP = false>
-__global__ void __launch_bounds__(EPI2 ? F_THREADS + 128 : F_THREADS, 1)
+          bool F16OP = false, bool C8 = false>
+__global__ void __launch_bounds__((EPI2 || C8) ? F_THREADS + 128 : F_THREADS, 1)
 sim_fused_kernel(const __grid_constant__ LevelMaps amaps, const __grid_constant__ LevelMaps bmaps,
                  const __grid_constant__ LevelMaps cmaps, const FusedParams p) {
   // BN64: N tiles of 64 classes.  Tensor memory then holds two 64-column accumulators and a TWELVE-slot A
@@ -243,6 +246,19 @@ sim_fused_kernel(const __grid_constant__ LevelMaps amaps, const __grid_constant_
   // the 8-slot ring every block of the next tile had to wait for the last N tile's MMAs on the same slot
   // and the converter - ~550 cycles per block against 256 cycles of MMAs - left the tensor pipe idle for
   // ~2800 cycles per anchor tile (tools/trace_fused.py, profiles/r2_trace_*.txt).
+  // CONV8 (the dim = 512 cosine kernels without a second epilogue group): EIGHT converter warps - warps
+  // 12-15 join warps 4-7, each warp converts HALF of every 64-k block (32 k = 16 TMEM columns of its 32
+  // rows) and holds FOUR half blocks in registers.  The boundary between anchor tiles is a serial chain in
+  // the converter (tools/trace_fused.py: ~6000 cycles for 8 publishes + 5 conversions of ~600 cycles with
+  // four warps at 96 B/clk of shared-memory loads); with eight warps a conversion takes half as long,
+  // the shared-memory pipe runs at its 128 B/clk, and four blocks instead of three are ready before
+  // the boundary begins.  The sum of squares of a row is the sum of the two halves' partial sums, formed
+  // by the epilogue (which also writes inv_norm).
+  // It pays where anchor-tile boundaries are frequent - few N tiles per anchor tile (80 prompts, batch 64:
+  // 0.220 -> 0.179 ms, 0.78 -> 0.94 of the HBM bandwidth) - and costs 1-3 % at 1203 prompts, where the
+  // 128-register cap of a 512-thread block squeezes the epilogue: the launcher picks it for <= 3 N tiles.
+  static_assert(!C8 || (!SPLIT3 && !PROJ && KB_T == 8 && !EPI2 && MODE != 2), "eight converter warps: the cosine kernels");
+  constexpr bool CONV8 = C8;
   constexpr bool BN64 = CG == 2 && !PROJ && !SPLIT3 && KB_T == 8 && OVDET_F_BN64;
   constexpr int BN = BN64 ? 64 : F_BLOCK_N;
   constexpr int A_COL = BN64 ? 2 * BN : F_A_COL;                   // first column of the A ring
@@ -290,13 +306,13 @@ sim_fused_kernel(const __grid_constant__ LevelMaps amaps, const __grid_constant_
   if (warp == 0 && lane == 0) {
     for (int l = 0; l < p.levels; ++l) { ptx::prefetch_tmap(&amaps.m[l]); ptx::prefetch_tmap(&bmaps.m[PROJ ? l : 0]); }
     for (int s = 0; s < F_B_STAGES; ++s) { ptx::mbar_init(b_full0 + 8u * s, 1); ptx::mbar_init(b_empty0 + 8u * s, 1); }
-    for (int s = 0; s < F_A_STAGES; ++s) { ptx::mbar_init(as_full0 + 8u * s, 1); ptx::mbar_init(as_empty0 + 8u * s, 4); }
+    for (int s = 0; s < F_A_STAGES; ++s) { ptx::mbar_init(as_full0 + 8u * s, 1); ptx::mbar_init(as_empty0 + 8u * s, CONV8 ? 8 : 4); }
     // a_ready / t_empty collect the converter / epilogue warps of BOTH CTAs on the leader
-    for (int k = 0; k < F_MAX_SLOTS; ++k) { ptx::mbar_init(a_ready0 + 8u * k, 4 * CG);
+    for (int k = 0; k < F_MAX_SLOTS; ++k) { ptx::mbar_init(a_ready0 + 8u * k, (CONV8 ? 8 : 4) * CG);
       // projected: the epilogue warps read x' back from the A region, so they release it too
       ptx::mbar_init(a_free0 + 8u * k, PROJ ? (EPI2 ? 9 : 5) : 1); }
     for (int s = 0; s < 2; ++s) { ptx::mbar_init(t_full0 + 8u * s, 1); ptx::mbar_init(t_empty0 + 8u * s, 4 * CG); }
-    for (int s = 0; s < 3; ++s) ptx::mbar_init(n_ready0 + 8u * s, 4);
+    for (int s = 0; s < 3; ++s) ptx::mbar_init(n_ready0 + 8u * s, CONV8 ? 8 : 4);
     ptx::fence_mbar_init();
   }
   if (warp == 2) {
@@ -501,6 +517,85 @@ sim_fused_kernel(const __grid_constant__ LevelMaps amaps, const __grid_constant_
       for (int kb = 0; kb < KB_IN; ++kb)
         ptx::tma_prefetch_l2_3d_if(issue, map, tc.m0, kb * F_BLOCK_K, tc.b);
     }
+  } else if (CONV8 && ((warp >= 4 && warp < 8) || warp >= 12)) {
+    // ================================ converters, eight warps (CONV8) ========================
+    if constexpr (CONV8) {
+      const int lg = warp & 3;
+      const int half = warp >= 12 ? 1 : 0;             // which 32 k of every 64-k block
+      const int arow = lg * 32 + lane;                 // anchor row of the tile == TMEM lane
+      constexpr int AH = 4;                            // half blocks held in registers
+      uint32_t held[AH][16];
+      bool poll_freed = false, poll_landed = false;    // results of the polls issued one block earlier
+      uint32_t ia = 0, lt = 0;
+      auto publish_half = [&](uint32_t lt_, int i, const uint32_t (&regs)[16], bool peeked) {
+        const int t = a_slot(lt_, i);
+        if (warp == 4) OVDET_TR(1, 12);
+        if (!peeked) ptx::mbar_wait_lazy(a_free0 + 8u * t, a_phase(lt_, i) ^ 1u, lazy_ns >> 1);
+        if (warp == 4) OVDET_TR(1, 13);
+        ptx::tc_fence_after();
+        ptx::tmem_st_32x32_x16(tmem_base + ((uint32_t)(lg * 32) << 16) + (uint32_t)(A_COL + t * 32 + 16 * half), regs);
+        ptx::tmem_st_wait();
+        ptx::tc_fence_before();
+        __syncwarp();
+        if (lane == 0) {
+          if constexpr (CG == 2) ptx::mbar_arrive_cluster(lead_a_ready0 + 8u * t);
+          else ptx::mbar_arrive(a_ready0 + 8u * t);
+        }
+        if (warp == 4) OVDET_TR(1, 14);
+      };
+      for (int w = pair0; w < total_work; w += pair_stride, ++lt) {
+        float ss0 = 0.f, ss1 = 0.f, ss2 = 0.f, ss3 = 0.f;
+        float row_scale = 1.0f;                        // F16OP: power of two applied before the fp16 rounding
+#pragma unroll
+        for (int kb = 0; kb < KB_T; ++kb, ++ia) {
+          const uint32_t s = ia % F_A_STAGES;
+          if (warp == 4) OVDET_TR(1, 10);
+          if (kb >= AH) publish_half(lt, kb - AH, held[kb % AH], poll_freed);
+          if (!poll_landed) ptx::mbar_wait_lazy(as_full0 + 8u * s, (ia / F_A_STAGES) & 1u, lazy_ns >> 1);
+          if (warp == 4) OVDET_TR(1, 11);
+          const float* col = a_stage_ptr + s * (F_A_STAGE_BYTES / 4) + arow;
+          const __nv_bfloat16* col16 = reinterpret_cast<const __nv_bfloat16*>(a_stage_ptr + s * (F_A_STAGE_BYTES / 4)) + arow;
+          auto ldx = [&](int k) -> float {               // k = position in the 64-k block
+            if constexpr (IN16) return __bfloat162float(col16[k * F_BLOCK_M]);
+            else return col[k * F_BLOCK_M];
+          };
+          if constexpr (F16OP) {
+            if (kb == 0) {                               // both halves take the same eight samples: the same scale
+              float m = 0.f;
+#pragma unroll
+              for (int k = 0; k < 64; k += 8) m = fmaxf(m, fabsf(ldx(k)));
+              const uint32_t e = (__float_as_uint(m) >> 23) & 0xffu;
+              row_scale = e >= 2u ? __uint_as_float((256u - e) << 23) : 1.0f;
+            }
+          }
+          {                                              // polls for the next iteration / the closing publishes
+            const int nb = kb + 1;
+            poll_freed = nb >= AH ? ptx::mbar_test_wait(a_free0 + 8u * a_slot(lt, nb - AH), a_phase(lt, nb - AH) ^ 1u) : true;
+            poll_landed = ptx::mbar_test_wait(as_full0 + 8u * ((ia + 1u) % F_A_STAGES), ((ia + 1u) / F_A_STAGES) & 1u);
+          }
+          uint32_t (&packed)[16] = held[kb % AH];
+#pragma unroll
+          for (int k = 0; k < 32; k += 4) {
+            float x0 = ldx(32 * half + k + 0), x1 = ldx(32 * half + k + 1);
+            float x2 = ldx(32 * half + k + 2), x3 = ldx(32 * half + k + 3);
+            if constexpr (F16OP) { x0 *= row_scale; x1 *= row_scale; x2 *= row_scale; x3 *= row_scale; }
+            ss0 = fmaf(x0, x0, ss0); ss1 = fmaf(x1, x1, ss1);
+            ss2 = fmaf(x2, x2, ss2); ss3 = fmaf(x3, x3, ss3);
+            packed[(k >> 1) + 0] = F16OP ? pack_f16x2_sat(x0, x1) : pack_bf16x2(x0, x1);
+            packed[(k >> 1) + 1] = F16OP ? pack_f16x2_sat(x2, x3) : pack_bf16x2(x2, x3);
+          }
+          __syncwarp();
+          if (lane == 0) ptx::mbar_arrive(as_empty0 + 8u * s);   // staging slot may be refilled (8 arrivals)
+        }
+#pragma unroll
+        for (int kb = KB_T - AH; kb < KB_T; ++kb) publish_half(lt, kb, held[kb % AH], kb == KB_T - AH ? poll_freed : false);
+        const int slot = lt % 3;
+        norm_s[(slot * 3 + half) * F_BLOCK_M + arow] = (ss0 + ss1) + (ss2 + ss3);
+        if (half == 0) norm_s[(slot * 3 + 2) * F_BLOCK_M + arow] = row_scale;
+        __syncwarp();
+        if (lane == 0) ptx::mbar_arrive(n_ready0 + 8u * slot);
+      }
+    }
   } else if (warp >= 4 && warp < 8) {
     // ================================ converters =============================================
     const int lg = warp & 3;
@@ -552,7 +647,11 @@ sim_fused_kernel(const __grid_constant__ LevelMaps amaps, const __grid_constant_
       const int nt_b = (w % NSPLIT) * NT / NSPLIT, nt_e = (w % NSPLIT + 1) * NT / NSPLIT;
       (void)nt_b; (void)nt_e;
       const TileCoord tc = decode_tile(p, tile);
+      // the sum of squares in the association of the eight-warp converter above (one partial sum per
+      // 32-k half of every block, four interleaved accumulators each): the kernels of one shape family
+      // - with and without a second epilogue group - then agree BIT FOR BIT on every row norm
       float ss0 = 0.f, ss1 = 0.f, ss2 = 0.f, ss3 = 0.f;
+      float st0 = 0.f, st1 = 0.f, st2 = 0.f, st3 = 0.f;
       float row_scale = 1.0f;                          // F16OP: power of two applied before the fp16 rounding
       auto publish = [&](int i, const uint32_t (&regs)[32]) { publish_at(lt, i, regs, false); };
 #pragma unroll
@@ -583,8 +682,8 @@ sim_fused_kernel(const __grid_constant__ LevelMaps amaps, const __grid_constant_
           // polls for the NEXT iteration (or the tile's closing publishes): issued now, consumed after
           // this block's ~400 cycles of shared-memory reads and packing
           const int nb = kb + 1;                           // next block of this tile, or KB_IN = the closing publishes
-          poll_freed = nb >= AH ? ptx::mbar_try_wait(a_free0 + 8u * a_slot(lt, nb - AH), a_phase(lt, nb - AH) ^ 1u) : true;
-          poll_landed = ptx::mbar_try_wait(as_full0 + 8u * ((ia + 1u) % F_A_STAGES), ((ia + 1u) / F_A_STAGES) & 1u);
+          poll_freed = nb >= AH ? ptx::mbar_test_wait(a_free0 + 8u * a_slot(lt, nb - AH), a_phase(lt, nb - AH) ^ 1u) : true;
+          poll_landed = ptx::mbar_test_wait(as_full0 + 8u * ((ia + 1u) % F_A_STAGES), ((ia + 1u) / F_A_STAGES) & 1u);
         }
         if constexpr (F16OP) {
           if (kb == 0) {
@@ -602,8 +701,13 @@ sim_fused_kernel(const __grid_constant__ LevelMaps amaps, const __grid_constant_
           float x0 = ldx(k + 0), x1 = ldx(k + 1);
           float x2 = ldx(k + 2), x3 = ldx(k + 3);
           if constexpr (F16OP) { x0 *= row_scale; x1 *= row_scale; x2 *= row_scale; x3 *= row_scale; }
-          ss0 = fmaf(x0, x0, ss0); ss1 = fmaf(x1, x1, ss1);
-          ss2 = fmaf(x2, x2, ss2); ss3 = fmaf(x3, x3, ss3);
+          if (k < 32) {
+            ss0 = fmaf(x0, x0, ss0); ss1 = fmaf(x1, x1, ss1);
+            ss2 = fmaf(x2, x2, ss2); ss3 = fmaf(x3, x3, ss3);
+          } else {
+            st0 = fmaf(x0, x0, st0); st1 = fmaf(x1, x1, st1);
+            st2 = fmaf(x2, x2, st2); st3 = fmaf(x3, x3, st3);
+          }
           packed[(k >> 1) + 0] = F16OP ? pack_f16x2_sat(x0, x1) : pack_bf16x2(x0, x1);
           packed[(k >> 1) + 1] = F16OP ? pack_f16x2_sat(x2, x3) : pack_bf16x2(x2, x3);
           if constexpr (SPLIT3) {
@@ -628,11 +732,12 @@ sim_fused_kernel(const __grid_constant__ LevelMaps amaps, const __grid_constant_
 #pragma unroll
         for (int kb = KB_IN - AH; kb < KB_IN; ++kb) publish_at(lt, kb, held[kb % AH], kb == KB_IN - AH ? poll_freed : false);
       }
-      float inv = 1.0f / fmaxf(sqrtf((ss0 + ss1) + (ss2 + ss3)), 1e-12f);
+      const float ssq = ((ss0 + ss1) + (ss2 + ss3)) + ((st0 + st1) + (st2 + st3));
+      float inv = 1.0f / fmaxf(sqrtf(ssq), 1e-12f);
       const int slot = lt % 3;
       if constexpr (F16OP) {
         // ||x|| = ||s x|| / s; the accumulators hold <s x, 16 t>: the row factor is 1 / (16 s max(||x||, eps))
-        inv = 1.0f / fmaxf(sqrtf((ss0 + ss1) + (ss2 + ss3)) / row_scale, 1e-12f);
+        inv = 1.0f / fmaxf(sqrtf(ssq) / row_scale, 1e-12f);
         norm_s[slot * F_BLOCK_M + arow] = inv / (16.0f * row_scale);
       } else {
         norm_s[slot * F_BLOCK_M + arow] = inv;
@@ -676,7 +781,24 @@ sim_fused_kernel(const __grid_constant__ LevelMaps amaps, const __grid_constant_
       const long long grow = tc.out_row0 + r_in_tile;
       const int slot = lt % 3;
       if constexpr (!PROJ) ptx::mbar_wait(n_ready0 + 8u * slot, (lt / 3) & 1u);
-      const float scale = PROJ ? 1.0f : (p.normalize ? p.alpha * norm_s[slot * F_BLOCK_M + r_in_tile] : p.alpha);
+      float scale;
+      if constexpr (CONV8) {
+        // the row's sum of squares = the two converter halves' partial sums; F16OP: over the scaled values
+        const float ssq = norm_s[(slot * 3 + 0) * F_BLOCK_M + r_in_tile] + norm_s[(slot * 3 + 1) * F_BLOCK_M + r_in_tile];
+        float inv, factor;
+        if constexpr (F16OP) {
+          const float rs = norm_s[(slot * 3 + 2) * F_BLOCK_M + r_in_tile];
+          inv = 1.0f / fmaxf(sqrtf(ssq) / rs, 1e-12f);      // ||x|| = ||s x|| / s
+          factor = inv / (16.0f * rs);                        // the accumulators hold <s x, 16 t>
+        } else {
+          inv = 1.0f / fmaxf(sqrtf(ssq), 1e-12f);
+          factor = inv;
+        }
+        if (p.inv_norm != nullptr && row_ok) p.inv_norm[grow] = inv;
+        scale = p.normalize ? p.alpha * factor : p.alpha;
+      } else {
+        scale = PROJ ? 1.0f : (p.normalize ? p.alpha * norm_s[slot * F_BLOCK_M + r_in_tile] : p.alpha);
+      }
       float q = 0.f;                                   // projected: ||W x + b||^2
       const float beta = p.beta;
       float bv[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
@@ -1373,23 +1495,26 @@ int fused_launch(const float* const* obj_embeds, const int64_t* hw, const int64_
   if (f16_operands && cg != 2) return OVDET_ERR_UNSUPPORTED_SHAPE;   // fp16 tier: the dim = 512 CTA-pair kernel only
   if (vp && cg != 2) return OVDET_ERR_UNSUPPORTED_SHAPE;      // key exchange: the dim = 512 CTA-pair kernel only
 #define OVDET_FOR_EACH_FUSED(X)                                                                        \
-  X(8, false, 2, false, false, 0, false, false) X(8, false, 2, false, false, 1, false, false) X(8, false, 2, false, false, 2, false, false) \
-  X(8, false, 2, false, true, 0, false, false)  X(8, false, 2, false, true, 1, false, false)  X(8, false, 2, false, true, 2, false, false)  \
-  X(4, false, 2, true, false, 0, false, false)                                                                \
-  X(8, false, 2, false, false, 0, true, false)  X(8, false, 2, false, true, 0, true, false)  X(4, false, 2, true, false, 0, true, false)     \
-  X(8, false, 2, false, false, 1, true, false)  X(8, false, 2, false, true, 1, true, false)                           \
-  X(8, false, 1, false, false, 0, false, false) X(8, false, 1, false, false, 1, false, false)                        \
-  X(0, false, 1, false, false, 0, false, false) X(0, false, 1, false, false, 1, false, false)                        \
-  X(0, true, 1, false, false, 0, false, false)  X(0, true, 1, false, false, 1, false, false)                         \
-  X(0, false, 1, true, false, 0, false, false)                                                                \
-  X(0, false, 1, false, true, 0, false, false)  X(0, false, 1, false, true, 1, false, false)  \
-  X(8, false, 2, false, false, 0, false, true) X(8, false, 2, false, false, 1, false, true)            \
-  X(8, false, 2, false, false, 1, true, true)                                                          \
-  X(1, false, 2, false, false, 0, false, false) X(2, false, 2, false, false, 0, false, false)          \
-  X(3, true, 2, false, false, 0, false, false)  X(6, true, 2, false, false, 0, false, false)
+  X(8, false, 2, false, false, 0, false, false, false) X(8, false, 2, false, false, 1, false, false, false) X(8, false, 2, false, false, 2, false, false, false) \
+  X(8, false, 2, false, true, 0, false, false, false)  X(8, false, 2, false, true, 1, false, false, false)  X(8, false, 2, false, true, 2, false, false, false)  \
+  X(4, false, 2, true, false, 0, false, false, false)                                                                \
+  X(8, false, 2, false, false, 0, true, false, false)  X(8, false, 2, false, true, 0, true, false, false)  X(4, false, 2, true, false, 0, true, false, false)     \
+  X(8, false, 2, false, false, 1, true, false, false)  X(8, false, 2, false, true, 1, true, false, false)                           \
+  X(8, false, 1, false, false, 0, false, false, false) X(8, false, 1, false, false, 1, false, false, false)                        \
+  X(0, false, 1, false, false, 0, false, false, false) X(0, false, 1, false, false, 1, false, false, false)                        \
+  X(0, true, 1, false, false, 0, false, false, false)  X(0, true, 1, false, false, 1, false, false, false)                         \
+  X(0, false, 1, true, false, 0, false, false, false)                                                                \
+  X(0, false, 1, false, true, 0, false, false, false)  X(0, false, 1, false, true, 1, false, false, false)  \
+  X(8, false, 2, false, false, 0, false, true, false) X(8, false, 2, false, false, 1, false, true, false)            \
+  X(8, false, 2, false, false, 1, true, true, false)                                                          \
+  X(1, false, 2, false, false, 0, false, false, false) X(2, false, 2, false, false, 0, false, false, false)          \
+  X(3, true, 2, false, false, 0, false, false, false)  X(6, true, 2, false, false, 0, false, false, false)  \
+  X(8, false, 2, false, false, 0, false, false, true) X(8, false, 2, false, true, 0, false, false, true)   \
+  X(8, false, 2, false, false, 0, false, true, true)  X(8, false, 2, false, false, 1, false, false, true)  \
+  X(8, false, 2, false, false, 1, false, true, true)  X(8, false, 2, false, true, 1, false, false, true)
   if (int rc = once_per_device(1, []() -> int {
-#define OVDET_SET_SMEM(KB, S3, CGV, PR, I16, MD, E2, F16)                                                  \
-        OVDET_CUDA_TRY(cudaFuncSetAttribute(sim_fused_kernel<KB, S3, CGV, PR, I16, MD, E2, F16>,        \
+#define OVDET_SET_SMEM(KB, S3, CGV, PR, I16, MD, E2, F16, C8V)                                             \
+        OVDET_CUDA_TRY(cudaFuncSetAttribute(sim_fused_kernel<KB, S3, CGV, PR, I16, MD, E2, F16, C8V>,   \
                                             cudaFuncAttributeMaxDynamicSharedMemorySize,                   \
                                             FSmem<CGV, (PR && CGV == 2), (CGV == 2 && !PR && !S3 && KB == 8 && OVDET_F_BN64)>::bytes));
         OVDET_FOR_EACH_FUSED(OVDET_SET_SMEM)
@@ -1403,6 +1528,10 @@ int fused_launch(const float* const* obj_embeds, const int64_t* hw, const int64_
   const bool epi2 = cg == 2 && ((mode == 0 && ((proj && (epi2_env & 1)) || (!proj && kb == 8 && (epi2_env & 2)))) ||
                                 (mode == 1 && logits_tma && (epi2_env & 4))) &&
                     !(f16_operands && mode == 0);
+  // eight converter warps (CONV8 in the kernel): few N tiles per anchor tile, no second epilogue group
+  static const int conv8_env = []() { const char* e = getenv("OVDET_CONV8_TILES"); return e ? atoi(e) : 3; }();
+  const bool conv8 = OVDET_F_CONV8 && cg == 2 && !proj && !split3 && kb == 8 && !epi2 && mode != 2 &&
+                     p.n_tiles <= conv8_env && p.nsplit == 1;
   // shape variant of this launch
   const int v_kb = cg == 2 ? (proj ? 4 : p.kb) : ((!in_bf16 && !proj && !split3 && p.kb == 8) ? 8 : 0);
   cudaLaunchConfig_t cfg{};
@@ -1424,12 +1553,12 @@ int fused_launch(const float* const* obj_embeds, const int64_t* hw, const int64_
     cfg.dynamicSmemBytes = FSmem<1>::bytes;
   }
   bool launched = false;
-#define OVDET_TRY_LAUNCH(KB, S3, CGV, PR, I16, MD, E2, F16)                                                \
+#define OVDET_TRY_LAUNCH(KB, S3, CGV, PR, I16, MD, E2, F16, C8V)                                           \
   if (!launched && v_kb == KB && (split3 != 0) == S3 && cg == CGV && (proj != 0) == PR &&               \
-      (in_bf16 != 0) == I16 && mode == MD && epi2 == E2 && (f16_operands != 0) == F16) {                                            \
-    cfg.blockDim = dim3(E2 ? F_THREADS + 128 : F_THREADS);                                              \
+      (in_bf16 != 0) == I16 && mode == MD && epi2 == E2 && (f16_operands != 0) == F16 && conv8 == C8V) { \
+    cfg.blockDim = dim3((E2 || C8V) ? F_THREADS + 128 : F_THREADS);                                     \
     cfg.dynamicSmemBytes = FSmem<CGV, (PR && CGV == 2), (CGV == 2 && !PR && !S3 && KB == 8 && OVDET_F_BN64)>::bytes; \
-    OVDET_CUDA_TRY(cudaLaunchKernelEx(&cfg, sim_fused_kernel<KB, S3, CGV, PR, I16, MD, E2, F16>, maps, bmaps, cmaps, p)); \
+    OVDET_CUDA_TRY(cudaLaunchKernelEx(&cfg, sim_fused_kernel<KB, S3, CGV, PR, I16, MD, E2, F16, C8V>, maps, bmaps, cmaps, p)); \
     launched = true;                                                                                    \
   }
   OVDET_FOR_EACH_FUSED(OVDET_TRY_LAUNCH)
