@@ -240,6 +240,14 @@ OVDET_API int ovdet_concat_embeddings(const float* x, int64_t batch, int64_t dim
                                       int64_t stride_b, int64_t stride_d, float* out,
                                       int64_t rows_per_batch, int64_t row_offset, void* stream);
 
+/* E2  Re-pitch the rows of a conv output (row r of `row_elems` elements at src + r*src_pitch -> dst +
+ * r*dst_pitch, the tail [row_elems, dst_pitch) zero filled) so that the TMA loads of ovdet_similarity_fused*
+ * can address a level whose H*W is not a multiple of 4 (13x13, 15x15, 19x19 ... at image sizes 416, 480, 608).
+ * No reference counterpart: it stands in for the alignment torch's own kernels do not need
+ * (model/heads/text_contrastive.py:134 permutes any H*W).  elem_size 4 (fp32) or 2 (bf16); pitches in elements. */
+OVDET_API int ovdet_repitch_rows(const void* src, int64_t rows, int64_t row_elems, int64_t src_pitch,
+                                 void* dst, int64_t dst_pitch, int elem_size, void* stream);
+
 /* ------------------------------------------------------------------------------------------
  * K3  DFL box decode for all levels + score activation + confidence threshold.
  * Replaces: model/heads/box_head.py:150-218 (decode_boxes; grid of :115-148 is implicit),

@@ -79,6 +79,7 @@ PROTOTYPES = {
                                            c_int64, c_int, c_float, c_float, c_void_p, c_void_p, c_void_p,
                                            c_void_p]),
     "ovdet_rowmax": (c_int, [c_void_p, c_int, c_int64, c_int64, c_int64, c_void_p, c_void_p, c_void_p]),
+    "ovdet_repitch_rows": (c_int, [c_void_p, c_int64, c_int64, c_int64, c_void_p, c_int64, c_int, c_void_p]),
     "ovdet_concat_embeddings": (c_int, [c_void_p, c_int64, c_int64, c_int64, c_int64, c_int64, c_void_p,
                                         c_int64, c_int64, c_void_p]),
     "ovdet_decode_filter": (c_int, [POINTER(c_void_p), POINTER(c_int32), POINTER(c_int32),

@@ -43,7 +43,43 @@ concat_embeddings_kernel(const float* __restrict__ x, int dim, int hw, int64_t s
   }
 }
 
+// E2: re-pitch the rows of a conv output so that TMA can address it.  The fused similarity kernel reads
+// [64 k x 128 anchors] boxes straight out of the NCHW tensor, which needs 16-byte aligned rows: H*W a
+// multiple of 4 (fp32).  Image sizes such as 416, 480 or 608 give a 13x13 / 15x15 / 19x19 P5 level; without this
+// the WHOLE step fell back to the two-kernel path.  One warp per row of `row_elems` elements (4-byte
+// or 2-byte), 8 rows per block, coalesced along the row.
+template <typename T>
+__global__ void __launch_bounds__(256)
+repitch_rows_kernel(const T* __restrict__ src, int64_t rows, int row_elems, int64_t src_pitch,
+                    T* __restrict__ dst, int64_t dst_pitch) {
+  const int64_t r = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (r >= rows) return;
+  const T* s = src + r * src_pitch;
+  T* d = dst + r * dst_pitch;
+  for (int i = threadIdx.x & 31; i < dst_pitch; i += 32) d[i] = i < row_elems ? s[i] : T(0);
+}
+
 }  // namespace ovdet
+
+extern "C" int ovdet_repitch_rows(const void* src, int64_t rows, int64_t row_elems, int64_t src_pitch,
+                                  void* dst, int64_t dst_pitch, int elem_size, void* stream) {
+  using namespace ovdet;
+  if (rows == 0) return check_device();
+  if (!src || !dst || rows < 0 || row_elems <= 0 || src_pitch < row_elems || dst_pitch < row_elems ||
+      (elem_size != 2 && elem_size != 4) || row_elems >= (1ll << 31) || dst_pitch >= (1ll << 31))
+    return OVDET_ERR_INVALID_ARG;
+  if (ceil_div<int64_t>(rows, 8) >= (1ll << 31)) return OVDET_ERR_UNSUPPORTED_SHAPE;
+  if (int rc = check_device()) return rc;
+  const unsigned grid = (unsigned)ceil_div<int64_t>(rows, 8);
+  if (elem_size == 4)
+    repitch_rows_kernel<uint32_t><<<grid, 256, 0, as_stream(stream)>>>(
+        static_cast<const uint32_t*>(src), rows, (int)row_elems, src_pitch, static_cast<uint32_t*>(dst), dst_pitch);
+  else
+    repitch_rows_kernel<uint16_t><<<grid, 256, 0, as_stream(stream)>>>(
+        static_cast<const uint16_t*>(src), rows, (int)row_elems, src_pitch, static_cast<uint16_t*>(dst), dst_pitch);
+  OVDET_LAUNCH_CHECK();
+  return OVDET_OK;
+}
 
 extern "C" int ovdet_concat_embeddings(const float* x, int64_t batch, int64_t dim, int64_t hw,
                                        int64_t stride_b, int64_t stride_d, float* out,

@@ -99,7 +99,7 @@ class TextContrastiveHead(nn.Module):
         (the same transposed view, with the same strides, the reference returns)."""
         b, d, h, w = obj_embed.shape
         c = text_embed.shape[-2]
-        level = [obj_embed.float()]
+        level = ops.tma_addressable([obj_embed.float()])
         if self.precision == "fp16" and ops.fused_fp16_supported(level):
             text_op = ops.l2norm_text(text_embed.float(), split="fp16")
             logits, _, _ = ops.similarity_fused(level, text_op, self.cls_alpha, self.cls_beta,
@@ -173,6 +173,7 @@ def _similarity_levels(obj_embeds: Sequence[torch.Tensor], text_embeddings: torc
     dim <= 512); K1 -> K2 otherwise."""
     classes = text_embeddings.shape[-2]
     levels = [e if e.dtype in (torch.float32, torch.bfloat16) else e.float() for e in obj_embeds]
+    levels = ops.tma_addressable(levels)          # odd H*W (13x13, 19x19 ...): rows re-pitched to 16 bytes
     if precision == "auto":             # inside the fp32 bar at the best speed the shape allows
         # (the same rule as pipeline.resolve_precision: the fp16 tier - one tensor-core pass, |dlogit| <= 1e-4 -
         # wherever its kernel takes the shape; the three-pass recipe otherwise and for fp32 logits)

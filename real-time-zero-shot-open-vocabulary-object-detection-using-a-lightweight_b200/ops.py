@@ -168,6 +168,42 @@ def fused_supported(obj_embeds: Sequence[torch.Tensor]) -> bool:
     return True
 
 
+def tma_addressable(obj_embeds: Sequence[torch.Tensor], buffers: Optional[list] = None) -> list:
+    """Levels as the fused kernel's TMA loads can address them.  A level whose rows are not 16-byte
+    aligned (H*W not a multiple of 4 for fp32 / 8 for bf16: 13x13, 15x15, 19x19 ... at image sizes such
+    as 416, 480, 608) or that is not row-contiguous is copied once into a buffer with padded rows
+    (``ovdet_repitch_rows``) and handed on as a ``[B, D, H, W]`` view of that buffer; aligned levels pass
+    through untouched.  ``buffers``: a list the caller keeps (one slot per level) so that a steady-state
+    step allocates nothing."""
+    out = []
+    for l, e in enumerate(obj_embeds):
+        if e.dtype not in (torch.float32, torch.bfloat16) or e.dim() != 4 or not e.is_cuda:
+            out.append(e)
+            continue
+        b, d, h, w = e.shape
+        per16 = 16 // e.element_size()
+        ok = (e.stride(3) == 1 and e.stride(2) == w and e.stride(1) % per16 == 0 and e.stride(0) % per16 == 0
+              and e.data_ptr() % 16 == 0 and e.stride(1) >= h * w)
+        if ok or b == 0:
+            out.append(e)
+            continue
+        if e.stride(3) != 1 or e.stride(2) != w or e.stride(0) != d * e.stride(1):
+            e = e.contiguous()                     # exotic views: one library copy, then the re-pitch below
+        pitch = (h * w + per16 - 1) // per16 * per16
+        buf = buffers[l] if buffers is not None and l < len(buffers) else None
+        if buf is None or buf.shape != (b, d, pitch) or buf.dtype != e.dtype or buf.device != e.device:
+            buf = torch.empty(b, d, pitch, device=e.device, dtype=e.dtype)
+            if buffers is not None:
+                while len(buffers) <= l:
+                    buffers.append(None)
+                buffers[l] = buf
+        with torch.cuda.device(e.device):
+            check(lib().ovdet_repitch_rows(e.data_ptr(), b * d, h * w, e.stride(1), buf.data_ptr(), pitch,
+                                           e.element_size(), _stream(e)), "ovdet_repitch_rows")
+        out.append(buf.as_strided((b, d, h, w), (d * pitch, pitch, w, 1)))
+    return out
+
+
 def text_operand_fp32(text: torch.Tensor) -> torch.Tensor:
     """Unit-norm text rows as the ``[hi | lo | hi]`` bf16 operand of ``similarity_fused(fp32=True)``
     (one K1b launch)."""

@@ -74,7 +74,7 @@ def resolve_precision(config: "HeadConfig", level_shapes, num_classes: int, proj
     if projected:
         return "bf16"                       # the projected similarity is a single bf16 pass by construction
     d = config.embed_dim
-    tma_ok = all((h * w) % 4 == 0 for h, w in level_shapes) and len(level_shapes) <= 4
+    tma_ok = len(level_shapes) <= 4         # levels with unaligned rows are re-pitched first (ops.tma_addressable)
     if config.fused and tma_ok and d == 512 and config.logits_dtype != "fp32":
         return "fp16"                       # one pass of the CTA-pair kernel, ~1e-5 (max 7e-5)
     return "fp32"                           # three passes: fused streaming mode (<= 128 classes) or K1 -> K2
@@ -161,6 +161,7 @@ class HeadPipeline:
         self.last_single_call = False      # the previous run() was ONE C call (ovdet_head_step)
         self._step_args = None             # ovdet_head_step_args, filled on first use
         self._parallel_decode = False      # set by capture(): decode forked beside the similarity kernel
+        self._pad_bufs = []                # re-pitched copies of levels TMA cannot address as they are (odd H*W)
         self._side = None
         self._fork = None
 
@@ -236,6 +237,8 @@ class HeadPipeline:
     def _run(self, obj_embeds, box_preds, text, events) -> ops.NmsResult:
         cfg = self.cfg
         self.check_inputs(obj_embeds, box_preds, text)
+        if self.want_fused or self.want_fused_fp32 or self.projections is not None:
+            obj_embeds = ops.tma_addressable(obj_embeds, self._pad_bufs)
 
         def mark(name, begin):
             if begin:

@@ -547,6 +547,48 @@ def test_config4_config5_shapes_vs_oracle(ov, cuda_device, image_size, classes):
         np.testing.assert_array_equal(res.boxes[i, :k].cpu().numpy(), want[i]["boxes"])
 
 
+@pytest.mark.parametrize("image_size,precision", [(416, "bf16"), (416, "auto"), (608, "bf16"), (480, "auto")])
+def test_odd_level_sizes_stay_on_the_fused_kernel(ov, cuda_device, image_size, precision):
+    """Image sizes whose P5 level has an odd number of cells (416 -> 13x13, 480 -> 15x15, 608 -> 19x19):
+    TMA needs 16-byte rows, so that level is re-pitched (ovdet_repitch_rows) and the step stays on the
+    fused kernel and the single C call; same bars as everywhere else vs the oracle."""
+    from ovdet import ops, synth
+    from ovdet.pipeline import HeadConfig, HeadPipeline
+    b, classes = 3, 300
+    inp = synth.make_inputs(batch=b, image_size=image_size, num_classes=classes, seed=21)
+    tail = ref_port.head_tail(inp.obj_embeds, inp.text_batched(), inp.box_preds)
+    s = image_size
+    shapes = [(s // 8, s // 8), (s // 16, s // 16), (s // 32, s // 32)]
+    assert (shapes[2][0] * shapes[2][1]) % 4 != 0
+    dev_embs = [e.to(cuda_device) for e in inp.obj_embeds]
+    assert not ops.fused_supported(dev_embs) and ops.fused_supported(ops.tma_addressable(dev_embs))
+    # the helper alone: aligned levels pass through, the odd one becomes a padded view with equal values
+    padded = ops.tma_addressable(dev_embs)
+    assert padded[0] is dev_embs[0] and padded[1] is dev_embs[1] and padded[2].stride(1) % 4 == 0
+    assert torch.equal(padded[2], dev_embs[2])
+    pipe = HeadPipeline(b, shapes, classes, HeadConfig(precision=precision), device=cuda_device)
+    pipe.set_vocabulary(inp.text.to(cuda_device))
+    sizes = [(s, s)] * b
+    pipe.set_geometry(sizes, [1.0] * b)
+    res = pipe.run(dev_embs, [p.to(cuda_device) for p in inp.box_preds])
+    torch.cuda.synchronize()
+    assert pipe.last_path == "fused" and pipe.last_single_call
+    assert_logits_close(pipe.scores, tail["scores"], "bf16" if precision == "bf16" else "fp32")
+    torch.testing.assert_close(pipe.boxes.cpu(), tail["boxes"], rtol=1e-4, atol=1e-3)
+    fed = {"boxes": pipe.boxes.cpu(), "scores": pipe.scores.cpu(), "class_ids": pipe.class_ids.cpu().long()}
+    want = ref_port.postprocess_batch(fed, sizes, [1.0] * b)
+    for i in range(b):
+        k = int(res.count[i])
+        assert k == len(want[i]["keep"]) and k > 5
+        np.testing.assert_array_equal(res.keep[i, :k].cpu().numpy(), want[i]["keep"])
+        np.testing.assert_array_equal(res.boxes[i, :k].cpu().numpy(), want[i]["boxes"])
+    # the drop-in tail takes the same route
+    from ovdet.heads import head_tail
+    out = head_tail(dev_embs, inp.text.to(cuda_device).unsqueeze(0).expand(b, -1, -1),
+                    [p.to(cuda_device) for p in inp.box_preds], precision=precision)
+    assert_logits_close(out["scores"], tail["scores"], "bf16" if precision == "bf16" else "fp32")
+
+
 # ------------------------------------------------------------------------------------------
 # K1+K2 fused (fp32 NCHW in, A operand resident in tensor memory)
 # ------------------------------------------------------------------------------------------
