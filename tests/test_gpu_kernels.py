@@ -9,6 +9,7 @@ Tolerances (BASELINE.json north_star):
   * NMS / ordering / indices / classes: bit-exact on identical inputs.
 """
 import os
+import sys
 
 import numpy as np
 import pytest
@@ -1546,3 +1547,15 @@ def test_decode_bf16_box_logits(ov, cuda_device):
         torch.cuda.synchronize()
         torch.testing.assert_close(boxes.cpu(), ref, rtol=1e-4, atol=1e-3)
         assert torch.equal(_unpack(mask.cpu(), ref.shape[1]), scores > 0.25)
+
+
+def test_soak_fused_protocol_small(ov, cuda_device, monkeypatch, capsys):
+    """tools/soak_fused.py for a few iterations: random shapes, every fused launch against the two-kernel
+    path (2e-5) and the fp16 tier against fp64 torch (1e-4) - the check that a change to the converter /
+    MMA / epilogue hand-shakes did not open a race."""
+    import runpy
+    tool = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tools", "soak_fused.py")
+    monkeypatch.setattr(sys, "argv", [tool, "30", "11"])
+    runpy.run_path(tool, run_name="__main__")
+    assert '"ok": true' in capsys.readouterr().out
+
