@@ -1530,8 +1530,12 @@ int fused_launch(const float* const* obj_embeds, const int64_t* hw, const int64_
                     !(f16_operands && mode == 0);
   // eight converter warps (CONV8 in the kernel): few N tiles per anchor tile, no second epilogue group
   static const int conv8_env = []() { const char* e = getenv("OVDET_CONV8_TILES"); return e ? atoi(e) : 3; }();
+  // ... or a launch so small that every CTA pair converts at most two anchor tiles (batch 1: the first
+  // tile's conversion chain is fully exposed, there is nothing to hide it behind)
+  const long long work_items = (tiles + 1) / 2 * p.nsplit;
   const bool conv8 = OVDET_F_CONV8 && cg == 2 && !proj && !split3 && kb == 8 && !epi2 && mode != 2 &&
-                     p.n_tiles <= conv8_env && p.nsplit == 1;
+                     ((p.n_tiles + p.nsplit - 1) / p.nsplit <= conv8_env ||
+                      (conv8_env > 0 && work_items <= 2ll * (sm_count() / 2)));
   // shape variant of this launch
   const int v_kb = cg == 2 ? (proj ? 4 : p.kb) : ((!in_bf16 && !proj && !split3 && p.kb == 8) ? 8 : 0);
   cudaLaunchConfig_t cfg{};
