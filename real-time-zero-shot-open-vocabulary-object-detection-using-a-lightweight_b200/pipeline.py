@@ -97,6 +97,10 @@ class HeadPipeline:
         self.per_image_text = per_image_text
         if config.precision not in ("auto", "bf16", "fp16", "fp32"):
             raise ValueError("ovdet: precision is 'auto', 'bf16', 'fp16' or 'fp32'")
+        self._auto = config.precision == "auto"
+        self._twin = None                  # "auto" + bf16 activations: the bf16-operand pipeline of the same shape
+        self._vocab_text = None
+        self._ctor = (batch, [tuple(s) for s in level_shapes], num_classes, device, per_image_text, projections)
         if config.precision == "auto":
             import dataclasses
             config = dataclasses.replace(config, precision=resolve_precision(
@@ -170,6 +174,9 @@ class HeadPipeline:
         """Normalise a shared ``[C, D]`` vocabulary once (the reference re-normalises it three
         times per forward, text_contrastive.py:138)."""
         assert not self.per_image_text
+        self._vocab_text = text
+        if self._twin is not None:
+            self._twin.set_vocabulary(text)
         if self.projections is not None:
             self.level_ops = [ops.project_vocabulary(text, w, b) for w, b in self.projections]
         else:
@@ -237,6 +244,8 @@ class HeadPipeline:
     def _run(self, obj_embeds, box_preds, text, events) -> ops.NmsResult:
         cfg = self.cfg
         self.check_inputs(obj_embeds, box_preds, text)
+        if self._auto and self.f16 and obj_embeds[0].dtype == torch.bfloat16:
+            return self._run_bf16_twin(obj_embeds, box_preds, text, events)
         if self.want_fused or self.want_fused_fp32 or self.projections is not None:
             obj_embeds = ops.tma_addressable(obj_embeds, self._pad_bufs)
 
@@ -274,8 +283,9 @@ class HeadPipeline:
         fused = self.want_fused and ops.fused_supported(obj_embeds)
         fused32 = self.want_fused_fp32 and ops.fused_supported(obj_embeds)
         if self.f16 and not (fused and ops.fused_fp16_supported(obj_embeds)):
-            raise ValueError("ovdet: precision 'fp16' needs fp32 activations with TMA-addressable levels "
-                             "(H*W and strides multiples of 4); use 'fp32' or 'bf16' for this input")
+            raise ValueError("ovdet: precision 'fp16' (also what 'auto' resolves to at embed_dim 512) needs fp32 "
+                             "activations; for bf16 activations (heads under autocast) construct the pipeline with "
+                             "precision='bf16', for other layouts with precision='fp32'")
         self.last_path = "fused" if fused else ("fused_fp32" if fused32 else "split")
         mark("l2norm", True)
         if not fused and not fused32:
@@ -308,6 +318,29 @@ class HeadPipeline:
                            want_max=True, row_max=self.scores, row_arg=self.class_ids)
         mark("similarity", False)
         return self._decode_and_nms(box_preds, mark)
+
+    def _run_bf16_twin(self, obj_embeds, box_preds, text, events) -> ops.NmsResult:
+        """``precision="auto"`` resolved to the fp16 tier, but the activations arrive as bf16 (the heads ran
+        under autocast): they are already rounded, the bf16-operand kernel multiplies them exactly and only
+        the text rows are rounded to bf16.  A second pipeline of the same shape with ``precision="bf16"``
+        takes the call; this one's result attributes point at its buffers afterwards."""
+        if self._twin is None:
+            import dataclasses
+            batch, shapes, classes, device, per_image, projections = self._ctor
+            self._twin = HeadPipeline(batch, shapes, classes, dataclasses.replace(self.cfg, precision="bf16"),
+                                      device=device, per_image_text=per_image, projections=projections)
+            if self._vocab_text is not None and not per_image:
+                self._twin.set_vocabulary(self._vocab_text)
+        twin = self._twin
+        twin.use_geometry = self.use_geometry
+        if self.use_geometry:
+            twin.scale.copy_(self.scale)
+            twin.clip_wh.copy_(self.clip_wh)
+        res = twin._run(obj_embeds, box_preds, text, events)
+        self.scores, self.class_ids, self.boxes, self.inv_norm = twin.scores, twin.class_ids, twin.boxes, twin.inv_norm
+        self.pass_mask, self.result, self.logits = twin.pass_mask, twin.result, twin.logits
+        self.last_path, self.last_single_call = twin.last_path, twin.last_single_call
+        return res
 
     # -- the bf16 step as ONE C call (ovdet_head_step): same kernels, one host round trip ----------
     def _single_call_ok(self, box_preds) -> bool:

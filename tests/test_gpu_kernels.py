@@ -1500,6 +1500,41 @@ def test_similarity_fused_bf16_activations(ov, cuda_device, classes, batched, di
     assert (logits - l32).abs().max().item() <= 2e-6
 
 
+def test_auto_precision_with_autocast_activations(ov, cuda_device):
+    """The default configuration (precision="auto" -> fp16 tier) meets bf16 conv outputs (heads under
+    autocast): the pipeline hands the call to its bf16-operand twin instead of raising; scores inside the bf16
+    bar against the oracle on the same (exactly representable) values, post-processing bit-exact, and the
+    same pipeline object keeps serving fp32 activations through the fp16 tier."""
+    from ovdet import synth
+    from ovdet.pipeline import HeadConfig, HeadPipeline
+    b, classes, s = 2, 300, 256
+    shapes = [(s // 8, s // 8), (s // 16, s // 16), (s // 32, s // 32)]
+    inp = synth.make_inputs(batch=b, image_size=s, num_classes=classes, seed=33)
+    embs16 = [e.to(torch.bfloat16) for e in inp.obj_embeds]
+    preds16 = [p.to(torch.bfloat16) for p in inp.box_preds]
+    tail = ref_port.head_tail([e.float() for e in embs16], inp.text_batched(), [p.float() for p in preds16])
+    pipe = HeadPipeline(b, shapes, classes, HeadConfig(), device=cuda_device)
+    assert pipe.cfg.precision == "fp16"
+    pipe.set_vocabulary(inp.text.to(cuda_device))
+    sizes = [(s, s)] * b
+    pipe.set_geometry(sizes, [1.0] * b)
+    res = pipe.run([e.to(cuda_device) for e in embs16], [p.to(cuda_device) for p in preds16])
+    torch.cuda.synchronize()
+    assert pipe.last_path == "fused"
+    assert_logits_close(pipe.scores, tail["scores"], "bf16")
+    fed = {"boxes": pipe.boxes.cpu(), "scores": pipe.scores.cpu(), "class_ids": pipe.class_ids.cpu().long()}
+    want = ref_port.postprocess_batch(fed, sizes, [1.0] * b)
+    for i in range(b):
+        k = int(res.count[i])
+        assert k == len(want[i]["keep"]) and k > 3
+        np.testing.assert_array_equal(res.keep[i, :k].cpu().numpy(), want[i]["keep"])
+    # fp32 activations afterwards: the fp16 tier again, inside the fp32 bar
+    tail32 = ref_port.head_tail(inp.obj_embeds, inp.text_batched(), inp.box_preds)
+    pipe.run([e.to(cuda_device) for e in inp.obj_embeds], [p.to(cuda_device) for p in inp.box_preds])
+    torch.cuda.synchronize()
+    assert (pipe.scores.cpu() - tail32["scores"]).abs().max().item() <= 1e-4
+
+
 @pytest.mark.parametrize("batch,classes", [(1, 1203), (1, 300), (2, 80)])
 def test_small_launch_class_split(ov, cuda_device, batch, classes):
     """Batch 1 at 640^2 fills 34 of the 74 CTA pairs: ovdet_head_step splits the class tiles of every
