@@ -44,6 +44,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <mutex>
+#include <type_traits>
 
 namespace ovdet {
 namespace {
@@ -546,6 +547,7 @@ sim_fused_kernel(const __grid_constant__ LevelMaps amaps, const __grid_constant_
       for (int w = pair0; w < total_work; w += pair_stride, ++lt) {
         float ss0 = 0.f, ss1 = 0.f, ss2 = 0.f, ss3 = 0.f;
         float row_scale = 1.0f;                        // F16OP: power of two applied before the fp16 rounding
+        bool unit_rows = false;                        // F16OP: every row of this warp keeps scale 1 (see below)
 #pragma unroll
         for (int kb = 0; kb < KB_T; ++kb, ++ia) {
           const uint32_t s = ia % F_A_STAGES;
@@ -566,6 +568,12 @@ sim_fused_kernel(const __grid_constant__ LevelMaps amaps, const __grid_constant_
               for (int k = 0; k < 64; k += 8) m = fmaxf(m, fabsf(ldx(k)));
               const uint32_t e = (__float_as_uint(m) >> 23) & 0xffu;
               row_scale = e >= 2u ? __uint_as_float((256u - e) << 23) : 1.0f;
+              // Every row of the warp with its sampled maximum in [2^-4, 2^5): fp16 holds such rows as they
+              // are (full 11-bit significands down to 6e-5, head-room x2000 above the sample), so the warp
+              // skips the 64 multiplies per block - they made the fp16 converter 40 % slower than the bf16
+              // one (700 vs 495 cycles per block in the trace), on the boundary's critical chain.
+              unit_rows = __all_sync(0xffffffffu, e >= 123u && e <= 131u);
+              if (unit_rows) row_scale = 1.0f;
             }
           }
           {                                              // polls for the next iteration / the closing publishes
@@ -574,16 +582,20 @@ sim_fused_kernel(const __grid_constant__ LevelMaps amaps, const __grid_constant_
             poll_landed = ptx::mbar_test_wait(as_full0 + 8u * ((ia + 1u) % F_A_STAGES), ((ia + 1u) / F_A_STAGES) & 1u);
           }
           uint32_t (&packed)[16] = held[kb % AH];
+          auto convert = [&](auto scaled) {
 #pragma unroll
-          for (int k = 0; k < 32; k += 4) {
-            float x0 = ldx(32 * half + k + 0), x1 = ldx(32 * half + k + 1);
-            float x2 = ldx(32 * half + k + 2), x3 = ldx(32 * half + k + 3);
-            if constexpr (F16OP) { x0 *= row_scale; x1 *= row_scale; x2 *= row_scale; x3 *= row_scale; }
-            ss0 = fmaf(x0, x0, ss0); ss1 = fmaf(x1, x1, ss1);
-            ss2 = fmaf(x2, x2, ss2); ss3 = fmaf(x3, x3, ss3);
-            packed[(k >> 1) + 0] = F16OP ? pack_f16x2_sat(x0, x1) : pack_bf16x2(x0, x1);
-            packed[(k >> 1) + 1] = F16OP ? pack_f16x2_sat(x2, x3) : pack_bf16x2(x2, x3);
-          }
+            for (int k = 0; k < 32; k += 4) {
+              float x0 = ldx(32 * half + k + 0), x1 = ldx(32 * half + k + 1);
+              float x2 = ldx(32 * half + k + 2), x3 = ldx(32 * half + k + 3);
+              if constexpr (decltype(scaled)::value) { x0 *= row_scale; x1 *= row_scale; x2 *= row_scale; x3 *= row_scale; }
+              ss0 = fmaf(x0, x0, ss0); ss1 = fmaf(x1, x1, ss1);
+              ss2 = fmaf(x2, x2, ss2); ss3 = fmaf(x3, x3, ss3);
+              packed[(k >> 1) + 0] = F16OP ? pack_f16x2_sat(x0, x1) : pack_bf16x2(x0, x1);
+              packed[(k >> 1) + 1] = F16OP ? pack_f16x2_sat(x2, x3) : pack_bf16x2(x2, x3);
+            }
+          };
+          if (F16OP && !unit_rows) convert(std::true_type{});
+          else convert(std::false_type{});
           __syncwarp();
           if (lane == 0) ptx::mbar_arrive(as_empty0 + 8u * s);   // staging slot may be refilled (8 arrivals)
         }
@@ -653,6 +665,7 @@ sim_fused_kernel(const __grid_constant__ LevelMaps amaps, const __grid_constant_
       float ss0 = 0.f, ss1 = 0.f, ss2 = 0.f, ss3 = 0.f;
       float st0 = 0.f, st1 = 0.f, st2 = 0.f, st3 = 0.f;
       float row_scale = 1.0f;                          // F16OP: power of two applied before the fp16 rounding
+      bool unit_rows = false;                          // F16OP: every row of this warp keeps scale 1 (as above)
       auto publish = [&](int i, const uint32_t (&regs)[32]) { publish_at(lt, i, regs, false); };
 #pragma unroll
       for (int kb = 0; kb < KB_IN; ++kb, ++ia) {
@@ -694,13 +707,16 @@ sim_fused_kernel(const __grid_constant__ LevelMaps amaps, const __grid_constant_
             for (int k = 0; k < 64; k += 8) m = fmaxf(m, fabsf(ldx(k)));
             const uint32_t e = (__float_as_uint(m) >> 23) & 0xffu;
             row_scale = e >= 2u ? __uint_as_float((256u - e) << 23) : 1.0f;
+            unit_rows = __all_sync(0xffffffffu, e >= 123u && e <= 131u);
+            if (unit_rows) row_scale = 1.0f;
           }
         }
+        auto convert = [&](auto scaled) {
 #pragma unroll
         for (int k = 0; k < 64; k += 4) {
           float x0 = ldx(k + 0), x1 = ldx(k + 1);
           float x2 = ldx(k + 2), x3 = ldx(k + 3);
-          if constexpr (F16OP) { x0 *= row_scale; x1 *= row_scale; x2 *= row_scale; x3 *= row_scale; }
+          if constexpr (decltype(scaled)::value) { x0 *= row_scale; x1 *= row_scale; x2 *= row_scale; x3 *= row_scale; }
           if (k < 32) {
             ss0 = fmaf(x0, x0, ss0); ss1 = fmaf(x1, x1, ss1);
             ss2 = fmaf(x2, x2, ss2); ss3 = fmaf(x3, x3, ss3);
@@ -718,6 +734,9 @@ sim_fused_kernel(const __grid_constant__ LevelMaps amaps, const __grid_constant_
                                                   x3 - __uint_as_float(h23 & 0xffff0000u));
           }
         }
+        };
+        if (F16OP && !unit_rows) convert(std::true_type{});
+        else convert(std::false_type{});
         __syncwarp();
         if (lane == 0) ptx::mbar_arrive(as_empty0 + 8u * s);   // staging slot may be refilled
         if constexpr (SPLIT3) {
