@@ -371,8 +371,8 @@ sim_fused_kernel(const __grid_constant__ LevelMaps amaps, const __grid_constant_
     const uint32_t issue = ptx::elect_one();
     uint32_t g = 0;                                    // N tiles produced so far
     for (int w = pair0; w < total_work; w += pair_stride) {
-      const int tile = (w / NSPLIT) * CG + (int)rank;
-      const int nt_b = (w % NSPLIT) * NT / NSPLIT, nt_e = (w % NSPLIT + 1) * NT / NSPLIT;
+      const int tile = (NSPLIT == 1 ? w : w / NSPLIT) * CG + (int)rank;
+      const int nt_b = NSPLIT == 1 ? 0 : (w % NSPLIT) * NT / NSPLIT, nt_e = NSPLIT == 1 ? NT : (w % NSPLIT + 1) * NT / NSPLIT;
       (void)nt_b; (void)nt_e;
       const TileCoord tc = decode_tile(p, tile);
       const int tb = p.text_batched ? tc.b : 0;
@@ -412,7 +412,7 @@ sim_fused_kernel(const __grid_constant__ LevelMaps amaps, const __grid_constant_
     const uint32_t smem_b_u = __shfl_sync(0xffffffffu, smem_b, 0);
     uint32_t g = 0, lt = 0;
     for (int w = pair0; w < total_work; w += pair_stride, ++lt) {
-      const int nt_b = (w % NSPLIT) * NT / NSPLIT, nt_e = (w % NSPLIT + 1) * NT / NSPLIT;
+      const int nt_b = NSPLIT == 1 ? 0 : (w % NSPLIT) * NT / NSPLIT, nt_e = NSPLIT == 1 ? NT : (w % NSPLIT + 1) * NT / NSPLIT;
       for (int nt = nt_b; nt < nt_e; ++nt, ++g) {
         const int n_size = ntile_nsize(nt);
         const uint32_t idesc = F16OP ? ptx::umma_idesc_f16_f32(F_BLOCK_M * CG, (uint32_t)n_size)
@@ -476,8 +476,8 @@ sim_fused_kernel(const __grid_constant__ LevelMaps amaps, const __grid_constant_
     const uint32_t issue = ptx::elect_one();
     uint32_t ia = 0;
     for (int w = pair0; w < total_work; w += pair_stride) {
-      const int tile = (w / NSPLIT) * CG + (int)rank;
-      const int nt_b = (w % NSPLIT) * NT / NSPLIT, nt_e = (w % NSPLIT + 1) * NT / NSPLIT;
+      const int tile = (NSPLIT == 1 ? w : w / NSPLIT) * CG + (int)rank;
+      const int nt_b = NSPLIT == 1 ? 0 : (w % NSPLIT) * NT / NSPLIT, nt_e = NSPLIT == 1 ? NT : (w % NSPLIT + 1) * NT / NSPLIT;
       (void)nt_b; (void)nt_e;
       const TileCoord tc = decode_tile(p, tile);
       const CUtensorMap* map = &amaps.m[tc.level];
@@ -501,8 +501,8 @@ sim_fused_kernel(const __grid_constant__ LevelMaps amaps, const __grid_constant_
     const uint32_t issue = ptx::elect_one();
     uint32_t lt = 0;
     for (int w = pair0; w < total_work; w += pair_stride, ++lt) {
-      const int tile = (w / NSPLIT) * CG + (int)rank;
-      const int nt_b = (w % NSPLIT) * NT / NSPLIT, nt_e = (w % NSPLIT + 1) * NT / NSPLIT;
+      const int tile = (NSPLIT == 1 ? w : w / NSPLIT) * CG + (int)rank;
+      const int nt_b = NSPLIT == 1 ? 0 : (w % NSPLIT) * NT / NSPLIT, nt_e = NSPLIT == 1 ? NT : (w % NSPLIT + 1) * NT / NSPLIT;
       (void)nt_b; (void)nt_e;
       const int next = tile + pair_stride * CG;
       if (next >= total_tiles || !(p.dbg & 1)) break;       // off unless OVDET_DBG bit 0 is set
@@ -599,8 +599,16 @@ sim_fused_kernel(const __grid_constant__ LevelMaps amaps, const __grid_constant_
           __syncwarp();
           if (lane == 0) ptx::mbar_arrive(as_empty0 + 8u * s);   // staging slot may be refilled (8 arrivals)
         }
+        {
+          // the closing publishes: all their slots are polled first (the polls' latencies overlap), then stored
+          bool freed[AH];
+          freed[0] = poll_freed;
 #pragma unroll
-        for (int kb = KB_T - AH; kb < KB_T; ++kb) publish_half(lt, kb, held[kb % AH], kb == KB_T - AH ? poll_freed : false);
+          for (int i = 1; i < AH; ++i)
+            freed[i] = ptx::mbar_test_wait(a_free0 + 8u * a_slot(lt, KB_T - AH + i), a_phase(lt, KB_T - AH + i) ^ 1u);
+#pragma unroll
+          for (int i = 0; i < AH; ++i) publish_half(lt, KB_T - AH + i, held[(KB_T - AH + i) % AH], freed[i]);
+        }
         const int slot = lt % 3;
         norm_s[(slot * 3 + half) * F_BLOCK_M + arow] = (ss0 + ss1) + (ss2 + ss3);
         if (half == 0) norm_s[(slot * 3 + 2) * F_BLOCK_M + arow] = row_scale;
@@ -655,8 +663,8 @@ sim_fused_kernel(const __grid_constant__ LevelMaps amaps, const __grid_constant_
       if (warp == 4) OVDET_TR(1, 14);
     };
     for (int w = pair0; w < total_work; w += pair_stride, ++lt) {
-      const int tile = (w / NSPLIT) * CG + (int)rank;
-      const int nt_b = (w % NSPLIT) * NT / NSPLIT, nt_e = (w % NSPLIT + 1) * NT / NSPLIT;
+      const int tile = (NSPLIT == 1 ? w : w / NSPLIT) * CG + (int)rank;
+      const int nt_b = NSPLIT == 1 ? 0 : (w % NSPLIT) * NT / NSPLIT, nt_e = NSPLIT == 1 ? NT : (w % NSPLIT + 1) * NT / NSPLIT;
       (void)nt_b; (void)nt_e;
       const TileCoord tc = decode_tile(p, tile);
       // the sum of squares in the association of the eight-warp converter above (one partial sum per
@@ -748,8 +756,13 @@ sim_fused_kernel(const __grid_constant__ LevelMaps amaps, const __grid_constant_
         }
       }
       if constexpr (AHEAD2) {                          // the tile's last blocks
+        bool freed[AH];                                // all closing slots polled first: the latencies overlap
+        freed[0] = poll_freed;
 #pragma unroll
-        for (int kb = KB_IN - AH; kb < KB_IN; ++kb) publish_at(lt, kb, held[kb % AH], kb == KB_IN - AH ? poll_freed : false);
+        for (int i = 1; i < AH; ++i)
+          freed[i] = ptx::mbar_test_wait(a_free0 + 8u * a_slot(lt, KB_IN - AH + i), a_phase(lt, KB_IN - AH + i) ^ 1u);
+#pragma unroll
+        for (int i = 0; i < AH; ++i) publish_at(lt, KB_IN - AH + i, held[(KB_IN - AH + i) % AH], freed[i]);
       }
       const float ssq = ((ss0 + ss1) + (ss2 + ss3)) + ((st0 + st1) + (st2 + st3));
       float inv = 1.0f / fmaxf(sqrtf(ssq), 1e-12f);
@@ -791,8 +804,8 @@ sim_fused_kernel(const __grid_constant__ LevelMaps amaps, const __grid_constant_
     };
     uint32_t acc_it = 0, lt = 0;
     for (int w = pair0; w < total_work; w += pair_stride, ++lt) {
-      const int tile = (w / NSPLIT) * CG + (int)rank;
-      const int nt_b = (w % NSPLIT) * NT / NSPLIT, nt_e = (w % NSPLIT + 1) * NT / NSPLIT;
+      const int tile = (NSPLIT == 1 ? w : w / NSPLIT) * CG + (int)rank;
+      const int nt_b = NSPLIT == 1 ? 0 : (w % NSPLIT) * NT / NSPLIT, nt_e = NSPLIT == 1 ? NT : (w % NSPLIT + 1) * NT / NSPLIT;
       (void)nt_b; (void)nt_e;
       const TileCoord tc = decode_tile(p, tile);
       const int r_in_tile = lg * 32 + lane;
