@@ -142,3 +142,31 @@ def test_head_step_args_mirror(handle):
     from ovdet import _cabi
     assert ctypes.sizeof(_cabi.HeadStepArgs) == handle.ovdet_head_step_args_size()
     assert handle.ovdet_head_step(None, None) == -1
+
+
+def test_precision_auto_rule():
+    """What precision="auto" resolves to (pipeline.resolve_precision): the fp16 operand tier for the
+    reference's embed_dim 512 - for any class count and any level size (odd levels are re-pitched) - the
+    three-pass recipe for other dims and for fp32 logits, bf16 for the projected mode."""
+    from ovdet.pipeline import HeadConfig, resolve_precision
+    shapes640, shapes416 = [(80, 80), (40, 40), (20, 20)], [(52, 52), (26, 26), (13, 13)]
+    assert resolve_precision(HeadConfig(), shapes640, 1203) == "fp16"
+    assert resolve_precision(HeadConfig(), shapes640, 80) == "fp16"
+    assert resolve_precision(HeadConfig(), shapes416, 80) == "fp16"
+    assert resolve_precision(HeadConfig(embed_dim=256), shapes640, 80) == "fp32"
+    assert resolve_precision(HeadConfig(logits_dtype="fp32"), shapes640, 1203) == "fp32"
+    assert resolve_precision(HeadConfig(fused=False), shapes640, 1203) == "fp32"
+    assert resolve_precision(HeadConfig(), shapes640, 1203, projected=True) == "bf16"
+    for explicit in ("bf16", "fp16", "fp32"):
+        assert resolve_precision(HeadConfig(precision=explicit), shapes640, 1203) == explicit
+
+
+def test_repitch_rows_validates_arguments(handle):
+    """ovdet_repitch_rows without a GPU: argument errors come before the device check."""
+    f = handle.ovdet_repitch_rows
+    assert f(None, 4, 3, 3, None, 4, 4, None) == -1                 # null pointers
+    buf = (ctypes.c_float * 16)()
+    p = ctypes.cast(buf, ctypes.c_void_p)
+    assert f(p, 4, 5, 3, p, 8, 4, None) == -1                       # source pitch shorter than the row
+    assert f(p, 4, 3, 3, p, 2, 4, None) == -1                       # destination pitch shorter than the row
+    assert f(p, 4, 3, 3, p, 4, 3, None) == -1                       # element size must be 2 or 4
