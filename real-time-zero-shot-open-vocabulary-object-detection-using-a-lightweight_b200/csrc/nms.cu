@@ -144,30 +144,60 @@ __device__ __forceinline__ float box_area(const float4 b) {
 // quotient is below the midpoint m between thr and the next float above it (or equal to it when
 // the tie rounds down to thr, i.e. thr's mantissa is even).  m has a 25-bit mantissa and denom a
 // 24-bit one, so denom * m is exact in double and the comparison is exact.
+//
+// The double arithmetic is itself slow on this GPU (a warp-wide FP64 multiply or conversion issues at a small
+// fraction of the fp32 rate: with it on every pair the 171-candidate mask of a batch-1 call took 17 k cycles),
+// so it only DECIDES THE CLOSE CALLS: an approximate quotient a = inter * rcp(denom) (relative error < 2^-21)
+// settles every pair with a < thr (1 - 2^-20) (certainly kept) or a > thr (1 + 2^-20) (certainly suppressed);
+// what lies between - about one pair in a million - takes the exact test below.  Same decisions, bit for bit.
 struct IouTest {
   double mid;        // (thr + nextafter(thr, +inf)) / 2
   int tie_down;      // a quotient exactly at `mid` rounds to thr
   int exact_ok;      // thr finite and >= 0: the double test applies
   float thr;
+  float lo, hi;      // below lo: iou <= thr for certain; above hi: iou > thr for certain (lo > hi: filter off)
 };
 
-// true when `b` must be dropped because of the already kept `a`: NOT (iou <= thr)
-__device__ __forceinline__ bool suppresses(const float4 a, const float area_a, const float4 b,
-                                           const float area_b, const IouTest& t) {
-  const float ix1 = fmaxf(a.x, b.x), iy1 = fmaxf(a.y, b.y);
-  const float ix2 = fminf(a.z, b.z), iy2 = fminf(a.w, b.w);
-  const float iw = fmaxf(0.f, __fsub_rn(ix2, ix1));
-  const float ih = fmaxf(0.f, __fsub_rn(iy2, iy1));
-  const float inter = __fmul_rn(iw, ih);
-  const float uni = __fsub_rn(__fadd_rn(area_a, area_b), inter);
-  const float denom = __fadd_rn(uni, 1e-7f);
-  if (t.exact_ok && denom > 0.f && inter <= 3.0e38f) {          // the common case (NaN fails both tests)
+// the close calls and the out-of-range inputs: exact, out of line (about one pair in a million gets here)
+__device__ __noinline__ bool suppresses_exact(const float inter, const float denom, const IouTest& t) {
+  if (t.exact_ok && denom > 0.f && inter <= 3.0e38f) {          // (NaN fails both tests)
     const double lhs = (double)inter, rhs = __dmul_rn((double)denom, t.mid);
     const bool keep = lhs < rhs || (t.tie_down && lhs == rhs);
     return !keep;
   }
   const float iou = __fdiv_rn(inter, denom);
   return !(iou <= t.thr);
+}
+
+// Branch-free part of the test: intersection and denominator as numpy forms them, then the approximate
+// quotient q = inter * rcp.approx(denom) (|relative error| < 2^-21).  `sure_sup`: q above the upper bound -
+// suppressed for certain; `unsure`: q between the bounds, not a number, or a denominator beyond the
+// approximation's range - the exact test decides.  (Non-positive denominators need no guard: the approximate
+// quotient then has the sign / infinity the IEEE quotient has, and the bounds are positive.)
+__device__ __forceinline__ void iou_classify(const float4 a, const float area_a, const float4 b, const float area_b,
+                                             const IouTest& t, float& inter, float& denom, bool& sure_sup, bool& unsure) {
+  const float ix1 = fmaxf(a.x, b.x), iy1 = fmaxf(a.y, b.y);
+  const float ix2 = fminf(a.z, b.z), iy2 = fminf(a.w, b.w);
+  const float iw = fmaxf(0.f, __fsub_rn(ix2, ix1));
+  const float ih = fmaxf(0.f, __fsub_rn(iy2, iy1));
+  inter = __fmul_rn(iw, ih);
+  const float uni = __fsub_rn(__fadd_rn(area_a, area_b), inter);
+  denom = __fadd_rn(uni, 1e-7f);
+  float r;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(denom));
+  const float q = __fmul_rn(inter, r);
+  sure_sup = q > t.hi;
+  unsure = !((sure_sup || q < t.lo) && denom < 1.0e30f);
+}
+
+// true when `b` must be dropped because of the already kept `a`: NOT (iou <= thr)
+__device__ __forceinline__ bool suppresses(const float4 a, const float area_a, const float4 b,
+                                           const float area_b, const IouTest& t) {
+  float inter, denom;
+  bool sure_sup, unsure;
+  iou_classify(a, area_a, b, area_b, t, inter, denom, sure_sup, unsure);
+  if (!unsure) return sure_sup;
+  return suppresses_exact(inter, denom, t);
 }
 
 __global__ void __launch_bounds__(NMS_THREADS)
@@ -187,7 +217,16 @@ nms_batched_kernel(const NmsParams p) {
   __shared__ uint32_t s_removed[CHUNK_WORDS];
   __shared__ int s_count, s_kept_total, s_kept_chunk, s_carry;
 
+#ifdef OVDET_NMS_TRACE
+  // timing build only: thread 0 drops the low 32 bits of the SM clock at the phase boundaries into the unused
+  // tail of out_keep (tools/batch1_breakdown.py reads them back)
+#define NMS_TR(i) do { if (threadIdx.x == 0 && p.out_keep && p.max_det >= 300) p.out_keep[(size_t)blockIdx.x * p.max_det + 280 + (i)] = (int)clock64(); } while (0)
+#else
+#define NMS_TR(i) do { } while (0)
+#endif
+  NMS_TR(0);
   if (p.pdl) cudaGridDependencySynchronize();   // the decode kernel (and, through it, the similarity kernel) is done
+  NMS_TR(1);
   const int b = blockIdx.x;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int A = p.anchors, W = p.words;
@@ -262,6 +301,7 @@ nms_batched_kernel(const NmsParams p) {
       if (w_lo + i < W) { s_prefix[w_lo + i] = run; run += __popc(mask_word(w_lo + i)); }
     resident = N <= SORT_CAP && (p.topk == 0 || p.topk >= N);
     __syncthreads();
+    NMS_TR(2);
   } else {
     N = -1;
   }
@@ -284,19 +324,30 @@ nms_batched_kernel(const NmsParams p) {
       }
     }
     __syncthreads();
+    NMS_TR(3);
     // ---- 2r. sort in shared memory -------------------------------------------------------------
     if (N <= CHUNK) {
       // rank sort: thread i counts the keys larger than its own (keys are pairwise distinct, so
       // the ranks are a permutation): one pass of broadcast reads and one barrier instead of
       // the 36 barrier-separated steps a 256-key bitonic network takes.
+      // every thread takes a slice of the comparisons of one key (512 / N threads per key, ranks summed
+      // with shared-memory atomics): at N = 171 three threads per key instead of 171 busy and 341 idle
+      const int per_key = N <= NMS_THREADS / 4 ? 4 : (N <= NMS_THREADS / 2 ? 2 : 1);
+      const int key_i = tid / per_key, part = tid - key_i * per_key;
       unsigned long long mine = 0ull;
-      int rank = 0;
-      if (tid < N) {
-        mine = s_big[tid];
-        for (int j = 0; j < N; ++j) rank += s_big[j] > mine;
+      if (tid < N) s_scan[tid] = 0;
+      __syncthreads();
+      if (key_i < N) {
+        mine = s_big[key_i];
+        const int len = (N + per_key - 1) / per_key;
+        const int j_end = min(N, (part + 1) * len);
+        int rank = 0;
+        for (int j = part * len; j < j_end; ++j) rank += s_big[j] > mine;
+        if (per_key > 1) atomicAdd(&s_scan[key_i], rank);
+        else s_scan[key_i] = rank;
       }
       __syncthreads();
-      if (tid < N) s_big[rank] = mine;
+      if (key_i < N && part == 0) s_big[s_scan[key_i]] = mine;
       __syncthreads();
     } else {
       int P = 32;
@@ -370,6 +421,7 @@ nms_batched_kernel(const NmsParams p) {
   }
   }
 
+  NMS_TR(4);
   // ---- 4. greedy NMS over the sorted candidates ----------------------------------------------
   const float scale = p.scale ? p.scale[b] : 1.0f;
   const bool do_scale = p.scale != nullptr;
@@ -383,6 +435,14 @@ nms_batched_kernel(const NmsParams p) {
     const float up = __uint_as_float(__float_as_uint(p.iou_thr) + 1u);      // next float above (thr >= 0)
     thr.mid = 0.5 * ((double)p.iou_thr + (double)up);
     thr.tie_down = (__float_as_uint(p.iou_thr) & 1u) == 0u;
+    // the filter's certainty bounds (rounded outwards); off for thresholds too small to bracket
+    if (thr.exact_ok && p.iou_thr >= 1.0e-30f) {
+      thr.lo = __fmul_rd(p.iou_thr, 1.0f - 9.5367431640625e-07f);
+      thr.hi = __fmul_ru(p.iou_thr, 1.0f + 9.5367431640625e-07f);
+    } else {
+      thr.lo = -INFINITY;
+      thr.hi = INFINITY;
+    }
   }
   const bool aware = p.class_aware && classes != nullptr;
   uint32_t* mask = reinterpret_cast<uint32_t*>(s_big);           // [CHUNK][CHUNK_WORDS]
@@ -460,34 +520,62 @@ nms_batched_kernel(const NmsParams p) {
       if (tid < n && s_hit[tid]) dead = true;
       __syncthreads();
     }
+    NMS_TR(5);
     const uint32_t dead_bits = __ballot_sync(0xffffffffu, dead);
     if (lane == 0) s_removed[warp] = dead_bits;
     __syncthreads();
-    // 4c. suppression bitmask, 32 x 32 tiles on or above the diagonal, one ballot per row
+    // 4c. suppression bitmask, 32 x 32 tiles on or above the diagonal.  A lane owns one ROW i of the tile
+    // and walks the tile's 32 columns j - every lane reads the same s_box[j] (a broadcast) - setting bit j
+    // of its own word: 32 independent IoU tests per thread, no ballot and no cross-lane traffic.  (The first
+    // version gave a lane one column and took a warp ballot per row: a 32-deep chain of ballots and selects
+    // that ran at an IPC of 0.16 - 18.5 k cycles of the kernel's 36 k at batch 1.)
     const int nblk = (n + 31) >> 5;
     const int ntiles = nblk * (nblk + 1) / 2;
-    for (int t = warp; t < ntiles; t += NMS_WARPS) {
+    // a task = 16 columns of a tile (two tasks per tile, written as the two halves of the row's word): with 21
+    // tiles on 16 warps whole-tile tasks left 11 warps waiting for the 5 that had two
+    for (int task = warp; task < 2 * ntiles; task += NMS_WARPS) {
+      const int t = task >> 1, h = task & 1;
       // tile index -> (row block rb <= column block cb)
       int cb = 0;
       while ((cb + 1) * (cb + 2) / 2 <= t) ++cb;
       const int rb = t - cb * (cb + 1) / 2;
-      const int j = (cb << 5) + lane;
-      const float4 bj = s_box[j];
-      const float aj = s_area[j];
-      const int cj = s_cls[j];
-      uint32_t my_word = 0;
-#pragma unroll 4
-      for (int r = 0; r < 32; ++r) {
-        const int i = (rb << 5) + r;
-        const float4 bi = s_box[i];
-        bool sup = (j > i) && suppresses(bi, s_area[i], bj, aj, thr);
-        if (aware) sup = sup && (s_cls[i] == cj);
-        const uint32_t word = __ballot_sync(0xffffffffu, sup);
-        if (lane == r) my_word = word;
+      const int i = (rb << 5) + lane;
+      const float4 bi = s_box[i];
+      const float ai = s_area[i];
+      const int ci = s_cls[i];
+      uint32_t my_word = 0, unsure_word = 0, same_cls = 0xffffu;
+#pragma unroll 8
+      for (int c = 0; c < 16; ++c) {
+        const int j = (cb << 5) + 16 * h + c;
+        float inter, denom;
+        bool sure_sup, unsure;
+        iou_classify(bi, ai, s_box[j], s_area[j], thr, inter, denom, sure_sup, unsure);
+        my_word |= (sure_sup ? 1u : 0u) << c;
+        unsure_word |= (unsure ? 1u : 0u) << c;
       }
-      mask[((rb << 5) + lane) * CHUNK_WORDS + cb] = my_word;
+      if (aware) {
+        same_cls = 0u;
+#pragma unroll 8
+        for (int c = 0; c < 16; ++c) same_cls |= (s_cls[(cb << 5) + 16 * h + c] == ci ? 1u : 0u) << c;
+      }
+      // only later candidates (j > i) of the same class (class-aware) can be suppressed by i
+      const uint32_t later32 = rb == cb ? (lane == 31 ? 0u : (0xffffffffu << (lane + 1))) : 0xffffffffu;
+      const uint32_t valid = (later32 >> (16 * h)) & 0xffffu & same_cls;
+      my_word &= valid & ~unsure_word;
+      unsure_word &= valid;
+      while (unsure_word) {                                    // the close calls: exact test, about one pair in 10^6
+        const int c = __ffs(unsure_word) - 1;
+        unsure_word &= unsure_word - 1;
+        const int j = (cb << 5) + 16 * h + c;
+        float inter, denom;
+        bool sure_sup, unsure;
+        iou_classify(bi, ai, s_box[j], s_area[j], thr, inter, denom, sure_sup, unsure);
+        if (suppresses_exact(inter, denom, thr)) my_word |= 1u << c;
+      }
+      reinterpret_cast<unsigned short*>(mask)[(i * CHUNK_WORDS + cb) * 2 + h] = (unsigned short)my_word;
     }
     __syncthreads();
+    NMS_TR(6);
     // 4d. resolve: warp 0, one 32-candidate block per step.  The 32 diagonal words are loaded up
     // front (broadcast reads, independent of the greedy chain), so the chain itself is 32
     // register-only steps; the rows of the kept candidates are then OR-ed into the later blocks
@@ -499,16 +587,22 @@ nms_batched_kernel(const NmsParams p) {
         const uint32_t cur = __shfl_sync(0xffffffffu, removed, wb);
         uint32_t alive = ~cur;
         const uint32_t* rows = mask + (wb << 5) * CHUNK_WORDS;
-        uint32_t d[32];
+        // every load of the block is issued before the chain starts: the diagonal words (broadcast) and
+        // this lane's word of each of the 32 rows, whose use is then a register select
+        uint32_t d[32], mine_w[32];
+        const int my_col = (lane < CHUNK_WORDS && lane > wb) ? lane : wb;
 #pragma unroll
-        for (int r = 0; r < 32; ++r) d[r] = rows[r * CHUNK_WORDS + wb];
+        for (int r = 0; r < 32; ++r) {
+          d[r] = rows[r * CHUNK_WORDS + wb];
+          mine_w[r] = rows[r * CHUNK_WORDS + my_col];
+        }
 #pragma unroll
         for (int r = 0; r < 32; ++r)
           if ((alive >> r) & 1u) alive &= ~d[r];
         if (lane < CHUNK_WORDS && lane > wb) {
 #pragma unroll
           for (int r = 0; r < 32; ++r)
-            if ((alive >> r) & 1u) removed |= rows[r * CHUNK_WORDS + lane];
+            if ((alive >> r) & 1u) removed |= mine_w[r];
         }
         if ((alive >> lane) & 1u)
           s_kept_pos[kept_chunk + __popc(alive & ((1u << lane) - 1u))] = (wb << 5) + lane;
@@ -517,6 +611,7 @@ nms_batched_kernel(const NmsParams p) {
       if (lane == 0) s_kept_chunk = kept_chunk;
     }
     __syncthreads();
+    NMS_TR(7);
     // 4e. emit the survivors of this chunk (kept order == score order)
     const int kept_chunk = s_kept_chunk;
     for (int e = tid; e < kept_chunk; e += NMS_THREADS) {
@@ -541,6 +636,7 @@ nms_batched_kernel(const NmsParams p) {
     if (tid == 0) s_kept_total = kept_before + kept_chunk;
     __syncthreads();
   }
+  NMS_TR(8);
   if (tid == 0) p.out_count[b] = min(s_kept_total, p.max_det);
 }
 
