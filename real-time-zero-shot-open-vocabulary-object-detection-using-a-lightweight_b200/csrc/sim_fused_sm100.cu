@@ -552,7 +552,10 @@ sim_fused_kernel(const __grid_constant__ LevelMaps amaps, const __grid_constant_
         for (int kb = 0; kb < KB_T; ++kb, ++ia) {
           const uint32_t s = ia % F_A_STAGES;
           if (warp == 4) OVDET_TR(1, 10);
-          if (kb >= AH) publish_half(lt, kb - AH, held[kb % AH], poll_freed);
+          // (the CTA's FIRST tile publishes every block as soon as it is converted: its slots have never
+          // been used, and holding blocks back would only delay the first MMA - at batch 1, where a CTA pair
+          // has one tile, by the conversion time of four blocks)
+          if (lt > 0 && kb >= AH) publish_half(lt, kb - AH, held[kb % AH], poll_freed);
           if (!poll_landed) ptx::mbar_wait_lazy(as_full0 + 8u * s, (ia / F_A_STAGES) & 1u, lazy_ns >> 1);
           if (warp == 4) OVDET_TR(1, 11);
           const float* col = a_stage_ptr + s * (F_A_STAGE_BYTES / 4) + arow;
@@ -598,8 +601,9 @@ sim_fused_kernel(const __grid_constant__ LevelMaps amaps, const __grid_constant_
           else convert(std::false_type{});
           __syncwarp();
           if (lane == 0) ptx::mbar_arrive(as_empty0 + 8u * s);   // staging slot may be refilled (8 arrivals)
+          if (lt == 0) publish_half(lt, kb, held[kb % AH], true);
         }
-        {
+        if (lt > 0) {
           // the closing publishes: all their slots are polled first (the polls' latencies overlap), then stored
           bool freed[AH];
           freed[0] = poll_freed;
@@ -685,7 +689,7 @@ sim_fused_kernel(const __grid_constant__ LevelMaps amaps, const __grid_constant_
           // on a completed barrier still takes 150-180 cycles in this kernel (tools/trace_fused.py), which
           // in the boundary's serial chain was a third of every block's time.  A poll that came back true
           // is final; one that came back false is followed by the real wait.
-          if (kb >= AH) publish_at(lt, kb - AH, held[kb % AH], poll_freed);
+          if (lt > 0 && kb >= AH) publish_at(lt, kb - AH, held[kb % AH], poll_freed);   // (first tile: see below)
           if (!poll_landed) ptx::mbar_wait_lazy(as_full0 + 8u * s, (ia / F_A_STAGES) & 1u, lazy_ns >> 1);
         } else {
           ptx::mbar_wait_lazy(as_full0 + 8u * s, (ia / F_A_STAGES) & 1u, lazy_ns >> 1);
@@ -753,9 +757,11 @@ sim_fused_kernel(const __grid_constant__ LevelMaps amaps, const __grid_constant_
           publish(3 * kb + 2, packed_lo);
         } else if constexpr (!AHEAD2) {
           publish(kb, packed);
+        } else if (lt == 0) {
+          publish_at(lt, kb, packed, true);            // the CTA's first tile: its slots have never been used
         }
       }
-      if constexpr (AHEAD2) {                          // the tile's last blocks
+      if (AHEAD2 && lt > 0) {                          // the tile's last blocks
         bool freed[AH];                                // all closing slots polled first: the latencies overlap
         freed[0] = poll_freed;
 #pragma unroll

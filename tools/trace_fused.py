@@ -29,6 +29,7 @@ def main():
     ap.add_argument("--classes", type=int, default=1203)
     ap.add_argument("--lib", default="libovdet_trace.so")
     ap.add_argument("--out", default=None)
+    ap.add_argument("--single-call", action="store_true", help="trace the product call (ovdet_head_step: class split at batch 1)")
     args = ap.parse_args()
     import torch
     import ovdet
@@ -51,9 +52,16 @@ def main():
     trace.zero_()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ev = {}
-    pipe.run(inp.obj_embeds, inp.box_preds, events=ev)
-    torch.cuda.synchronize()
-    ms = ev["similarity"][0].elapsed_time(ev["similarity"][1])
+    if args.single_call:
+        ev0.record()
+        pipe.run(inp.obj_embeds, inp.box_preds)
+        ev1.record()
+        torch.cuda.synchronize()
+        ms = ev0.elapsed_time(ev1)
+    else:
+        pipe.run(inp.obj_embeds, inp.box_preds, events=ev)
+        torch.cuda.synchronize()
+        ms = ev["similarity"][0].elapsed_time(ev["similarity"][1])
     t = trace.cpu().numpy().astype("uint64").reshape(roles, cap)
     out = {"similarity_ms": ms, "roles": {}}
     mask = (1 << 48) - 1
@@ -63,6 +71,12 @@ def main():
         tags = (row[:n] >> 48).astype("int64")
         clk = (row[:n] & mask).astype("int64")
         out["roles"][r] = (tags, clk)
+    if args.out:
+        dump = {"similarity_ms": ms,
+                "roles": {str(r): {"tags": out["roles"][r][0][:6000].tolist(), "clk": out["roles"][r][1][:6000].tolist()}
+                          for r in range(roles)}}
+        with open(args.out, "w") as f:
+            json.dump(dump, f)
     # ---- MMA warp: split the launch into N tiles (tag 1 ... tag 5) ---------------------------------
     tags, clk = out["roles"][0]
     t_start, t_end = int(clk[0]), int(clk[-1])
@@ -103,7 +117,7 @@ def main():
     print(f"  waiting t_empty {wait_tempty / total:6.1%}   a_ready {wait_aready / total:6.1%}   "
           f"b_full {wait_b / total:6.1%}   rest (issue + commit) {1 - (wait_tempty + wait_aready + wait_b) / total:6.1%}")
     import numpy as np
-    ft = np.array(first_tiles[2:-1])
+    ft = np.array(first_tiles[2:-1] if len(first_tiles) > 4 else first_tiles)
     print("  first N tile of an anchor tile: median wait t_empty / a_ready / b_full / duration =",
           np.median(ft, axis=0).tolist())
     pn = np.array(per_ntile)
