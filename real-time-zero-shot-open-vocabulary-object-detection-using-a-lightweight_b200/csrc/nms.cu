@@ -268,6 +268,13 @@ nms_batched_kernel(const NmsParams p) {
   };
   int N, M;
   bool resident = false;
+  // one mask word per thread (anchors <= 16384): the scores of the word's first four candidates are loaded
+  // BEFORE the block-wide scan, so that their L2 round trip overlaps it (the key build used to walk the set
+  // bits with one dependent load each: ~3 k cycles at batch 1 for clumps of three candidates per word)
+  float early_score[4] = {0.f, 0.f, 0.f, 0.f};
+  int early_anchor[4] = {0, 0, 0, 0};
+  int early_n = 0;
+  uint32_t early_rest = 0;
   const unsigned long long* sorted_keys = keys;     // where phase 4 reads the sorted keys from
 
   if (W <= FAST_WORDS) {
@@ -277,6 +284,18 @@ nms_batched_kernel(const NmsParams p) {
     int local = 0;
     for (int i = 0; i < per; ++i)
       if (w_lo + i < W) local += __popc(mask_word(w_lo + i));
+    if (per == 1 && tid < W) {
+      early_rest = mask_word(tid);
+#pragma unroll
+      for (int q = 0; q < 4; ++q)
+        if (early_rest) {
+          const int a = (tid << 5) + __ffs(early_rest) - 1;
+          early_rest &= early_rest - 1;
+          early_anchor[q] = a;
+          early_score[q] = scores[a];
+          early_n = q + 1;
+        }
+    }
     int incl = local;                                              // inclusive scan over the block
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
@@ -316,6 +335,13 @@ nms_batched_kernel(const NmsParams p) {
     for (int w = tid; w < W; w += NMS_THREADS) {
       uint32_t bits = mask_word(w);
       int slot = s_prefix[w];
+      if (W <= NMS_THREADS) {                      // (== the `per == 1` case above: w == tid, one word per thread)
+#pragma unroll
+        for (int q = 0; q < 4; ++q)
+          if (q < early_n)
+            s_big[slot++] = ((unsigned long long)float_to_ordered(early_score[q]) << 32) | (unsigned)early_anchor[q];
+        bits = early_rest;
+      }
       while (bits) {
         const int l = __ffs(bits) - 1;
         bits &= bits - 1;
